@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py - sequences/sec of one biGRU train step on N B200s (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+  N>1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N
+
+A "step" is the body of the reference training loop (biGRU_model.py:198-210): zero_grad -> forward ->
+CrossEntropy loss -> backward -> [gradient all-reduce] -> clip_grad_norm_(50) -> Adam, on the workload
+BASELINE.json quotes the metric on: per-GPU batch 512, seq_len 128, 64 features, hidden 256, 2 layers,
+bidirectional, 3 classes (configs[1]); weak scaling (per-GPU batch fixed, global batch = 512*N).
+Rank 0 prints ONE JSON line.  `--impl reference` times the reference's CPU implementation of the same
+step (the oracle port: torch.nn.GRU on the host cores, as biGRU_model.py:54-56/:102 call it).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sequences/sec (train step) biGRU h=256 seq=128 feat=64"
+WORK = dict(per_gpu_batch=512, seq_len=128, n_features=64, hidden=256, layers=2, classes=3)
+
+
+def flops_train_per_seq(T, F, H, L, C, D=2):
+    """fwd = 12*T*H*sum_l(I_l+H) + 2*3H*C (bidirectional), train = 3x fwd."""
+    fwd = 0
+    for l in range(L):
+        I = F if l == 0 else D * H
+        fwd += 6 * D * T * H * (I + H)
+    fwd += 2 * 3 * H * C
+    return 3 * fwd
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic(B, T, F, C, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, T, F, generator=g), torch.randint(0, C, (B,), generator=g)
+
+
+def time_cpu_reference(steps, warmup, budget_s=150.0, batch=None):
+    """The reference CPU path (oracle port) on the host cores, bounded sample of the same workload."""
+    import torch
+    import torch.nn as nn
+    from oracle.bigru_oracle import OracleBiGRU, train_step
+    W = WORK
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = OracleBiGRU(W["hidden"], W["n_features"], W["classes"], W["layers"], 50, 0.0, False, True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    loss_fn = nn.CrossEntropyLoss()
+    model.train()
+    B = batch or W["per_gpu_batch"]
+    x, t = synthetic(B, W["seq_len"], W["n_features"], W["classes"], 1234)
+    t0 = time.perf_counter()
+    train_step(model, opt, loss_fn, x, t)                       # first warm-up step, also sizes the sample
+    first = time.perf_counter() - t0
+    total = steps + max(warmup - 1, 0)
+    if batch is None and first * total > budget_s:
+        B = max(32, int(B * budget_s / (first * total)) // 32 * 32)
+        x, t = x[:B].contiguous(), t[:B].contiguous()
+    for _ in range(max(warmup - 1, 0)):
+        train_step(model, opt, loss_fn, x, t)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        train_step(model, opt, loss_fn, x, t)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": B / dt, "unit": "sequences/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} train steps of batch {B} x seq {W['seq_len']} x feat {W['n_features']} "
+                      f"(hidden {W['hidden']}, {W['layers']} layers, bidirectional) through oracle/bigru_oracle.py "
+                      f"(torch.nn.GRU CPU, {torch.get_num_threads()} threads)",
+            "ms_per_step": dt * 1e3, "batch": B}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = time_cpu_reference(args.steps, args.warmup)
+    W = WORK
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "sequences/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus, "fp32", cpu=True, batch=r["batch"]),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, precision, cpu=False, batch=None):
+    W = WORK
+    b = batch or W["per_gpu_batch"]
+    return {"workload": "BASELINE.json configs[1]: biGRU train step, batch 512/GPU x seq 128 x feat 64, hidden 256, "
+                        "2 layers, bidirectional, 3-class cross-entropy, clip 50, Adam 1e-3",
+            "global_batch": b * (1 if cpu else n_gpus), "per_gpu_batch": b, "seq_len": W["seq_len"],
+            "n_features": W["n_features"], "hidden": W["hidden"], "layers": W["layers"], "bidirectional": True,
+            "classes": W["classes"], "loss": "CrossEntropyLoss", "optimizer": "Adam(lr=1e-3)+clip_grad_norm_(50)",
+            "parallelism": "cpu" if cpu else f"dp{n_gpus}", "precision": precision,
+            "l2": "8 rotating input batches + >1 GB of activation traffic per step (>> 126 MB L2)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("BIGRU_B200_PRECISION", "auto"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.nn as nn
+    import torch.distributed as dist
+    import financial_market_data_analysis_b200 as pkg
+    from financial_market_data_analysis_b200.parallel import max_over_ranks
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py: --gpus N>1 must be launched with torch.distributed.run --nproc-per-node N")
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = pkg._lib.load()
+    C_ = pkg._lib.C
+
+    precision = args.precision
+    if precision == "auto":
+        h = C_.c_void_p()
+        ok = lib.bigru_plan_create(WORK["per_gpu_batch"], WORK["seq_len"], WORK["n_features"], WORK["hidden"],
+                                   WORK["layers"], WORK["classes"], 1, pkg._lib.PREC_BF16, C_.byref(h)) == 0
+        if ok:
+            lib.bigru_plan_destroy(h)
+        precision = "bf16" if ok else "fp32"
+
+    W = WORK
+    B, T, F, H, L, C = W["per_gpu_batch"], W["seq_len"], W["n_features"], W["hidden"], W["layers"], W["classes"]
+    torch.manual_seed(0)                                    # same replica on every rank
+    model = pkg.BiGRU(H, F, C, L, 50, 0.0, False, True, precision=precision).cuda()
+    model.add_loss_fn(nn.CrossEntropyLoss())
+    model.add_optimizer(torch.optim.Adam(model.parameters(), lr=1e-3))
+    model.add_device(dev)
+    model.train()
+    if world > 1:
+        model.enable_data_parallel()
+
+    NBUF = 8
+    host = [synthetic(B, T, F, C, 1234 + rank + 97 * i) for i in range(NBUF)]
+    host = [(x.pin_memory(), t.pin_memory()) for x, t in host]
+    resident = [(x.to(dev), t.to(dev)) for x, t in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = lib.bigru_launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lib.bigru_launch_count() - n0
+        if world > 1:
+            ms = max_over_ranks(ms, dev)
+        return ms, launches
+
+    # ---- device-resident throughput (`value`) --------------------------------------------------------
+    def step_resident(i):
+        x, t = resident[i % NBUF]
+        model.train_step(x, t)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ms, launches = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms / args.steps
+    value = B * world / (ms_step * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (`e2e`) ---------------------------------
+    last_loss = [0.0]
+
+    def step_e2e(i):
+        x, t = host[i % NBUF]                               # pinned host tensors: H2D inside train_step
+        loss, _ = model.train_step(x, t)
+        last_loss[0] = float(loss)                          # D2H read of the step's loss
+
+    ms_e, _ = timed(step_e2e, args.steps, args.warmup)
+    e2e_value = B * world / (ms_e / args.steps * 1e-3)
+    h2d = host[0][0].numel() * 4 + host[0][1].numel() * 8
+    e2e = {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+           "ms_per_step": ms_e / args.steps, "loss": last_loss[0]}
+
+    # ---- live roofline of the dominant kernel (separate pass with per-launch events) ------------------
+    roofline = None
+    if rank == 0:
+        lib.bigru_prof_enable(1)
+        psteps = 3
+        for i in range(psteps):
+            step_resident(i)
+        torch.cuda.synchronize()
+        rows = []
+        for k in range(lib.bigru_prof_classes()):
+            a, n, fl, by = C_.c_double(), C_.c_longlong(), C_.c_double(), C_.c_double()
+            lib.bigru_prof_report(k, C_.byref(a), C_.byref(n), C_.byref(fl), C_.byref(by))
+            if n.value:
+                rows.append(dict(name=lib.bigru_prof_class_name(k).decode(), ms=a.value / psteps,
+                                 launches=n.value // psteps, flops=fl.value / psteps, bytes=by.value / psteps))
+        lib.bigru_prof_enable(0)
+        rows.sort(key=lambda r: -r["ms"])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        tf_peak = peaks.get("bf16_tflops_sustained") or 1400.0     # kernel timed inside a long step
+        hbm_peak = peaks.get("hbm_gbs") or 6650.0
+        src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        if rows:
+            top = rows[0]
+            if top["flops"] > 0:
+                ach = top["flops"] / (top["ms"] * 1e-3) / 1e12
+                roofline = {"kernel": top["name"], "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
+                            "frac": ach / tf_peak, "traffic": None, "peak_source": src + ", sustained bf16",
+                            "ms_per_step_in_kernel": top["ms"], "launches_per_step": top["launches"]}
+            else:
+                ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9
+                roofline = {"kernel": top["name"], "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": ach / hbm_peak, "traffic": None, "peak_source": src,
+                            "ms_per_step_in_kernel": top["ms"], "launches_per_step": top["launches"]}
+            step_flops = flops_train_per_seq(T, F, H, L, C) * B
+            roofline["step_model_tflops"] = step_flops / (ms_step * 1e-3) / 1e12
+            roofline["step_frac_of_gemm_roofline"] = roofline["step_model_tflops"] / tf_peak
+            roofline["kernel_shares"] = [{"kernel": r["name"], "ms_per_step": round(r["ms"], 4), "launches": r["launches"]}
+                                         for r in rows[:8]]
+
+    # ---- reference CPU path on this box's host cores (rank 0, N=1) -----------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = time_cpu_reference(steps=3, warmup=1, budget_s=25.0)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+                "config": workload_config(world, precision), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

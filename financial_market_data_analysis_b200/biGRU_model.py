@@ -1,0 +1,476 @@
+"""B200-native drop-in for the reference's ``biGRU_model`` module.
+
+``BiGRU`` keeps the class surface of /root/reference/biGRU_model.py:8-286 - constructor
+argument order (:32-33), attribute names (:39-47), submodule names ``dropout`` /
+``spatial_dropout1d`` / ``gru`` / ``linear`` (so ``model_params.pt`` loads unchanged),
+``forward(input_seq, hidden=None)`` (:63), ``add_loss_fn`` / ``add_optimizer`` / ``add_device``
+(:141-159), ``train_model`` (:162) and ``evaluate_model`` (:227) with the same return tuples -
+but every floating-point operation of forward/backward, the loss, gradient clipping and the
+Adam update run in hand-written sm_100a CUDA kernels behind the C ABI of
+``libbigru_b200.so`` (include/bigru_b200.h).  PyTorch only owns device memory, streams and the
+process group.  There is no CPU path: parameters must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .parallel import allreduce_flat_
+
+_PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+
+
+def _stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _GRUWeights(nn.Module):
+    """Holds the recurrent parameters under torch.nn.GRU's names, shapes, registration order and
+    initialisation (U(-1/sqrt(H), 1/sqrt(H)), drawn in registration order), i.e. what
+    biGRU_model.py:54-56 constructs.  It has no forward of its own: the recurrence runs inside
+    libbigru_b200."""
+
+    def __init__(self, input_size, hidden_size, num_layers, bidirectional, dropout):
+        super().__init__()
+        self.input_size, self.hidden_size, self.num_layers = input_size, hidden_size, num_layers
+        self.bidirectional, self.dropout, self.batch_first, self.bias = bidirectional, float(dropout), True, True
+        dirs = 2 if bidirectional else 1
+        for layer in range(num_layers):
+            fan = input_size if layer == 0 else hidden_size * dirs
+            for d in range(dirs):
+                sfx = f"l{layer}" + ("_reverse" if d else "")
+                self.register_parameter(f"weight_ih_{sfx}", nn.Parameter(torch.empty(3 * hidden_size, fan)))
+                self.register_parameter(f"weight_hh_{sfx}", nn.Parameter(torch.empty(3 * hidden_size, hidden_size)))
+                self.register_parameter(f"bias_ih_{sfx}", nn.Parameter(torch.empty(3 * hidden_size)))
+                self.register_parameter(f"bias_hh_{sfx}", nn.Parameter(torch.empty(3 * hidden_size)))
+        bound = 1.0 / math.sqrt(hidden_size) if hidden_size > 0 else 0.0
+        with torch.no_grad():
+            for p in self.parameters():
+                p.uniform_(-bound, bound)
+
+    def forward(self, *args, **kwargs):
+        raise RuntimeError("BiGRU.gru only stores parameters; call BiGRU.forward (libbigru_b200 runs the recurrence)")
+
+
+class _Plan:
+    """A C plan plus its device workspaces for one (B, T) shape."""
+
+    def __init__(self, model: "BiGRU", B: int, T: int, device):
+        lib = _lib.load()
+        _lib.check(lib.bigru_device_check(device.index if device.index is not None else torch.cuda.current_device()),
+                   "bigru_device_check")
+        h = _lib.C.c_void_p()
+        _lib.check(lib.bigru_plan_create(B, T, model.n_features, model.hidden_size, model.n_layers, model.output_size,
+                                         int(model.bidirectional), _PRECISIONS[model.precision], _lib.C.byref(h)),
+                   "bigru_plan_create")
+        self.handle, self.B, self.T, self.device = h, B, T, device
+        a, b = _lib.C.c_size_t(), _lib.C.c_size_t()
+        _lib.check(lib.bigru_workspace_bytes(h, _lib.C.byref(a), _lib.C.byref(b)), "bigru_workspace_bytes")
+        self.stash_bytes, self.scratch_bytes = a.value, b.value
+        self.scratch = torch.empty(max(self.scratch_bytes, 16), dtype=torch.uint8, device=device)
+        self._free_stash = []
+
+    def acquire_stash(self):
+        if self._free_stash:
+            return self._free_stash.pop()
+        return torch.empty(max(self.stash_bytes, 16), dtype=torch.uint8, device=self.device)
+
+    def release_stash(self, s):
+        if len(self._free_stash) < 2:
+            self._free_stash.append(s)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.load().bigru_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class _BiGRUFunction(torch.autograd.Function):
+    """autograd boundary: forward/backward are single calls into the C ABI."""
+
+    @staticmethod
+    def forward(ctx, model, x, h0, *params):
+        lib = _lib.load()
+        plan = model._plan_for(x)
+        B = x.shape[0]
+        logits = torch.empty(B, model.output_size, device=x.device, dtype=torch.float32)
+        hn = torch.empty(model.n_layers * model.n_directions, B, model.hidden_size, device=x.device, dtype=torch.float32)
+        need_grad = any(ctx.needs_input_grad)        # grad mode is off inside Function.forward; ask the ctx
+        stash = plan.acquire_stash()
+        training = bool(model.training and model.dropout_p > 0)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
+        _lib.check(lib.bigru_forward(plan.handle, _lib.ptr(model._flat), _lib.ptr(x), _lib.ptr(h0),
+                                     float(model.dropout_p), int(bool(model.spatial_dropout)), int(training), seed,
+                                     _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(logits), _lib.ptr(hn),
+                                     _stream_ptr()), "bigru_forward")
+        model._last_hidden = hn
+        if need_grad:
+            ctx.model, ctx.plan, ctx.stash, ctx.seed, ctx.training = model, plan, stash, seed, training
+            ctx.save_for_backward(x, h0 if h0 is not None else torch.empty(0, device=x.device))
+            ctx.has_h0 = h0 is not None
+        else:
+            plan.release_stash(stash)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        lib = _lib.load()
+        model, plan = ctx.model, ctx.plan
+        x, h0 = ctx.saved_tensors
+        h0 = h0 if ctx.has_h0 else None
+        dlogits = dlogits.contiguous().float()
+        grads = torch.empty_like(model._flat)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[1] else None
+        dh0 = torch.empty_like(h0) if (h0 is not None and ctx.needs_input_grad[2]) else None
+        _lib.check(lib.bigru_backward(plan.handle, _lib.ptr(model._flat), _lib.ptr(x), _lib.ptr(h0),
+                                      float(model.dropout_p), int(bool(model.spatial_dropout)), int(ctx.training),
+                                      ctx.seed, _lib.ptr(ctx.stash), _lib.ptr(plan.scratch), _lib.ptr(dlogits),
+                                      _lib.ptr(grads), _lib.ptr(dx), _lib.ptr(dh0), _stream_ptr()), "bigru_backward")
+        plan.release_stash(ctx.stash)
+        ctx.stash = None
+        pg = tuple(grads[o:o + n].view(shape) for (o, n, shape) in model._views)
+        return (None, dx, dh0) + pg
+
+
+class BiGRU(nn.Module):
+    """Bidirectional GRU classifier (reference: biGRU_model.py:8).
+
+    Parameters (same order and defaults as the reference, :32-33): hidden_size, n_features,
+    output_size, n_layers=1, clip=50, dropout=0.2, spatial_dropout=True, bidirectional=True.
+    Extra keyword ``precision``: "fp32" (FFMA kernels; the parity path) or "bf16" (bf16 operands
+    on tcgen05 tensor cores, fp32 accumulation and state).  Default: $BIGRU_B200_PRECISION or "fp32".
+    """
+
+    def __init__(self, hidden_size, n_features, output_size, n_layers=1, clip=50, dropout=0.2,
+                 spatial_dropout=True, bidirectional=True, precision: Optional[str] = None):
+        super().__init__()
+        self.hidden_size = hidden_size
+        self.n_features = n_features
+        self.output_size = output_size
+        self.n_layers = n_layers
+        self.clip = clip
+        self.dropout_p = dropout
+        self.spatial_dropout = spatial_dropout
+        self.bidirectional = bidirectional
+        self.n_directions = 2 if bidirectional else 1
+        self.precision = precision or os.environ.get("BIGRU_B200_PRECISION", "fp32")
+        if self.precision not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+
+        # same submodule names and construction order as the reference (:50-60) so that a given
+        # torch.manual_seed produces the same initial weights and state_dict keys
+        self.dropout = nn.Dropout(self.dropout_p)
+        if self.spatial_dropout:
+            self.spatial_dropout1d = nn.Dropout2d(self.dropout_p)
+        self.gru = _GRUWeights(n_features, hidden_size, n_layers, bidirectional, 0 if n_layers == 1 else dropout)
+        self.linear = nn.Linear(hidden_size * 3, output_size)
+
+        self.device = torch.device("cpu")
+        self.loss_fn = None
+        self.optimizer = None
+        self._flat = None            # all parameters, one contiguous fp32 vector (C-ABI order)
+        self._views = []             # (offset, numel, shape) per parameter in C-ABI order
+        self._plans = {}
+        self._adam = None            # fused-step optimiser state (flat m, v, step)
+        self._dp_group = None
+        self._dp_world = 1
+        self._last_hidden = None
+        self._flatten()
+
+    # ------------------------------------------------------------------ parameter storage
+    def _ordered_params(self):
+        out = []
+        for layer in range(self.n_layers):
+            for d in range(self.n_directions):
+                sfx = f"l{layer}" + ("_reverse" if d else "")
+                for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+                    out.append(getattr(self.gru, f"{n}_{sfx}"))
+        out += [self.linear.weight, self.linear.bias]
+        return out
+
+    def _flatten(self):
+        """(Re)pack every parameter into one contiguous vector and make the nn.Parameters views of it,
+        keeping the Parameter objects (optimisers hold references to them)."""
+        params = self._ordered_params()
+        dev = params[0].device
+        total = sum(p.numel() for p in params)
+        flat = torch.empty(total, dtype=torch.float32, device=dev)
+        views, off = [], 0
+        with torch.no_grad():
+            for p in params:
+                n = p.numel()
+                flat[off:off + n].copy_(p.detach().reshape(-1).to(device=dev, dtype=torch.float32))
+                p.data = flat[off:off + n].view(p.shape)
+                views.append((off, n, tuple(p.shape)))
+                off += n
+        self._flat, self._views = flat, views
+        self._plans = {}
+        self._adam = None
+
+    def _is_flat(self):
+        f = self._flat
+        if f is None:
+            return False
+        base = f.data_ptr()
+        for p, (off, n, _) in zip(self._ordered_params(), self._views):
+            if p.device != f.device or p.dtype != torch.float32 or p.data_ptr() != base + 4 * off:
+                return False
+        return True
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)       # .cuda() / .to() create fresh tensors per parameter
+        self._flatten()
+        return out
+
+    def flat_parameters(self) -> torch.Tensor:
+        if not self._is_flat():
+            self._flatten()
+        return self._flat
+
+    # ------------------------------------------------------------------ plans
+    def _plan_for(self, x) -> _Plan:
+        key = (int(x.shape[0]), int(x.shape[1]), self.precision, x.device.index)
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) > 8:
+                self._plans.clear()
+            plan = self._plans[key] = _Plan(self, key[0], key[1], x.device)
+        return plan
+
+    def _prepare_input(self, input_seq, hidden):
+        if not self._is_flat():
+            self._flatten()
+        dev = self._flat.device
+        if dev.type != "cuda":
+            raise RuntimeError("BiGRU (B200-native) has no CPU path: move the model to a CUDA device with .cuda() first")
+        if input_seq.dim() != 3 or input_seq.shape[2] != self.n_features:
+            raise ValueError(f"input_seq must be [batch, seq_len, {self.n_features}], got {tuple(input_seq.shape)}")
+        x = input_seq.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        h0 = None
+        if hidden is not None:
+            want = (self.n_layers * self.n_directions, x.shape[0], self.hidden_size)
+            if tuple(hidden.shape) != want:
+                raise RuntimeError(f"Expected hidden size {want}, got {tuple(hidden.shape)}")
+            h0 = hidden.to(device=dev, dtype=torch.float32).contiguous()
+        return x, h0
+
+    # ------------------------------------------------------------------ reference surface
+    def forward(self, input_seq, hidden=None):
+        """Logits [batch, output_size] (biGRU_model.py:63-138)."""
+        x, h0 = self._prepare_input(input_seq, hidden)
+        self.batch_size, self.input_length = x.size(0), x.size(1)          # as the reference sets (:82-85)
+        return _BiGRUFunction.apply(self, x, h0, *self._ordered_params())
+
+    def add_loss_fn(self, loss_fn):
+        self.loss_fn = loss_fn
+
+    def add_optimizer(self, optimizer):
+        self.optimizer = optimizer
+        self._adam = None
+
+    def add_device(self, device=torch.device("cpu")):
+        self.device = device
+
+    def enable_data_parallel(self, process_group=None):
+        """Batch data parallelism: one process per GPU, every rank holds a replica and a batch shard;
+        train_step/train_model all-reduce the flat gradient once per step (NCCL over NVLink)."""
+        import torch.distributed as dist
+        self._dp_group = process_group if process_group is not None else dist.group.WORLD
+        self._dp_world = dist.get_world_size(self._dp_group)
+
+    # ------------------------------------------------------------------ fused training step
+    def _loss_spec(self):
+        fn = self.loss_fn
+        if isinstance(fn, nn.CrossEntropyLoss):
+            if fn.weight is None and fn.reduction == "mean" and getattr(fn, "label_smoothing", 0.0) == 0.0 \
+                    and fn.ignore_index == -100:
+                return _lib.LOSS_CE, None, None
+        elif isinstance(fn, nn.BCEWithLogitsLoss):
+            if fn.reduction == "mean":
+                return _lib.LOSS_BCE, fn.weight, fn.pos_weight
+        elif isinstance(fn, nn.MultiLabelSoftMarginLoss):
+            if fn.weight is None and fn.reduction == "mean":
+                return _lib.LOSS_MLSM, None, None
+        return None
+
+    def _adam_spec(self):
+        opt = self.optimizer
+        if not isinstance(opt, torch.optim.Adam) or len(opt.param_groups) != 1:
+            return None
+        g = opt.param_groups[0]
+        if g.get("weight_decay", 0) != 0 or g.get("amsgrad", False) or g.get("maximize", False):
+            return None
+        mine = {id(p) for p in self._ordered_params()}
+        if {id(p) for p in g["params"]} != mine:
+            return None
+        return g
+
+    def can_fuse_step(self) -> bool:
+        return self._loss_spec() is not None and self._adam_spec() is not None
+
+    def _loss_vec(self, w, C):
+        if w is None:
+            return None
+        w = w.to(device=self._flat.device, dtype=torch.float32).reshape(-1)
+        if w.numel() == 1:
+            w = w.expand(C)
+        if w.numel() != C:
+            raise ValueError("loss weight must have one entry per class")
+        return w.contiguous()
+
+    def train_step(self, input_seq, target, hidden=None):
+        """One optimisation step = the body of the reference loop (biGRU_model.py:198-210):
+        zero_grad, forward, loss, backward, clip_grad_norm_(clip), Adam step - as six C-ABI calls with
+        no autograd graph.  Returns (loss, logits) as device tensors (no host sync)."""
+        spec, g = self._loss_spec(), self._adam_spec()
+        if spec is None or g is None:
+            raise RuntimeError("train_step needs add_loss_fn(CrossEntropyLoss | BCEWithLogitsLoss | "
+                               "MultiLabelSoftMarginLoss, mean reduction) and add_optimizer(torch.optim.Adam(model.parameters()))")
+        lib = _lib.load()
+        x, h0 = self._prepare_input(input_seq, hidden)
+        dev = x.device
+        kind, w, pw = spec
+        B, C = x.shape[0], self.output_size
+        if kind == _lib.LOSS_CE:
+            tgt = target.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+            if tgt.shape != (B,):
+                raise ValueError(f"CrossEntropyLoss target must be [{B}] class indices")
+            denom = float(B * self._dp_world)
+        else:
+            tgt = target.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+            if tuple(tgt.shape) != (B, C):
+                raise ValueError(f"target must be [{B}, {C}]")
+            denom = float(B * C * self._dp_world)
+        plan = self._plan_for(x)
+        st = self._adam
+        if st is None:
+            st = self._adam = {"m": torch.zeros_like(self._flat), "v": torch.zeros_like(self._flat), "step": 0,
+                               "grad": torch.empty_like(self._flat),
+                               "scal": torch.zeros(2, device=dev, dtype=torch.float32)}
+        logits = torch.empty(B, C, device=dev, dtype=torch.float32)
+        dlogits = torch.empty_like(logits)
+        stash = plan.acquire_stash()
+        training = bool(self.training and self.dropout_p > 0)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
+        s = _stream_ptr()
+        args = (float(self.dropout_p), int(bool(self.spatial_dropout)), int(training), seed)
+        _lib.check(lib.bigru_forward(plan.handle, _lib.ptr(self._flat), _lib.ptr(x), _lib.ptr(h0), *args,
+                                     _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(logits), None, s), "bigru_forward")
+        loss = st["scal"][0:1]
+        sq = st["scal"][1:2]
+        _lib.check(lib.bigru_loss(kind, _lib.ptr(logits), _lib.ptr(tgt), _lib.ptr(self._loss_vec(w, C)),
+                                  _lib.ptr(self._loss_vec(pw, C)), B, C, denom, _lib.ptr(loss), _lib.ptr(dlogits), s),
+                   "bigru_loss")
+        _lib.check(lib.bigru_backward(plan.handle, _lib.ptr(self._flat), _lib.ptr(x), _lib.ptr(h0), *args,
+                                      _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(dlogits), _lib.ptr(st["grad"]),
+                                      None, None, s), "bigru_backward")
+        plan.release_stash(stash)
+        if self._dp_world > 1:
+            allreduce_flat_(st["grad"], self._dp_group)          # sum of shard gradients of the global-mean loss
+            allreduce_flat_(loss, self._dp_group)
+        sq.zero_()
+        _lib.check(lib.bigru_sqnorm(_lib.ptr(st["grad"]), st["grad"].numel(), _lib.ptr(sq), s), "bigru_sqnorm")
+        st["step"] += 1
+        b1, b2 = g["betas"]
+        _lib.check(lib.bigru_clip_adam_step(_lib.ptr(self._flat), _lib.ptr(st["grad"]), _lib.ptr(st["m"]),
+                                            _lib.ptr(st["v"]), self._flat.numel(), _lib.ptr(sq), float(self.clip),
+                                            float(g["lr"]), float(b1), float(b2), float(g["eps"]), st["step"], 1.0, s),
+                   "bigru_clip_adam_step")
+        return loss.clone(), logits
+
+    def _generic_step(self, x, target):
+        """Any loss / optimiser: autograd drives the same CUDA forward/backward kernels."""
+        self.optimizer.zero_grad()
+        pred = self.forward(x)
+        if isinstance(self.loss_fn, nn.Module):
+            self.loss_fn.to(pred.device)                 # class weights follow the logits
+        loss = self.loss_fn(pred, target.to(pred.device))
+        loss.backward()
+        if self._dp_world > 1:
+            for p in self.parameters():
+                allreduce_flat_(p.grad, self._dp_group)
+                p.grad.div_(self._dp_world)
+        nn.utils.clip_grad_norm_(self.parameters(), self.clip)
+        self.optimizer.step()
+        return loss.detach().reshape(1), pred.detach()
+
+    # ------------------------------------------------------------------ epoch loops
+    def _metric_counts(self, logits, target, counts_row):
+        if target.dim() != 2 or target.shape != logits.shape:
+            raise ValueError("multilabel metrics need a [batch, n_classes] indicator target "
+                             "(biGRU_model.py:213-221 feeds sigmoid(pred) > 0.5 to sklearn)")
+        tgt = target.to(device=logits.device, dtype=torch.float32).contiguous()
+        _lib.check(_lib.load().bigru_multilabel_counts(_lib.ptr(logits), _lib.ptr(tgt), logits.shape[0],
+                                                       logits.shape[1], _lib.ptr(counts_row), _stream_ptr()),
+                   "bigru_multilabel_counts")
+
+    @staticmethod
+    def _scores(counts: np.ndarray, sizes, C, beta=0.5):
+        """Per-batch accuracy / Hamming loss / F-beta from the device counters, then the mean over
+        batches (the reference averages per-batch sklearn scores, :224 / :286)."""
+        acc, ham, fb = [], [], []
+        b2 = beta * beta
+        for row, B in zip(counts, sizes):
+            acc.append(row[0] / B)
+            ham.append(row[1] / (B * C))
+            tp, fp, fn = row[2::3][:C], row[3::3][:C], row[4::3][:C]
+            den = (1 + b2) * tp + b2 * fn + fp
+            fb.append(np.where(den > 0, (1 + b2) * tp / np.maximum(den, 1), 0.0))
+        return float(np.mean(acc)), float(np.mean(ham)), np.mean(np.stack(fb), axis=0)
+
+    def train_model(self, train_iterator):
+        """One training epoch (biGRU_model.py:162-224).  Returns
+        (mean accuracy, mean Hamming loss, mean loss, mean F-beta(0.5) per class)."""
+        self.train()
+        fused = self.can_fuse_step()
+        losses, sizes, rows = [], [], []
+        C = self.output_size
+        for input_seq, target in train_iterator:
+            target = target.squeeze(1)                                   # [B,1,C] -> [B,C]  (:193)
+            if fused:
+                loss, logits = self.train_step(input_seq, target)
+            else:
+                x, _ = self._prepare_input(input_seq, None)
+                loss, logits = self._generic_step(x, target)
+            row = torch.zeros(2 + 3 * C, dtype=torch.int64, device=logits.device)
+            self._metric_counts(logits, target, row)
+            losses.append(loss.reshape(1))
+            rows.append(row)
+            sizes.append(logits.shape[0])
+        if not rows:
+            return float("nan"), float("nan"), float("nan"), np.full(C, np.nan)
+        counts = torch.stack(rows).cpu().numpy().astype(np.float64)      # one host sync per epoch
+        acc, ham, fb = self._scores(counts, sizes, C)
+        return acc, ham, float(torch.cat(losses).float().mean().item()), fb
+
+    def evaluate_model(self, eval_iterator):
+        """One evaluation epoch (biGRU_model.py:227-286).  Returns (mean accuracy, mean Hamming loss,
+        mean F-beta(0.5) per class, pred_total LongTensor, target_total LongTensor)."""
+        self.eval()
+        C = self.output_size
+        rows, sizes, preds, targets = [], [], [], []
+        with torch.no_grad():
+            for input_seq, target in eval_iterator:
+                target = target.squeeze(1)
+                logits = self.forward(input_seq)
+                row = torch.zeros(2 + 3 * C, dtype=torch.int64, device=logits.device)
+                self._metric_counts(logits, target, row)
+                rows.append(row)
+                sizes.append(logits.shape[0])
+                preds.append(logits > 0)                                  # sigmoid(x) > 0.5
+                targets.append(target)
+        if not rows:
+            return float("nan"), float("nan"), np.full(C, np.nan), torch.LongTensor(), torch.LongTensor()
+        counts = torch.stack(rows).cpu().numpy().astype(np.float64)
+        acc, ham, fb = self._scores(counts, sizes, C)
+        pred_total = torch.cat(preds).cpu().type(torch.LongTensor)
+        target_total = torch.cat([t.cpu() for t in targets]).type(torch.LongTensor)
+        return acc, ham, fb, pred_total, target_total

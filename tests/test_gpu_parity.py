@@ -1,0 +1,397 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+Run on the B200 box:  python -m pytest tests -m gpu -x -q"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+import fake_db
+import oracle_c
+from oracle import bigru_oracle as bo
+from oracle import loader_oracle as lo
+
+pytestmark = pytest.mark.gpu
+
+# fp32 path: logits <= 1e-4 rel (BASELINE.json north_star); gradients rel-L2 <= 1e-3
+TOL = {"fp32": dict(logits=1e-4, grads=1e-3, kat=1e-5, step=2e-5),
+       "bf16": dict(logits=3e-2, grads=6e-2, kat=3e-2, step=2e-3)}
+
+
+def _pkg():
+    import financial_market_data_analysis_b200 as pkg
+    return pkg
+
+
+def precisions():
+    pkg = _pkg()
+    lib = pkg._lib.load()
+    out = ["fp32"]
+    h = pkg._lib.C.c_void_p()
+    if lib.bigru_plan_create(128, 16, 64, 256, 1, 3, 1, pkg._lib.PREC_BF16, pkg._lib.C.byref(h)) == 0:
+        lib.bigru_plan_destroy(h)
+        out.append("bf16")
+    return out
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def params_of(z, prefix="p:"):
+    return {k[len(prefix):]: z[k] for k in z.files if k.startswith(prefix)}
+
+
+def make_model(d, sd_np, precision, dropout=0.0, spatial=False):
+    m = _pkg().BiGRU(d["H"], d["F"], d["C"], d["L"], 50, dropout, spatial, d["bidir"], precision=precision)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd_np.items()})
+    return m.cuda()
+
+
+def loss_from(z):
+    kind = str(z["loss_kind"])
+    if kind == "ce":
+        return nn.CrossEntropyLoss(), torch.from_numpy(z["target"])
+    if kind == "bce":
+        return (nn.BCEWithLogitsLoss(weight=torch.from_numpy(z["loss_weight"]), pos_weight=torch.from_numpy(z["loss_pos_weight"])),
+                torch.from_numpy(z["target"]))
+    return nn.MultiLabelSoftMarginLoss(), torch.from_numpy(z["target"])
+
+
+def test_library_is_native_and_device_ok():
+    pkg = _pkg()
+    lib = pkg._lib.load()
+    assert os.path.basename(pkg._lib.LIB_PATH) == "libbigru_b200.so"
+    assert lib.bigru_device_check(0) == 0, lib.bigru_last_error()
+
+
+def test_known_answer_vectors(golden_dir):
+    """Shipped model_params.pt through the CUDA path."""
+    z = np.load(os.path.join(golden_dir, "kat.npz"))
+    for precision in precisions():
+        m = make_model(dict(H=8, F=108, C=4, L=1, bidir=True), params_of(z), precision, dropout=0.2)
+        m.eval()
+        for i in (1, 2, 3):
+            with torch.no_grad():
+                y = m(torch.from_numpy(z[f"x{i}"])).cpu().numpy()      # CPU input: moved to the model's device
+            assert np.abs(y - z[f"y{i}"]).max() < TOL[precision]["kat"] * max(1.0, np.abs(z[f"y{i}"]).max()), (precision, i)
+
+
+@pytest.mark.parametrize("name", ["c0", "small_l2", "small_uni_bce", "small_bi_h0_mlsm", "ragged"])
+def test_golden_forward_backward_autograd(golden_dir, name):
+    """Logits, loss, every parameter gradient, dx and dh0 against the reference's own autograd."""
+    z = np.load(os.path.join(golden_dir, f"model_{name}.npz"))
+    B, T, F, H, L, C, bidir = [int(v) for v in z["meta"]]
+    d = dict(B=B, T=T, F=F, H=H, L=L, C=C, bidir=bool(bidir))
+    for precision in precisions():
+        tol = TOL[precision]
+        m = make_model(d, params_of(z), precision)
+        m.train()
+        x = torch.from_numpy(z["x"]).cuda().requires_grad_(True)
+        h0 = torch.from_numpy(z["h0"]).cuda().requires_grad_(True) if "h0" in z.files else None
+        loss_fn, tgt = loss_from(z)
+        loss_fn = loss_fn.cuda()
+        pred = m(x, h0)
+        assert rel(pred.detach().cpu().numpy(), z["logits"]) < tol["logits"], precision
+        loss = loss_fn(pred, tgt.cuda())
+        loss.backward()
+        assert abs(loss.item() - float(z["loss"])) < 10 * tol["logits"] * max(1.0, abs(float(z["loss"])))
+        for k, p in m.named_parameters():
+            g = z["g:" + k]
+            assert rel_l2(p.grad.cpu().numpy(), g) < tol["grads"] or np.abs(p.grad.cpu().numpy() - g).max() < 1e-7, (precision, k)
+        assert rel_l2(x.grad.cpu().numpy(), z["dx"]) < tol["grads"]
+        if h0 is not None:
+            assert rel_l2(h0.grad.cpu().numpy(), z["dh0"]) < tol["grads"]
+
+
+@pytest.mark.parametrize("name", ["c0", "small_uni_bce", "small_bi_h0_mlsm"])
+def test_golden_fused_train_step(golden_dir, name):
+    """zero_grad -> forward -> loss -> backward -> clip_grad_norm_ -> Adam (biGRU_model.py:198-210):
+    parameters after one fused step against the reference's."""
+    z = np.load(os.path.join(golden_dir, f"model_{name}.npz"))
+    B, T, F, H, L, C, bidir = [int(v) for v in z["meta"]]
+    d = dict(B=B, T=T, F=F, H=H, L=L, C=C, bidir=bool(bidir))
+    for precision in precisions():
+        tol = TOL[precision]
+        m = make_model(d, params_of(z), precision)
+        loss_fn, tgt = loss_from(z)
+        m.add_loss_fn(loss_fn)
+        m.add_optimizer(torch.optim.Adam(m.parameters(), lr=1e-3))
+        m.train()
+        h0 = torch.from_numpy(z["h0"]).cuda() if "h0" in z.files else None
+        loss, logits = m.train_step(torch.from_numpy(z["x"]).cuda(), tgt.cuda(), h0)
+        assert abs(float(loss) - float(z["loss"])) < 10 * tol["logits"] * max(1.0, abs(float(z["loss"])))
+        assert rel(logits.cpu().numpy(), z["logits"]) < tol["logits"]
+        gn = float(torch.sqrt(m._adam["scal"][1]))
+        assert abs(gn - float(z["grad_norm"])) < tol["grads"] * float(z["grad_norm"])
+        for k, v in m.state_dict().items():
+            assert np.abs(v.cpu().numpy() - z["q:" + k]).max() < tol["step"], (precision, k)
+
+
+SWEEP = [  # B, T, F, H, L, C, bidir, h0
+    (1, 1, 1, 1, 1, 1, True, False),
+    (2, 3, 5, 7, 1, 2, False, True),
+    (5, 4, 9, 33, 2, 3, True, True),
+    (17, 9, 12, 40, 3, 4, True, False),
+    (33, 6, 64, 64, 2, 3, False, False),
+    (64, 16, 32, 128, 2, 3, True, False),
+]
+
+
+@pytest.mark.parametrize("cfg", SWEEP)
+def test_sweep_against_c_oracle(cfg):
+    B, T, F, H, L, C, bidir, use_h0 = cfg
+    D = 2 if bidir else 1
+    for precision in precisions():
+        tol = TOL[precision]
+        torch.manual_seed(3)
+        m = _pkg().BiGRU(H, F, C, L, 50, 0.0, False, bidir, precision=precision).cuda()
+        g = torch.Generator().manual_seed(11)
+        x = torch.randn(B, T, F, generator=g)
+        h0 = torch.randn(L * D, B, H, generator=g) * 0.5 if use_h0 else None
+        dl = torch.randn(B, C, generator=g)
+        flat = m.flat_parameters().cpu().numpy()
+        sd = {k: v.cpu().numpy() for k, v in m.state_dict().items()}
+        assert np.array_equal(flat, oracle_c.flatten_params(sd, L, D))       # C-ABI parameter order
+        ref_logits, ref_hn, stash = oracle_c.forward(flat, x.numpy(), H, L, C, D, None if h0 is None else h0.numpy(), keep=True)
+        ref_g, ref_dx, ref_dh0 = oracle_c.backward(flat, x.numpy(), stash, dl.numpy(), H, L, C, D)
+        xg = x.cuda().requires_grad_(True)
+        hg = h0.cuda().requires_grad_(True) if use_h0 else None
+        y = m(xg, hg)
+        y.backward(dl.cuda())
+        scale = max(np.abs(ref_logits).max(), 1e-3)
+        assert np.abs(y.detach().cpu().numpy() - ref_logits).max() / scale < tol["logits"], (precision, cfg)
+        assert rel(m._last_hidden.cpu().numpy(), ref_hn) < tol["logits"] * 10
+        got = torch.cat([p.grad.reshape(-1) for p in m._ordered_params()]).cpu().numpy()
+        assert rel_l2(got, ref_g) < tol["grads"], (precision, cfg)
+        assert rel_l2(xg.grad.cpu().numpy(), ref_dx) < tol["grads"]
+        if use_h0:
+            assert rel_l2(hg.grad.cpu().numpy(), ref_dh0) < tol["grads"]
+
+
+def test_c1_shape_against_torch_oracle():
+    """BASELINE config 1 shape (B512,T128,F64,H256,L2): logits <= 1e-4 rel of the torch.nn.GRU CPU path,
+    gradients by rel-L2."""
+    B, T, F, H, L, C = 512, 128, 64, 256, 2, 3
+    torch.manual_seed(0)
+    ref = bo.OracleBiGRU(H, F, C, L, 50, 0.0, False, True)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(B, T, F, generator=g)
+    target = torch.randint(0, C, (B,), generator=g)
+    ref.train()
+    pred = ref(x)
+    loss = nn.CrossEntropyLoss()(pred, target)
+    loss.backward()
+    for precision in precisions():
+        tol = TOL[precision]
+        torch.manual_seed(0)
+        m = _pkg().BiGRU(H, F, C, L, 50, 0.0, False, True, precision=precision).cuda()
+        m.train()
+        y = m(x.cuda())
+        l2 = nn.CrossEntropyLoss()(y, target.cuda())
+        l2.backward()
+        assert rel(y.detach().cpu().numpy(), pred.detach().numpy()) < tol["logits"], precision
+        assert abs(l2.item() - loss.item()) < 10 * tol["logits"]
+        for (k, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+            assert rel_l2(p.grad.cpu().numpy(), q.grad.numpy()) < tol["grads"], (precision, k)
+
+
+def test_shard_gradients_sum_to_full_batch():
+    """Data-parallel property: the shard gradients of the global-mean loss add up to the full-batch
+    gradient (what the single all-reduce computes)."""
+    B, T, F, H, L, C = 64, 10, 16, 32, 2, 3
+    for precision in precisions():
+        torch.manual_seed(1)
+        m = _pkg().BiGRU(H, F, C, L, 50, 0.0, False, True, precision=precision).cuda()
+        x = torch.randn(B, T, F, device="cuda")
+        t = torch.randint(0, C, (B,), device="cuda")
+        ce = nn.CrossEntropyLoss(reduction="sum")
+
+        def grad(xs, ts):
+            m.zero_grad()
+            (ce(m(xs), ts) / B).backward()
+            return torch.cat([p.grad.reshape(-1) for p in m._ordered_params()]).clone()
+
+        full = grad(x, t)
+        parts = grad(x[:32], t[:32]) + grad(x[32:], t[32:])
+        assert rel_l2(parts.cpu().numpy(), full.cpu().numpy()) < (1e-5 if precision == "fp32" else 2e-2)
+
+
+def test_linearity_in_upstream_gradient():
+    """Size-independent property at a realistic size: backward is linear in dlogits."""
+    B, T, F, H, L, C = 128, 32, 64, 256, 2, 3
+    for precision in precisions():
+        torch.manual_seed(2)
+        m = _pkg().BiGRU(H, F, C, L, 50, 0.0, False, True, precision=precision).cuda()
+        x = torch.randn(B, T, F, device="cuda")
+        d1, d2 = torch.randn(B, C, device="cuda"), torch.randn(B, C, device="cuda")
+
+        def grad(dl):
+            m.zero_grad()
+            m(x).backward(dl)
+            return torch.cat([p.grad.reshape(-1) for p in m._ordered_params()]).clone()
+
+        lhs = grad(d1 + 2 * d2)
+        rhs = grad(d1) + 2 * grad(d2)
+        assert rel_l2(lhs.cpu().numpy(), rhs.cpu().numpy()) < (1e-4 if precision == "fp32" else 2e-2)
+
+
+def test_dropout_modes():
+    """Train-mode dropout: elementwise and channel-wise ('spatial', one mask per (b, f) over T) input
+    masks, inter-layer dropout; same mask in backward (dx is zero exactly where the input was dropped)."""
+    B, T, F, H, L, C = 16, 12, 24, 32, 2, 3
+    for spatial in (False, True):
+        torch.manual_seed(4)
+        m = _pkg().BiGRU(H, F, C, L, 50, 0.5, spatial, True, precision="fp32").cuda()
+        m.train()
+        x = (torch.rand(B, T, F, device="cuda") + 0.5).requires_grad_(True)
+        y1 = m(x)
+        y1.sum().backward()
+        dx = x.grad.clone()
+        zero = (dx == 0)
+        frac = zero.float().mean().item()
+        assert 0.35 < frac < 0.65, frac
+        if spatial:
+            per_channel = zero.all(dim=1) | (~zero).all(dim=1)          # a channel is dropped for all T or none
+            assert per_channel.all()
+        y2 = m(x)
+        assert not torch.equal(y1, y2)                                   # fresh mask per call
+        m.eval()
+        with torch.no_grad():
+            assert torch.equal(m(x), m(x))                               # eval: deterministic, no dropout
+
+
+def test_window_gather_matches_reference_loader(golden_dir):
+    """The gather/normalise kernel against batches delivered by the unmodified reference loader
+    (bit-exact: float32 subtract and IEEE divide)."""
+    z = np.load(os.path.join(golden_dir, "loader.npz"))
+    cols, targets, fields, query = fake_db.make_table(n_rows=250)
+    cur = fake_db.FakeCursor(cols, targets)
+    pkg = _pkg()
+    ids = tuple(int(v) for v in z["chunk1_ids"])
+    norm = (torch.from_numpy(z["chunk1_min"]), torch.from_numpy(z["chunk1_max"]))
+    for bs in (2, 8):
+        ds = pkg.MySQLBatchLoader(ids, norm, cur, "stock_data_joined", query, "t0, t1, t2, t3", 30)
+        assert np.array_equal(ds.x.cpu().numpy(), z[f"bs{bs}_xnorm"])
+        xs, ys = zip(*[(x.cpu().numpy(), y.cpu().numpy()) for x, y in ds.batches(bs)])
+        assert len(xs) == int(z[f"bs{bs}_nbatches"])
+        assert np.array_equal(np.concatenate(xs), z[f"bs{bs}_x"])
+        assert np.array_equal(np.concatenate(ys), z[f"bs{bs}_y"])
+        # per-sample drop-in path through torch's DataLoader
+        ds2 = pkg.MySQLBatchLoader(ids, norm, cur, "stock_data_joined", query, "t0, t1, t2, t3", 30)
+        got = [(x.cpu().numpy(), y.cpu().numpy()) for x, y in torch.utils.data.DataLoader(ds2, batch_size=bs)]
+        assert np.array_equal(np.concatenate([g[0] for g in got]), z[f"bs{bs}_x"])
+        assert np.array_equal(np.concatenate([g[1] for g in got]), z[f"bs{bs}_y"])
+    tail = list(ds.batches(8, drop_incomplete=False))
+    assert sum(x.shape[0] for x, _ in tail) == 100
+
+
+@pytest.mark.parametrize("shape", [(512, 128, 64), (256, 1024, 128), (7, 3, 5), (1, 1, 1), (0, 4, 8)])
+def test_window_gather_property(shape):
+    """Full-size property: the collated batch equals the strided view of the chunk (x.unfold)."""
+    B, T, F = shape
+    pkg = _pkg()
+    lib = pkg._lib.load()
+    N = B + T - 1 + 3
+    src = torch.rand(max(N, 1), F, device="cuda")
+    mn = src.min(0).values - 0.1
+    mx = src.max(0).values + 0.1
+    out = torch.empty(B, T, F, device="cuda")
+    pkg._lib.check(lib.bigru_window_gather_norm(src.data_ptr(), mn.data_ptr(), mx.data_ptr(), 2, N, B, T, F,
+                                                out.data_ptr(), torch.cuda.current_stream().cuda_stream), "gather")
+    if B:
+        ref = ((src - mn) / (mx - mn))[2:2 + B + T - 1].unfold(0, T, 1).permute(0, 2, 1)
+        assert torch.equal(out, ref.contiguous())
+        ref_c = oracle_c.window_gather_norm(src.cpu().numpy(), mn.cpu().numpy(), mx.cpu().numpy(), 2, min(B, 4), T)
+        assert np.array_equal(out[:4].cpu().numpy(), ref_c)
+    # out-of-range windows are an argument error, not a silent clamp
+    with pytest.raises(ValueError):
+        pkg._lib.check(lib.bigru_window_gather_norm(src.data_ptr(), None, None, N, N, 1, T, F, out.data_ptr(), 0), "gather")
+
+
+def test_train_and_evaluate_model_surface():
+    """train_model / evaluate_model return tuples (biGRU_model.py:224, :286); device metric counters
+    against sklearn on the same logits."""
+    from sklearn.metrics import accuracy_score, fbeta_score, hamming_loss
+    cols, targets, fields, query = fake_db.make_table(n_rows=120, with_nulls=False)
+    cur = fake_db.FakeCursor(cols, targets)
+    pkg = _pkg()
+    cl = pkg.MySQLChunkLoader(cur, "stock_data_joined", query, 60, 10, norm_params_path=None)
+    ids, norm = cl[1]
+    torch.manual_seed(0)
+    m = pkg.BiGRU(16, len(fields), 4, 1, 50, 0.0, False, True).cuda()
+    m.add_loss_fn(nn.BCEWithLogitsLoss(pos_weight=torch.tensor([2.0, 1.0, 3.0, 1.5])))
+    m.add_optimizer(torch.optim.Adam(m.parameters(), lr=1e-3))
+    m.add_device(torch.device("cuda"))
+    assert m.can_fuse_step()
+    ds = pkg.MySQLBatchLoader(ids, norm, cur, "stock_data_joined", query, "t0, t1, t2, t3", 10)
+    acc, ham, loss, fb = m.train_model(ds.batches(8))
+    assert 0 <= acc <= 1 and 0 <= ham <= 1 and np.isfinite(loss) and fb.shape == (4,)
+    ds = pkg.MySQLBatchLoader(ids, norm, cur, "stock_data_joined", query, "t0, t1, t2, t3", 10)
+    batches = list(ds.batches(8))
+    acc, ham, fb, pred_total, target_total = m.evaluate_model(batches)
+    assert pred_total.dtype == torch.int64 and pred_total.shape == target_total.shape == (len(batches) * 8, 4)
+    accs, hams, fbs = [], [], []
+    m.eval()
+    with torch.no_grad():
+        for x, y in batches:
+            p = (torch.sigmoid(m(x)) > 0.5).cpu().numpy()
+            t = y.squeeze(1).cpu().numpy()
+            accs.append(accuracy_score(t, p)); hams.append(hamming_loss(t, p))
+            fbs.append(fbeta_score(t, p, beta=0.5, average=None, zero_division=0))
+    assert abs(acc - np.mean(accs)) < 1e-12 and abs(ham - np.mean(hams)) < 1e-12
+    np.testing.assert_allclose(fb, np.mean(fbs, axis=0), atol=1e-12)
+    # generic (non-fusable) optimiser goes through autograd and the same kernels
+    m.add_optimizer(torch.optim.SGD(m.parameters(), lr=1e-2))
+    assert not m.can_fuse_step()
+    ds = pkg.MySQLBatchLoader(ids, norm, cur, "stock_data_joined", query, "t0, t1, t2, t3", 10)
+    out = m.train_model(torch.utils.data.DataLoader(ds, batch_size=4))
+    assert np.isfinite(out[2])
+    # class-index targets cannot feed the multilabel metrics (sklearn raises ValueError in the reference)
+    m.add_loss_fn(nn.CrossEntropyLoss())
+    with pytest.raises(ValueError):
+        m.train_model([(torch.rand(4, 10, len(fields)), torch.zeros(4, 1, dtype=torch.long))])
+
+
+def test_fused_step_matches_generic_step():
+    """train_step (C-ABI calls only) and the autograd + torch.optim path give the same parameters."""
+    B, T, F, H, L, C = 32, 8, 16, 32, 2, 4
+    pkg = _pkg()
+    x = torch.randn(B, T, F, device="cuda")
+    t = (torch.rand(B, C, device="cuda") < 0.3).float()
+    outs = []
+    for fused in (True, False):
+        torch.manual_seed(5)
+        m = pkg.BiGRU(H, F, C, L, 1, 0.0, False, True).cuda()           # clip=1 so that clipping is active
+        m.add_loss_fn(nn.MultiLabelSoftMarginLoss())
+        m.add_optimizer(torch.optim.Adam(m.parameters(), lr=1e-2))
+        m.train()
+        for _ in range(3):
+            if fused:
+                m.train_step(x, t)
+            else:
+                m._generic_step(x, t)
+        outs.append(m.flat_parameters().clone())
+    assert rel_l2(outs[0].cpu().numpy(), outs[1].cpu().numpy()) < 1e-5
+
+
+def test_error_conventions():
+    pkg = _pkg()
+    lib = pkg._lib.load()
+    h = pkg._lib.C.c_void_p()
+    assert lib.bigru_plan_create(0, 4, 4, 4, 1, 2, 1, 0, pkg._lib.C.byref(h)) == pkg._lib.ERR_ARG
+    assert b"bad shape" in lib.bigru_last_error()
+    m = pkg.BiGRU(8, 4, 2, 1).cuda()
+    with pytest.raises(ValueError):
+        m(torch.zeros(2, 3, 5))                       # wrong feature count
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 3, 4), torch.zeros(1, 2, 8))  # wrong hidden shape
+    with pytest.raises(RuntimeError):
+        pkg.BiGRU(8, 4, 2, 1)(torch.zeros(2, 3, 4))    # parameters on CPU: no CPU path
