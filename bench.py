@@ -85,29 +85,43 @@ def synthetic(B, T, F, C, seed):
     return torch.randn(B, T, F, generator=g), torch.randint(0, C, (B,), generator=g)
 
 
-def time_cpu_reference(steps, warmup, budget_s=150.0, batch=None):
-    """The reference CPU path (oracle port) on the host cores, bounded sample of the same workload."""
+def host_cores():
+    """Cores this process may actually use (affinity mask and cgroup quota, not the host's total)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def time_cpu_reference(steps, warmup, budget_s=150.0):
+    """The reference CPU path (oracle port) on the host cores, bounded sample of the same workload:
+    a small calibration batch sizes the sample so that the whole call stays near budget_s."""
     import torch
     import torch.nn as nn
     from oracle.bigru_oracle import OracleBiGRU, train_step
     W = WORK
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     model = OracleBiGRU(W["hidden"], W["n_features"], W["classes"], W["layers"], 50, 0.0, False, True)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     loss_fn = nn.CrossEntropyLoss()
     model.train()
-    B = batch or W["per_gpu_batch"]
-    x, t = synthetic(B, W["seq_len"], W["n_features"], W["classes"], 1234)
+    xf, tf = synthetic(W["per_gpu_batch"], W["seq_len"], W["n_features"], W["classes"], 1234)
+    cal = 32
+    train_step(model, opt, loss_fn, xf[:cal].contiguous(), tf[:cal].contiguous())       # library warm-up
     t0 = time.perf_counter()
-    train_step(model, opt, loss_fn, x, t)                       # first warm-up step, also sizes the sample
-    first = time.perf_counter() - t0
-    total = steps + max(warmup - 1, 0)
-    if batch is None and first * total > budget_s:
-        B = max(32, int(B * budget_s / (first * total)) // 32 * 32)
-        x, t = x[:B].contiguous(), t[:B].contiguous()
-    for _ in range(max(warmup - 1, 0)):
+    train_step(model, opt, loss_fn, xf[:cal].contiguous(), tf[:cal].contiguous())
+    per_seq = (time.perf_counter() - t0) / cal
+    total = steps + max(warmup, 1)
+    B = int(budget_s / (per_seq * total)) // 32 * 32
+    B = max(32, min(W["per_gpu_batch"], B))
+    x, t = xf[:B].contiguous(), tf[:B].contiguous()
+    for _ in range(max(warmup, 1)):
         train_step(model, opt, loss_fn, x, t)
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -116,7 +130,7 @@ def time_cpu_reference(steps, warmup, budget_s=150.0, batch=None):
     return {"value": B / dt, "unit": "sequences/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{steps} train steps of batch {B} x seq {W['seq_len']} x feat {W['n_features']} "
                       f"(hidden {W['hidden']}, {W['layers']} layers, bidirectional) through oracle/bigru_oracle.py "
-                      f"(torch.nn.GRU CPU, {torch.get_num_threads()} threads)",
+                      f"(torch.nn.GRU CPU, {torch.get_num_threads()} threads of {os.cpu_count()} host CPUs)",
             "ms_per_step": dt * 1e3, "batch": B}
 
 
@@ -305,7 +319,7 @@ def main():
     # ---- reference CPU path on this box's host cores (rank 0, N=1) -----------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = time_cpu_reference(steps=3, warmup=1, budget_s=25.0)
+        r = time_cpu_reference(steps=3, warmup=1, budget_s=20.0)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:

@@ -183,6 +183,7 @@ class BiGRU(nn.Module):
         self._dp_group = None
         self._dp_world = 1
         self._last_hidden = None
+        self._loss_cache = {}
         self._flatten()
 
     # ------------------------------------------------------------------ parameter storage
@@ -317,14 +318,22 @@ class BiGRU(nn.Module):
         return self._loss_spec() is not None and self._adam_spec() is not None
 
     def _loss_vec(self, w, C):
+        """Per-class loss weight as a device vector.  Cached (and kept alive across the asynchronous C
+        calls) until the source tensor changes."""
         if w is None:
             return None
-        w = w.to(device=self._flat.device, dtype=torch.float32).reshape(-1)
-        if w.numel() == 1:
-            w = w.expand(C)
-        if w.numel() != C:
-            raise ValueError("loss weight must have one entry per class")
-        return w.contiguous()
+        key = (id(w), w._version, C)
+        hit = self._loss_cache.get(key)
+        if hit is None:
+            v = w.detach().to(device=self._flat.device, dtype=torch.float32).reshape(-1)
+            if v.numel() == 1:
+                v = v.expand(C)
+            if v.numel() != C:
+                raise ValueError("loss weight must have one entry per class")
+            if len(self._loss_cache) > 8:
+                self._loss_cache.clear()
+            hit = self._loss_cache[key] = v.contiguous()
+        return hit
 
     def train_step(self, input_seq, target, hidden=None):
         """One optimisation step = the body of the reference loop (biGRU_model.py:198-210):
@@ -366,9 +375,9 @@ class BiGRU(nn.Module):
                                      _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(logits), None, s), "bigru_forward")
         loss = st["scal"][0:1]
         sq = st["scal"][1:2]
-        _lib.check(lib.bigru_loss(kind, _lib.ptr(logits), _lib.ptr(tgt), _lib.ptr(self._loss_vec(w, C)),
-                                  _lib.ptr(self._loss_vec(pw, C)), B, C, denom, _lib.ptr(loss), _lib.ptr(dlogits), s),
-                   "bigru_loss")
+        wv, pwv = self._loss_vec(w, C), self._loss_vec(pw, C)
+        _lib.check(lib.bigru_loss(kind, _lib.ptr(logits), _lib.ptr(tgt), _lib.ptr(wv), _lib.ptr(pwv), B, C, denom,
+                                  _lib.ptr(loss), _lib.ptr(dlogits), s), "bigru_loss")
         _lib.check(lib.bigru_backward(plan.handle, _lib.ptr(self._flat), _lib.ptr(x), _lib.ptr(h0), *args,
                                       _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(dlogits), _lib.ptr(st["grad"]),
                                       None, None, s), "bigru_backward")

@@ -1,0 +1,180 @@
+// tc_gemm.cuh - bf16 x bf16 -> fp32 GEMM on tcgen05 tensor cores, operands fed by TMA.
+//
+//   D[z][m, n] = sum_k A[a_row_off(z) + m, k] * B[b_row_off(z) + n, k + b_k_off(z)]   (+ bias[n])
+//
+// Both operands are K-major bf16 matrices described by 2-D tensor maps (128B swizzle, box 64 x 128).
+// One 128 x BN output tile per CTA (BN = 128), fp32 accumulator in TMEM, 3-stage smem ring:
+//   warp 0   TMA producer (one elected lane)
+//   warp 1   TMEM allocation + MMA issue (one elected lane, tcgen05.mma cta_group::1, M=128, N=BN, K=16)
+//   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns -> bias -> fp32 / bf16 store or fp32 atomic add
+// grid.z enumerates (batch z, split-K slice).  Out-of-range rows / K are zero-filled by TMA; the epilogue
+// guards m < M, n < N.  A negative or past-the-end K coordinate (b_k_off) reads zeros - used to express
+// the time-shifted h_{t-1} operand of dW_hh without materialising it.
+#pragma once
+#include "tc_common.cuh"
+
+namespace tcg {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;   // 3 x 32 KB: two CTAs per SM, so one tile's
+                                                              // epilogue overlaps the other's main loop
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int THREADS = 192;
+
+enum { OUT_F32 = 0, OUT_BF16 = 1, OUT_ATOMIC_F32 = 2 };
+
+struct Params {
+    int M, N, K;              // K = full reduction length (split across splitk slices)
+    int batch, splitk;
+    int mode;
+    void* C; int64_t ldc;     // row stride in elements
+    int64_t zC;               // element offset of batch z in C
+    int a_row_off[4], b_row_off[4], b_k_off[4];
+    const float* bias;        // per output column n (nullable), batch stride zBias
+    int64_t zBias;
+    unsigned int* dbg;        // watchdog record (nullable)
+};
+
+__global__ void __launch_bounds__(THREADS, 2)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
+    uint64_t* full = bars;                 // [STAGES] TMA -> MMA
+    uint64_t* empty = bars + STAGES;       // [STAGES] MMA -> TMA
+    uint64_t* accum = bars + 2 * STAGES;   // MMA -> epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int z = blockIdx.z / p.splitk, ks = blockIdx.z % p.splitk;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kblocks_total = (p.K + BK - 1) / BK;
+    const int kb_per = (kblocks_total + p.splitk - 1) / p.splitk;
+    const int kb0 = ks * kb_per;
+    const int nkb = max(0, min(kblocks_total, kb0 + kb_per) - kb0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        tc::mbar_init(accum, 1);
+        tc::fence_mbar_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, BN);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            tc::tma_prefetch_desc(&tmA);
+            tc::tma_prefetch_desc(&tmB);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                if (!tc::mbar_wait(&empty[s], ph ^ 1, p.dbg, 0x100 + s)) break;
+                tc::mbar_arrive_expect_tx(&full[s], A_BYTES + B_BYTES);
+                const int k = (kb0 + i) * BK;
+                tc::tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], k, p.a_row_off[z] + m0);
+                tc::tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], k + p.b_k_off[z], p.b_row_off[z] + n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc = tc::umma_idesc_bf16(BM, BN);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                if (!tc::mbar_wait(&full[s], ph, p.dbg, 0x200 + s)) break;
+                tc::tcgen05_fence_after();
+                const uint64_t da = tc::umma_desc_k_sw128(tc::smem_u32(sA + s * A_BYTES));
+                const uint64_t db = tc::umma_desc_k_sw128(tc::smem_u32(sB + s * B_BYTES));
+#pragma unroll
+                for (int kk = 0; kk < BK / 16; ++kk)      // advance 16 bf16 = 32 B = 2 descriptor units
+                    tc::umma_bf16(tmem, da + 2 * kk, db + 2 * kk, idesc, (i | kk) ? 1u : 0u);
+                tc::umma_commit(&empty[s]);               // frees the smem slot when these MMAs retire
+            }
+            tc::umma_commit(accum);
+        }
+    } else {
+        // epilogue warps 2..5 -> TMEM lane quarter = warp % 4
+        const int q = warp & 3;
+        const int m = m0 + q * 32 + lane;
+        bool ok = tc::mbar_wait(accum, 0, p.dbg, 0x300);
+        tc::tcgen05_fence_after();
+        const float* bias = p.bias ? p.bias + z * p.zBias : nullptr;
+        if (ok) {
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                if (nkb > 0) {
+                    tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c * 32, v);
+                    tc::tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0u;
+                }
+                const int nb = n0 + c * 32;
+                if (m < p.M && nb < p.N) {
+                    if (p.mode == OUT_BF16) {
+                        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + z * p.zC + (int64_t)m * p.ldc + nb;
+                        if (nb + 32 <= p.N && (p.ldc % 8 == 0)) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) {
+                                uint32_t w[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float a = __uint_as_float(v[i + 2 * j]), b = __uint_as_float(v[i + 2 * j + 1]);
+                                    if (bias) { a += bias[nb + i + 2 * j]; b += bias[nb + i + 2 * j + 1]; }
+                                    __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                                    w[j] = *reinterpret_cast<uint32_t*>(&h2);
+                                }
+                                *reinterpret_cast<uint4*>(crow + i) = make_uint4(w[0], w[1], w[2], w[3]);
+                            }
+                        } else {
+                            for (int i = 0; i < 32 && nb + i < p.N; ++i) {
+                                float a = __uint_as_float(v[i]);
+                                if (bias) a += bias[nb + i];
+                                crow[i] = __float2bfloat16(a);
+                            }
+                        }
+                    } else {
+                        float* crow = reinterpret_cast<float*>(p.C) + z * p.zC + (int64_t)m * p.ldc + nb;
+                        for (int i = 0; i < 32 && nb + i < p.N; ++i) {
+                            float a = __uint_as_float(v[i]);
+                            if (bias && ks == 0) a += bias[nb + i];
+                            if (p.mode == OUT_ATOMIC_F32) atomicAdd(crow + i, a);
+                            else crow[i] = a;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem, BN);
+}
+
+// K-major bf16 matrix [rows, K] with row stride ld (elements) -> 2-D map, box 64(K) x 128(rows)
+static inline int make_operand_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t K, uint64_t ld) {
+    const uint64_t dims[2] = {K, rows};
+    const uint64_t strides[1] = {ld * 2};
+    const uint32_t box[2] = {(uint32_t)BK, 128u};
+    return make_tmap_bf16(m, base, 2, dims, strides, box);
+}
+
+static inline cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.batch * p.splitk);
+    gemm_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
+    return cudaGetLastError();
+}
+
+}  // namespace tcg

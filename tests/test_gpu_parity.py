@@ -15,8 +15,10 @@ from oracle import loader_oracle as lo
 pytestmark = pytest.mark.gpu
 
 # fp32 path: logits <= 1e-4 rel (BASELINE.json north_star); gradients rel-L2 <= 1e-3
-TOL = {"fp32": dict(logits=1e-4, grads=1e-3, kat=1e-5, step=2e-5),
-       "bf16": dict(logits=3e-2, grads=6e-2, kat=3e-2, step=2e-3)}
+# step: Adam divides by |g| so elements with |g| ~ eps flip freely; bound the element error by a
+# fraction of lr (1e-3) and the whole update by rel-L2
+TOL = {"fp32": dict(logits=1e-4, grads=1e-3, kat=1e-5, step=2e-4, update=2e-2),
+       "bf16": dict(logits=3e-2, grads=6e-2, kat=3e-2, step=2e-3, update=0.5)}
 
 
 def _pkg():
@@ -131,8 +133,12 @@ def test_golden_fused_train_step(golden_dir, name):
         assert rel(logits.cpu().numpy(), z["logits"]) < tol["logits"]
         gn = float(torch.sqrt(m._adam["scal"][1]))
         assert abs(gn - float(z["grad_norm"])) < tol["grads"] * float(z["grad_norm"])
+        upd_got, upd_ref = [], []
         for k, v in m.state_dict().items():
             assert np.abs(v.cpu().numpy() - z["q:" + k]).max() < tol["step"], (precision, k)
+            upd_got.append((v.cpu().numpy() - z["p:" + k]).ravel())
+            upd_ref.append((z["q:" + k] - z["p:" + k]).ravel())
+        assert rel_l2(np.concatenate(upd_got), np.concatenate(upd_ref)) < tol["update"], precision
 
 
 SWEEP = [  # B, T, F, H, L, C, bidir, h0

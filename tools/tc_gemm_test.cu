@@ -1,0 +1,94 @@
+// Stand-alone bring-up test of the tcgen05/TMA GEMM (run on the GPU box):  tools/_bin/tc_gemm_test
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include "../financial_market_data_analysis_b200/csrc/tc_gemm.cuh"
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); return 1; } } while (0)
+
+static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+static int run_case(int M, int N, int K, int mode, int splitk, int kshift, bool use_bias, int a_off, int b_off) {
+    const int Arows = M + a_off, Brows = N + b_off;
+    std::vector<float> A((size_t)Arows * K), B((size_t)Brows * K), bias(N);
+    srand(M * 31 + N * 7 + K);
+    for (auto& v : A) v = bf((rand() % 2001 - 1000) / 1000.f);
+    for (auto& v : B) v = bf((rand() % 2001 - 1000) / 1000.f);
+    for (auto& v : bias) v = (rand() % 2001 - 1000) / 500.f;
+    std::vector<__nv_bfloat16> Ah(A.size()), Bh(B.size());
+    for (size_t i = 0; i < A.size(); ++i) Ah[i] = __float2bfloat16(A[i]);
+    for (size_t i = 0; i < B.size(); ++i) Bh[i] = __float2bfloat16(B[i]);
+    __nv_bfloat16 *dA, *dB; float* dbias; void* dC; unsigned int* dbg;
+    CK(cudaMalloc(&dA, Ah.size() * 2)); CK(cudaMalloc(&dB, Bh.size() * 2)); CK(cudaMalloc(&dbias, N * 4));
+    CK(cudaMalloc(&dC, (size_t)M * N * 4)); CK(cudaMalloc(&dbg, 64));
+    CK(cudaMemcpy(dA, Ah.data(), Ah.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, Bh.data(), Bh.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dbias, bias.data(), N * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dC, 0, (size_t)M * N * 4)); CK(cudaMemset(dbg, 0, 64));
+    CUtensorMap tA, tB;
+    if (tcg::make_operand_map(&tA, dA, Arows, K, K) || tcg::make_operand_map(&tB, dB, Brows, K, K)) { printf("tensor map failed\n"); return 1; }
+    tcg::Params p{};
+    p.M = M; p.N = N; p.K = K; p.batch = 1; p.splitk = splitk; p.mode = mode; p.C = dC; p.ldc = N; p.zC = 0;
+    p.a_row_off[0] = a_off; p.b_row_off[0] = b_off; p.b_k_off[0] = kshift; p.bias = use_bias ? dbias : nullptr; p.zBias = 0; p.dbg = dbg;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    CK(tcg::launch(tA, tB, p, 0));
+    CK(cudaDeviceSynchronize());
+    float ms = 0.f;
+    if (mode != tcg::OUT_ATOMIC_F32) {
+        cudaEventRecord(e0);
+        for (int i = 0; i < 5; ++i) CK(tcg::launch(tA, tB, p, 0));
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
+    }
+    unsigned int h[8]; CK(cudaMemcpy(h, dbg, 32, cudaMemcpyDeviceToHost));
+    std::vector<float> C((size_t)M * N);
+    if (mode == tcg::OUT_BF16) {
+        std::vector<__nv_bfloat16> Cb((size_t)M * N);
+        CK(cudaMemcpy(Cb.data(), dC, Cb.size() * 2, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < C.size(); ++i) C[i] = __bfloat162float(Cb[i]);
+    } else CK(cudaMemcpy(C.data(), dC, C.size() * 4, cudaMemcpyDeviceToHost));
+    // reference on a sample of entries (all for small problems)
+    double maxerr = 0, maxref = 0; long checked = 0;
+    const long total = (long)M * N; const long stride = total > 400000 ? total / 200003 : 1;
+    for (long idx = 0; idx < total; idx += stride) {
+        const int m = idx / N, n = idx % N;
+        double s = 0;
+        for (int k = 0; k < K; ++k) {
+            const int kb = k + kshift;
+            if (kb < 0 || kb >= K) continue;
+            s += (double)A[(size_t)(m + a_off) * K + k] * B[(size_t)(n + b_off) * K + kb];
+        }
+        if (use_bias) s += bias[n];
+        const double err = fabs(s - C[idx]);
+        if (err > maxerr) maxerr = err;
+        if (fabs(s) > maxref) maxref = fabs(s);
+        ++checked;
+    }
+    const double tol = mode == tcg::OUT_BF16 ? 1e-2 * (maxref + 1) : 2e-4 * (maxref + 1);
+    const bool pass = h[0] == 0 && maxerr < tol;
+    printf("%s M=%d N=%d K=%d mode=%d splitk=%d kshift=%d bias=%d off=(%d,%d): maxerr=%.3e (ref max %.2f, %ld checked) dbg=%x/%u/%u  %.3f ms %.1f TFLOP/s\n",
+           pass ? "PASS" : "FAIL", M, N, K, mode, splitk, kshift, (int)use_bias, a_off, b_off, maxerr, maxref, checked, h[0], h[1], h[2], ms,
+           ms > 0 ? 2.0 * M * N * K / ms / 1e9 : 0.0);
+    cudaFree(dA); cudaFree(dB); cudaFree(dbias); cudaFree(dC); cudaFree(dbg);
+    return pass ? 0 : 2;
+}
+
+int main() {
+    int bad = 0;
+    bad += run_case(128, 128, 64, tcg::OUT_F32, 1, 0, false, 0, 0);
+    bad += run_case(128, 128, 256, tcg::OUT_F32, 1, 0, true, 0, 0);
+    bad += run_case(256, 384, 512, tcg::OUT_BF16, 1, 0, true, 0, 0);
+    bad += run_case(300, 200, 136, tcg::OUT_F32, 1, 0, true, 0, 0);
+    bad += run_case(300, 200, 136, tcg::OUT_BF16, 1, 0, false, 128, 256);
+    bad += run_case(768, 256, 8192, tcg::OUT_ATOMIC_F32, 8, 0, false, 0, 0);
+    bad += run_case(768, 256, 8192, tcg::OUT_ATOMIC_F32, 16, -512, false, 768, 256);
+    bad += run_case(768, 256, 8192, tcg::OUT_ATOMIC_F32, 16, 512, false, 0, 0);
+    bad += run_case(65536, 1536, 64, tcg::OUT_BF16, 1, 0, true, 0, 0);
+    bad += run_case(65536, 1536, 512, tcg::OUT_BF16, 1, 0, true, 0, 0);
+    bad += run_case(65536, 512, 1536, tcg::OUT_F32, 1, 0, false, 0, 0);
+    bad += run_case(8192, 8192, 8192, tcg::OUT_BF16, 1, 0, false, 0, 0);
+    printf(bad ? "SOME FAILED\n" : "ALL PASSED\n");
+    return bad ? 1 : 0;
+}
