@@ -1,14 +1,388 @@
-// path_bf16.cuh - BIGRU_PREC_BF16: bf16 operands on tcgen05 tensor cores (placeholder until the
-// tensor-core kernels land; requesting the precision fails loudly, it never falls back to fp32).
+// path_bf16.cuh - BIGRU_PREC_BF16: the tensor-core path.
+//   input projections, dX and weight gradients : tc_gemm.cuh  (tcgen05 + TMA, bf16 operands, fp32 accumulate)
+//   recurrences forward / backward              : tc_scan.cuh  (persistent cluster kernels, W_hh resident in smem)
+//   head, loss glue, optimiser                  : the fp32 kernels of kernels_f32.cuh
+// All activations inside this path are TIME-MAJOR (row r = t*B + b) so that one step of one batch tile is a
+// contiguous block of rows.  Supported: H in {128, 256}, B % 16 == 0, F % 8 == 0, no initial hidden state;
+// anything else fails with BIGRU_ERR_UNSUPPORTED (the fp32 path covers the general case).
 #pragma once
 #include "common.cuh"
+#include "kernels_f32.cuh"
+#include "tc_gemm.cuh"
+#include "tc_scan.cuh"
+#include <algorithm>
 
-static int bf16_plan_check(const bigru_plan&) {
-    bigru_set_error("BIGRU_PREC_BF16 path not built into this library yet");
-    return BIGRU_ERR_UNSUPPORTED;
+typedef __nv_bfloat16 bf16_t;
+
+static int bf16_plan_check(const bigru_plan& p) {
+    if ((p.H != 128 && p.H != 256) || p.B % 16 != 0 || p.F % 8 != 0) {
+        bigru_set_error("BIGRU_PREC_BF16 supports hidden_size 128 or 256, batch %% 16 == 0, n_features %% 8 == 0 "
+                        "(got H=%d B=%d F=%d); use BIGRU_PREC_FP32 for other shapes", p.H, p.B, p.F);
+        return BIGRU_ERR_UNSUPPORTED;
+    }
+    return BIGRU_OK;
 }
-static void bf16_workspace(const bigru_plan&, size_t* a, size_t* b) { *a = 0; *b = 0; }
-static int forward_bf16(const bigru_plan&, const float*, const float*, const float*, float, int, int, uint64_t, void*,
-                        void*, float*, float*, cudaStream_t) { return BIGRU_ERR_UNSUPPORTED; }
-static int backward_bf16(const bigru_plan&, const float*, const float*, const float*, float, int, int, uint64_t,
-                         const void*, void*, const float*, float*, float*, float*, cudaStream_t) { return BIGRU_ERR_UNSUPPORTED; }
+
+struct Bf16Layout {            // byte offsets, 1024-aligned
+    size_t Yrow[16], YT[16], G[16], Xrow[16], XT[16];            // stash: activations
+    size_t Wih[16], WihT[16], Wimg[16], WTimg[16], bfold[16], bhn[16];   // stash: packed weights
+    size_t cat, arg, dbg, stash_total;
+    size_t gi, dgiT, dghT, dYa, dYb, dcat, dhinit, scratch_total;
+};
+static inline size_t al(size_t x) { return (x + 1023) & ~(size_t)1023; }
+static Bf16Layout bf16_layout(const bigru_plan& p) {
+    Bf16Layout L{};
+    const size_t R = (size_t)p.B * p.T, DH = (size_t)p.D * p.H, H = p.H, D = p.D;
+    size_t o = 0;
+    for (int l = 0; l < p.L; ++l) {
+        const size_t I = p.in_size(l);
+        L.Yrow[l] = o; o = al(o + R * DH * 2);
+        L.YT[l] = o; o = al(o + R * DH * 2);
+        L.G[l] = o; o = al(o + R * D * 4 * H * 2);
+        L.Xrow[l] = o; o = al(o + R * I * 2);
+        L.XT[l] = o; o = al(o + R * I * 2);
+        L.Wih[l] = o; o = al(o + D * 3 * H * I * 2);
+        L.WihT[l] = o; o = al(o + D * 3 * H * I * 2);
+        L.Wimg[l] = o; o = al(o + D * 3 * H * H * 2);
+        L.WTimg[l] = o; o = al(o + D * 3 * H * H * 2);
+        L.bfold[l] = o; o = al(o + D * 3 * H * 4);
+        L.bhn[l] = o; o = al(o + D * H * 4);
+    }
+    L.cat = o; o = al(o + (size_t)p.B * 3 * H * 4);
+    L.arg = o; o = al(o + (size_t)p.B * H * 4);
+    L.dbg = o; o = al(o + 256);
+    L.stash_total = o;
+    o = 0;
+    const size_t wide = DH > (size_t)p.F ? DH : (size_t)p.F;
+    L.gi = o; o = al(o + R * D * 3 * H * 2);
+    L.dgiT = o; o = al(o + R * D * 3 * H * 2);
+    L.dghT = o; o = al(o + R * D * 3 * H * 2);
+    L.dYa = o; o = al(o + R * wide * 4);
+    L.dYb = o; o = al(o + R * wide * 4);
+    L.dcat = o; o = al(o + (size_t)p.B * 3 * H * 4);
+    L.dhinit = o; o = al(o + D * (size_t)p.B * H * 4);
+    L.scratch_total = o;
+    return L;
+}
+static void bf16_workspace(const bigru_plan& p, size_t* a, size_t* b) {
+    const Bf16Layout L = bf16_layout(p);
+    *a = L.stash_total; *b = L.scratch_total;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// small kernels of this path
+// ---------------------------------------------------------------------------------------------------
+// x fp32 [B][T][F] -> Xrow bf16 [(t*B+b)][F] and XT bf16 [F][(t*B+b)], optional input dropout.
+// 32x32 tiles over (b, f) for a fixed t so that both the row-major and the transposed write coalesce.
+__global__ void cast_x_kernel(const float* __restrict__ x, bf16_t* __restrict__ Xrow, bf16_t* __restrict__ XT,
+                              int B, int T, int F, float pdrop, int spatial, uint64_t seed) {
+    __shared__ float tile[32][33];
+    const int t = blockIdx.z, b0 = blockIdx.y * 32, f0 = blockIdx.x * 32;
+    const int64_t R = (int64_t)T * B;
+    const float scale = pdrop > 0.f ? 1.f / (1.f - pdrop) : 1.f;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int b = b0 + i, f = f0 + threadIdx.x;
+        float v = 0.f;
+        if (b < B && f < F) {
+            v = x[((int64_t)b * T + t) * F + f];
+            if (pdrop > 0.f) {
+                const uint64_t key = spatial ? (uint64_t)b * F + f : ((uint64_t)b * T + t) * F + f;
+                v = bigru_uniform(seed, 0u, key) < pdrop ? 0.f : v * scale;
+            }
+            Xrow[((int64_t)t * B + b) * F + f] = __float2bfloat16(v);
+        }
+        tile[i][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int f = f0 + i, b = b0 + threadIdx.x;
+        if (b < B && f < F) XT[(int64_t)f * R + (int64_t)t * B + b] = __float2bfloat16(tile[threadIdx.x][i]);
+    }
+}
+
+// inter-layer dropout: Yrow -> Xrow (masked) and XT (masked, transposed); rows x cols = R x DH
+__global__ void dropout_rows_kernel(const bf16_t* __restrict__ Y, bf16_t* __restrict__ Xrow, bf16_t* __restrict__ XT,
+                                    int64_t R, int cols, int B, int T, float pdrop, uint64_t seed, uint32_t stream) {
+    const float scale = 1.f / (1.f - pdrop);
+    const int64_t total = R * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cidx = i % cols;
+        const int64_t r = i / cols;
+        const int64_t b = r % B, t = r / B;
+        const uint64_t key = ((uint64_t)b * T + t) * cols + cidx;          // batch-major key, as the fp32 path
+        const float v = bigru_uniform(seed, stream, key) < pdrop ? 0.f : __bfloat162float(Y[i]) * scale;
+        const bf16_t o = __float2bfloat16(v);
+        Xrow[i] = o;
+        XT[(int64_t)cidx * R + r] = o;
+    }
+}
+// gradient of the same dropout, in place on fp32 [R][cols] (time-major rows)
+__global__ void dropout_grad_rows_kernel(float* __restrict__ dX, int64_t R, int cols, int B, int T, float pdrop,
+                                         uint64_t seed, uint32_t stream) {
+    const float scale = 1.f / (1.f - pdrop);
+    const int64_t total = R * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cidx = i % cols;
+        const int64_t r = i / cols;
+        const int64_t b = r % B, t = r / B;
+        const uint64_t key = ((uint64_t)b * T + t) * cols + cidx;
+        dX[i] = bigru_uniform(seed, stream, key) < pdrop ? 0.f : dX[i] * scale;
+    }
+}
+
+// W_ih fp32 [3H][I] of direction d -> Wih bf16 rows d*3H.. of [D*3H][I] and WihT bf16 [I][D*3H]
+__global__ void pack_wih_kernel(const float* __restrict__ w, bf16_t* __restrict__ Wih, bf16_t* __restrict__ WihT,
+                                int H3, int I, int d, int D) {
+    const int64_t total = (int64_t)H3 * I;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = i % I, q = i / I;
+        const bf16_t v = __float2bfloat16(w[i]);
+        Wih[((int64_t)d * H3 + q) * I + k] = v;
+        WihT[(int64_t)k * D * H3 + (int64_t)d * H3 + q] = v;
+    }
+}
+// bias_fold[d*3H + q] = b_ih[q] + (q < 2H ? b_hh[q] : 0);  b_hn[d*H + j] = b_hh[2H + j]
+__global__ void pack_bias_kernel(const float* __restrict__ b_ih, const float* __restrict__ b_hh, float* __restrict__ bfold,
+                                 float* __restrict__ bhn, int H, int d) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= 3 * H) return;
+    bfold[d * 3 * H + q] = b_ih[q] + (q < 2 * H ? b_hh[q] : 0.f);
+    if (q >= 2 * H) bhn[d * H + q - 2 * H] = b_hh[q];
+}
+
+// pooling head on the time-major bf16 output (biGRU_model.py:111-133)
+__global__ void head_pool_tm_kernel(const bf16_t* __restrict__ Y, float* __restrict__ cat, int* __restrict__ arg,
+                                    int B, int T, int H, int D) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)B * H) return;
+    const int j = idx % H, b = idx / H;
+    const int ld = D * H;
+    float last = __bfloat162float(Y[((int64_t)(T - 1) * B + b) * ld + j]);
+    if (D == 2) last += __bfloat162float(Y[(int64_t)b * ld + H + j]);
+    float mx = -INFINITY, sum = 0.f;
+    int am = 0;
+    for (int t = 0; t < T; ++t) {
+        const bf16_t* y = Y + ((int64_t)t * B + b) * ld;
+        float s = __bfloat162float(y[j]);
+        if (D == 2) s += __bfloat162float(y[H + j]);
+        if (s > mx) { mx = s; am = t; }
+        sum += s;
+    }
+    float* c = cat + (int64_t)b * 3 * H;
+    c[j] = last; c[H + j] = mx; c[2 * H + j] = sum / (float)T;
+    arg[idx] = am;
+}
+// dY (time-major fp32 [R][D*H]) of the top layer and the initial dh carry [D][B][H]
+__global__ void head_bwd_dy_tm_kernel(const float* __restrict__ dcat, const int* __restrict__ arg, float* __restrict__ dY,
+                                      float* __restrict__ dhinit, int B, int T, int H, int D) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)B * T * H) return;
+    const int j = idx % H;
+    const int b = (idx / H) % B;
+    const int t = idx / ((int64_t)H * B);
+    const float* dc = dcat + (int64_t)b * 3 * H;
+    const float v = dc[2 * H + j] / (float)T + (arg[(int64_t)b * H + j] == t ? dc[H + j] : 0.f);
+    float* o = dY + ((int64_t)t * B + b) * D * H;
+    o[j] = v;
+    if (D == 2) o[H + j] = v;
+    if (t == 0) {
+        dhinit[(int64_t)b * H + j] = dc[j];
+        if (D == 2) dhinit[((int64_t)B + b) * H + j] = dc[j];
+    }
+}
+// dX of layer 0 from time-major fp32 [R][F] back to the caller's [B][T][F] (+ input-dropout mask)
+__global__ void dx_to_batch_major_kernel(const float* __restrict__ dXtm, float* __restrict__ dx, int B, int T, int F,
+                                         float pdrop, int spatial, uint64_t seed) {
+    const float scale = pdrop > 0.f ? 1.f / (1.f - pdrop) : 1.f;
+    const int64_t total = (int64_t)B * T * F;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int f = i % F;
+        const int64_t bt = i / F;
+        const int64_t t = bt % T, b = bt / T;
+        float v = dXtm[(t * B + b) * F + f];
+        if (pdrop > 0.f) {
+            const uint64_t key = spatial ? (uint64_t)b * F + f : (uint64_t)i;
+            v = bigru_uniform(seed, 0u, key) < pdrop ? 0.f : v * scale;
+        }
+        dx[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GEMM helper with accounting
+// ---------------------------------------------------------------------------------------------------
+static int tc_gemm(const void* A, int64_t a_rows, int64_t lda, const void* Bm, int64_t b_rows, int64_t ldb,
+                   tcg::Params& p, cudaStream_t st) {
+    CUtensorMap tA, tB;
+    if (tcg::make_operand_map(&tA, A, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda) ||
+        tcg::make_operand_map(&tB, Bm, (uint64_t)b_rows, (uint64_t)p.K, (uint64_t)ldb)) {
+        bigru_set_error("cuTensorMapEncodeTiled failed (rows %lld/%lld K %d ld %lld/%lld)", (long long)a_rows,
+                        (long long)b_rows, p.K, (long long)lda, (long long)ldb);
+        return BIGRU_ERR_CUDA;
+    }
+    ProfScope ps(KC_TC_GEMM, 2.0 * p.M * p.N * (double)p.K * p.batch, 0.0, st);
+    CUDA_TRY(tcg::launch(tA, tB, p, st));
+    return BIGRU_OK;
+}
+
+static inline unsigned nblk2(int64_t n, int bs) { return (unsigned)cdiv64(n, bs); }
+
+// ---------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------
+static int forward_bf16(const bigru_plan& p, const float* params, const float* x, const float* h0, float drop,
+                        int spatial, int training, uint64_t seed, void* stash_v, void* scratch_v, float* logits,
+                        float* hn, cudaStream_t st) {
+    if (h0) { bigru_set_error("BIGRU_PREC_BF16: an initial hidden state is not supported; use BIGRU_PREC_FP32"); return BIGRU_ERR_UNSUPPORTED; }
+    const Bf16Layout L = bf16_layout(p);
+    uint8_t* S = (uint8_t*)stash_v;
+    uint8_t* W = (uint8_t*)scratch_v;
+    const int B = p.B, T = p.T, H = p.H, D = p.D, F = p.F;
+    const int64_t R = (int64_t)B * T;
+    const bool do_drop = training && drop > 0.f;
+    unsigned int* dbg = (unsigned int*)(S + L.dbg);
+    CUDA_TRY(cudaMemsetAsync(dbg, 0, 64, st));
+
+    // 1. pack weights to bf16 operand images
+    for (int l = 0; l < p.L; ++l) {
+        const int I = (int)p.in_size(l);
+        for (int d = 0; d < D; ++d) {
+            KLAUNCH(KC_PACK, 0.0, 0.0, st, pack_wih_kernel<<<148, 256, 0, st>>>(params + p.off_wih(l, d), (bf16_t*)(S + L.Wih[l]),
+                                                                               (bf16_t*)(S + L.WihT[l]), 3 * H, I, d, D));
+            KLAUNCH(KC_PACK, 0.0, 0.0, st, tcs::pack_whh_image_kernel<<<148, 256, 0, st>>>(
+                                               params + p.off_whh(l, d), (bf16_t*)(S + L.Wimg[l]) + (size_t)d * 3 * H * H, H));
+            KLAUNCH(KC_PACK, 0.0, 0.0, st, tcs::pack_whhT_image_kernel<<<148, 256, 0, st>>>(
+                                               params + p.off_whh(l, d), (bf16_t*)(S + L.WTimg[l]) + (size_t)d * 3 * H * H, H));
+            KLAUNCH(KC_PACK, 0.0, 0.0, st, pack_bias_kernel<<<nblk2(3 * H, 128), 128, 0, st>>>(
+                                               params + p.off_bih(l, d), params + p.off_bhh(l, d), (float*)(S + L.bfold[l]),
+                                               (float*)(S + L.bhn[l]), H, d));
+        }
+    }
+    // 2. layer-0 input: cast + transpose (+ input dropout)
+    {
+        dim3 grid((F + 31) / 32, (B + 31) / 32, T);
+        KLAUNCH(KC_PACK, 0.0, 6.0 * R * F, st, cast_x_kernel<<<grid, dim3(32, 8), 0, st>>>(
+                                                   x, (bf16_t*)(S + L.Xrow[0]), (bf16_t*)(S + L.XT[0]), B, T, F,
+                                                   do_drop ? drop : 0.f, spatial, seed));
+    }
+    for (int l = 0; l < p.L; ++l) {
+        const int I = (int)p.in_size(l);
+        const bf16_t* Xrow = (const bf16_t*)(S + L.Xrow[l]);
+        if (l > 0) {
+            if (do_drop) {
+                KLAUNCH(KC_MISC, 0.0, 0.0, st, dropout_rows_kernel<<<148 * 8, 256, 0, st>>>(
+                                                   (const bf16_t*)(S + L.Yrow[l - 1]), (bf16_t*)(S + L.Xrow[l]),
+                                                   (bf16_t*)(S + L.XT[l]), R, I, B, T, drop, seed, (uint32_t)l));
+            } else {
+                Xrow = (const bf16_t*)(S + L.Yrow[l - 1]);
+            }
+        }
+        // 3. input projection for all t, both directions:  gi[R][D*3H] = X W_ih^T + bias
+        tcg::Params g{};
+        g.M = (int)R; g.N = D * 3 * H; g.K = I; g.batch = 1; g.splitk = 1; g.mode = tcg::OUT_BF16;
+        g.C = W + L.gi; g.ldc = D * 3 * H; g.bias = (const float*)(S + L.bfold[l]); g.dbg = dbg;
+        TRY(tc_gemm(Xrow, R, I, S + L.Wih[l], D * 3 * H, I, g, st));
+        // 4. recurrence
+        tcs::FwdParams f{};
+        f.B = B; f.T = T; f.H = H; f.D = D;
+        f.Wimg = (const bf16_t*)(S + L.Wimg[l]); f.gi = (const bf16_t*)(W + L.gi); f.b_hn = (const float*)(S + L.bhn[l]);
+        f.Yrow = (bf16_t*)(S + L.Yrow[l]); f.YT = (bf16_t*)(S + L.YT[l]); f.G = (bf16_t*)(S + L.G[l]);
+        f.hn_out = hn ? hn + (int64_t)l * D * B * H : nullptr; f.dbg = dbg;
+        {
+            ProfScope ps(KC_TC_SCAN_FWD, 2.0 * 3 * H * H * (double)R * D, 0.0, st);
+            CUDA_TRY(tcs::launch_fwd(f, st));
+        }
+    }
+    // 5. head
+    KLAUNCH(KC_HEAD, 0.0, 0.0, st, head_pool_tm_kernel<<<nblk2((int64_t)B * H, 128), 128, 0, st>>>(
+                                       (const bf16_t*)(S + L.Yrow[p.L - 1]), (float*)(S + L.cat), (int*)(S + L.arg), B, T, H, D));
+    GemmArgs lin = gemm_args((const float*)(S + L.cat), params + p.off_linw(), logits, B, p.C, 3 * H, 3 * H, 1, 3 * H, 1, p.C);
+    lin.bias = params + p.off_linb();
+    TRY(sgemm_launch(lin, st));
+    return BIGRU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------------
+static int backward_bf16(const bigru_plan& p, const float* params, const float* x, const float* h0, float drop,
+                         int spatial, int training, uint64_t seed, const void* stash_v, void* scratch_v,
+                         const float* dlogits, float* grads, float* dx, float* dh0, cudaStream_t st) {
+    (void)x;
+    if (h0 || dh0) { bigru_set_error("BIGRU_PREC_BF16: initial hidden state / its gradient are not supported"); return BIGRU_ERR_UNSUPPORTED; }
+    const Bf16Layout L = bf16_layout(p);
+    const uint8_t* S = (const uint8_t*)stash_v;
+    uint8_t* W = (uint8_t*)scratch_v;
+    const int B = p.B, T = p.T, H = p.H, D = p.D, C = p.C;
+    const int64_t R = (int64_t)B * T;
+    const bool do_drop = training && drop > 0.f;
+    unsigned int* dbg = (unsigned int*)(const_cast<uint8_t*>(S) + L.dbg);
+    CUDA_TRY(cudaMemsetAsync(grads, 0, sizeof(float) * p.nparams, st));
+    float* dcat = (float*)(W + L.dcat);
+    const float* cat = (const float*)(S + L.cat);
+    GemmArgs a = gemm_args(dlogits, params + p.off_linw(), dcat, B, 3 * H, C, C, 1, 1, 3 * H, 3 * H);
+    TRY(sgemm_launch(a, st));
+    GemmArgs w = gemm_args(dlogits, cat, grads + p.off_linw(), C, 3 * H, B, 1, C, 1, 3 * H, 3 * H);
+    TRY(sgemm_launch(w, st));
+    TRY(colsum_launch(dlogits, grads + p.off_linb(), B, C, C, 1, 0, 0, st));
+    float* dY = (float*)(W + L.dYa);
+    float* dYnext = (float*)(W + L.dYb);
+    float* dhinit = (float*)(W + L.dhinit);
+    KLAUNCH(KC_HEAD, 0.0, 0.0, st, head_bwd_dy_tm_kernel<<<nblk2(R * H, 256), 256, 0, st>>>(dcat, (const int*)(S + L.arg), dY,
+                                                                                           dhinit, B, T, H, D));
+    for (int l = p.L - 1; l >= 0; --l) {
+        const int I = (int)p.in_size(l);
+        // 1. BPTT scan
+        tcs::BwdParams b{};
+        b.B = B; b.T = T; b.H = H; b.D = D;
+        b.WTimg = (const bf16_t*)(S + L.WTimg[l]); b.G = (const bf16_t*)(S + L.G[l]); b.Yrow = (const bf16_t*)(S + L.Yrow[l]);
+        b.dY = dY; b.dh_init = l == p.L - 1 ? dhinit : nullptr;
+        b.dgi_row = (bf16_t*)(W + L.gi); b.dgiT = (bf16_t*)(W + L.dgiT); b.dghT = (bf16_t*)(W + L.dghT);
+        b.db_ih = grads + p.off_bih(l, 0); b.db_hh = grads + p.off_bhh(l, 0); b.dir_stride = p.ld_block(l); b.dbg = dbg;
+        {
+            ProfScope ps(KC_TC_SCAN_BWD, 2.0 * 3 * H * H * (double)R * D, 0.0, st);
+            CUDA_TRY(tcs::launch_bwd(b, st));
+        }
+        // layer input as the projection saw it
+        const bool dropped = do_drop && (l == 0 || p.L > 1);
+        const bf16_t* XT = (l == 0 || dropped) ? (const bf16_t*)(S + L.XT[l]) : (const bf16_t*)(S + L.YT[l - 1]);
+        // 2. dW_ih[d] = dgi[d]^T X   (M=3H, N=I, K=R), both directions in one launch, split-K + fp32 atomics
+        {
+            tcg::Params g{};
+            g.M = 3 * H; g.N = I; g.K = (int)R; g.batch = D; g.mode = tcg::OUT_ATOMIC_F32;
+            const int tiles = ((3 * H + 127) / 128) * ((I + 127) / 128) * D;
+            g.splitk = (int)std::max<int64_t>(1, std::min<int64_t>((R + 63) / 64, (148 * 3 + tiles - 1) / tiles));
+            g.C = grads + p.off_wih(l, 0); g.ldc = I; g.zC = p.ld_block(l);
+            for (int d = 0; d < D; ++d) { g.a_row_off[d] = d * 3 * H; g.b_row_off[d] = 0; g.b_k_off[d] = 0; }
+            g.dbg = dbg;
+            TRY(tc_gemm(W + L.dgiT, (int64_t)D * 3 * H, R, XT, I, R, g, st));
+        }
+        // 3. dW_hh[d] = dgh[d]^T H_prev  with H_prev(t) = Y(t-1) (dir 0) / Y(t+1) (dir 1): a K-coordinate shift of
+        //    +-B rows on the transposed output; out-of-range columns read as zero (h_prev = 0 at the first step)
+        {
+            tcg::Params g{};
+            g.M = 3 * H; g.N = H; g.K = (int)R; g.batch = D; g.mode = tcg::OUT_ATOMIC_F32;
+            const int tiles = ((3 * H + 127) / 128) * ((H + 127) / 128) * D;
+            g.splitk = (int)std::max<int64_t>(1, std::min<int64_t>((R + 63) / 64, (148 * 3 + tiles - 1) / tiles));
+            g.C = grads + p.off_whh(l, 0); g.ldc = H; g.zC = p.ld_block(l);
+            for (int d = 0; d < D; ++d) { g.a_row_off[d] = d * 3 * H; g.b_row_off[d] = d * H; g.b_k_off[d] = d == 0 ? -B : B; }
+            g.dbg = dbg;
+            TRY(tc_gemm(W + L.dghT, (int64_t)D * 3 * H, R, S + L.YT[l], (int64_t)D * H, R, g, st));
+        }
+        // 4. dX = dgi_row [R][D*3H] x W_ih (both directions concatenated along K)
+        const bool need_dx = l > 0 || dx != nullptr;
+        if (need_dx) {
+            tcg::Params g{};
+            g.M = (int)R; g.N = I; g.K = D * 3 * H; g.batch = 1; g.splitk = 1; g.mode = tcg::OUT_F32;
+            g.C = dYnext; g.ldc = I; g.dbg = dbg;
+            TRY(tc_gemm(W + L.gi, R, (int64_t)D * 3 * H, S + L.WihT[l], I, (int64_t)D * 3 * H, g, st));
+            if (l > 0 && dropped)
+                KLAUNCH(KC_MISC, 0.0, 0.0, st, dropout_grad_rows_kernel<<<148 * 8, 256, 0, st>>>(dYnext, R, I, B, T, drop, seed, (uint32_t)l));
+            if (l == 0)
+                KLAUNCH(KC_MISC, 0.0, 0.0, st, dx_to_batch_major_kernel<<<148 * 8, 256, 0, st>>>(dYnext, dx, B, T, I,
+                                                                                            do_drop ? drop : 0.f, spatial, seed));
+        }
+        float* tmp = dY; dY = dYnext; dYnext = tmp;
+    }
+    return BIGRU_OK;
+}

@@ -7,7 +7,7 @@
 #include <cstdint>
 
 #ifndef BIGRU_SPIN_LIMIT
-#define BIGRU_SPIN_LIMIT (1u << 24)     // bounded waits: a protocol bug reports instead of hanging the GPU
+#define BIGRU_SPIN_LIMIT (1u << 22)     // bounded waits: a protocol bug reports instead of hanging the GPU
 #endif
 
 namespace tc {

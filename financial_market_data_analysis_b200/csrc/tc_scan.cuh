@@ -1,0 +1,479 @@
+// tc_scan.cuh - persistent GRU recurrence on tcgen05 tensor cores (bf16 operands, fp32 accumulate/state).
+//
+// One thread-block CLUSTER walks all T steps of one (direction, 16-row batch tile).  The cluster has
+// CS = H/128 CTAs; CTA c owns hidden units [128c, 128c+128) and keeps its slice of W_hh (3 gates x 128
+// rows x H, bf16, 128B-swizzled K-major = 192 KB at H=256) RESIDENT in shared memory for the whole scan.
+// Per step ("swap-AB": weights are the M side, the batch tile is the N=16 side):
+//     D_g[unit, b] = sum_k W_hg[unit, k] * h_{t-1}[b, k]        g in {r, z, n}   (tcgen05.mma M=128 N=16 K=16)
+// accumulators live in TMEM (3 x 16 columns); 8 epilogue warps read them back (tcgen05.ld), add the
+// precomputed input projection gi (bf16, bias folded), apply sigmoid/tanh and the state update with the
+// fp32 state held in registers, and write the new h (bf16) straight into the UMMA operand tile of the
+// next step - locally with st.shared and into every peer CTA with one cp.async.bulk (DSMEM) that
+// completes on the peer's mbarrier.  h never goes through HBM on the critical path; what is streamed out
+// per step is the layer output (row-major and transposed, for the next layer's GEMMs) and the gate stash.
+//
+// Layouts (time-major rows r = t*B + b, R = T*B):
+//   gi   bf16 [R][D*3H]   input projection incl. b_ih (+ b_hh for r,z)        (read)
+//   Yrow bf16 [R][D*H]    layer output                                        (written)
+//   YT   bf16 [D*H][R]    layer output transposed (wgrad operand)             (written)
+//   G    bf16 [R][D*4H]   r, z, n, hn = W_hn h + b_hn  (stash for backward)   (written)
+//   Wimg bf16 [D][CS][3][H/64][128 rows][64]  swizzled smem images of W_hh    (read once)
+#pragma once
+#include "tc_common.cuh"
+
+namespace tcs {
+
+constexpr int NB = 16;            // batch rows per tile = UMMA N
+constexpr int UNITS = 128;        // hidden units per CTA = UMMA M
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = (EPI_WARPS + 2) * 32;    // + MMA/control warp + loader warp
+constexpr int W_CHUNK = UNITS * 128;             // bytes of one [128 x 64] bf16 chunk
+constexpr int H_CHUNK = NB * 128;                // bytes of one [16 x 64] bf16 chunk
+
+__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7) : "r"(taddr) : "memory");
+    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+    v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
+}
+
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
+
+static inline size_t fwd_smem_bytes(int H) {
+    const int KC = H / 64;
+    return (size_t)3 * KC * W_CHUNK + (size_t)2 * KC * H_CHUNK + 1024 + 256;
+}
+
+struct FwdParams {
+    int B, T, H, D;
+    const __nv_bfloat16* Wimg;
+    const __nv_bfloat16* gi;
+    const float* b_hn;            // [D][H]
+    __nv_bfloat16* Yrow;
+    __nv_bfloat16* YT;
+    __nv_bfloat16* G;
+    float* hn_out;                // [D][B][H] fp32, nullable
+    unsigned int* dbg;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int H = p.H, KC = H / 64, CS = H / UNITS, B = p.B, T = p.T, D = p.D;
+    uint8_t* sW = smem;                                    // [3][KC][W_CHUNK]
+    uint8_t* sH = smem + (size_t)3 * KC * W_CHUNK;         // [2][KC][H_CHUNK]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sH + (size_t)2 * KC * H_CHUNK);
+    uint64_t* w_full = bars;
+    uint64_t* h_full = bars + 1;       // [2]
+    uint64_t* mma_done = bars + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t c = CS > 1 ? tc::cluster_ctarank() : 0u;
+    const int cluster_id = blockIdx.x / CS;
+    const int ntiles = B / NB;
+    const int d = cluster_id / ntiles, tile = cluster_id % ntiles;
+    const int64_t R = (int64_t)T * B;
+
+    if (threadIdx.x == 0) {
+        tc::mbar_init(w_full, 1);
+        tc::mbar_init(&h_full[0], 2);
+        tc::mbar_init(&h_full[1], 2);
+        tc::mbar_init(mma_done, 1);
+        tc::fence_mbar_init();
+    }
+    if (warp == EPI_WARPS) tc::tmem_alloc(tmem_slot, 64);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (CS > 1) tc::cluster_sync_all();        // every CTA's barriers exist before any peer signals them
+    tc::tcgen05_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t chunk_bytes_mine = (uint32_t)(UNITS / 64) * H_CHUNK;    // the 2 K-chunks this CTA produces
+
+    if (warp == EPI_WARPS + 1) {
+        // ---- loader: W_hh slice image -> smem (bulk TMA copies, 16 KB each)
+        if (tc::elect_one()) {
+            const uint32_t total = (uint32_t)(3 * KC * W_CHUNK);
+            tc::mbar_arrive_expect_tx(w_full, total);
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Wimg) + ((size_t)d * CS + c) * total;
+            for (int i = 0; i < 3 * KC; ++i) tc::bulk_g2s(sW + (size_t)i * W_CHUNK, src + (size_t)i * W_CHUNK, W_CHUNK, w_full);
+        }
+    } else if (warp == EPI_WARPS) {
+        // ---- MMA issuer
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc = tc::umma_idesc_bf16(UNITS, NB);
+            bool ok = tc::mbar_wait(w_full, 0, p.dbg, 0x400);
+            for (int s = 0; s < T; ++s) {                  // after a watchdog hit: keep signalling, stop waiting
+                if (CS > 1) tc::mbar_arrive_expect_tx(&h_full[s & 1], (uint32_t)(CS - 1) * chunk_bytes_mine);
+                else tc::mbar_arrive(&h_full[s & 1]);
+                if (s == 0) continue;                      // h_{-1} = 0: nothing to multiply
+                const int pb = (s - 1) & 1;
+                if (ok) ok = tc::mbar_wait_cluster(&h_full[pb], ((s - 1) >> 1) & 1, p.dbg, 0x500 + (s & 0xff));
+                tc::tcgen05_fence_after();
+                const uint32_t hb = tc::smem_u32(sH + (size_t)pb * KC * H_CHUNK);
+                const uint32_t wb = tc::smem_u32(sW);
+#pragma unroll 1
+                for (int g = 0; g < 3; ++g) {
+#pragma unroll 1
+                    for (int kc = 0; kc < KC; ++kc) {
+                        const uint64_t da = tc::umma_desc_k_sw128(wb + (uint32_t)(g * KC + kc) * W_CHUNK);
+                        const uint64_t db = tc::umma_desc_k_sw128(hb + (uint32_t)kc * H_CHUNK);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            tc::umma_bf16(tmem + g * NB, da + 2 * kk, db + 2 * kk, idesc, (kc | kk) ? 1u : 0u);
+                    }
+                }
+                tc::umma_commit(mma_done);
+            }
+        }
+    } else {
+        // ---- epilogue: thread = hidden unit (TMEM lane), 8 of the 16 batch columns
+        const int q = warp & 3, half = warp >> 2;
+        const int j = q * 32 + lane;
+        const int unit = (int)c * UNITS + j;
+        const int col0 = half * 8;
+        const float bhn = p.b_hn[d * H + unit];
+        const int ldgi = D * 3 * H, ldy = D * H, ldg = D * 4 * H;
+        float hprev[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hprev[i] = 0.f;
+        bool ok = true;
+        for (int s = 0; s < T; ++s) {
+            const int t = d == 0 ? s : T - 1 - s;
+            const int64_t row0 = (int64_t)t * B + tile * NB + col0;
+            float gr[8], gz[8], gn[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const __nv_bfloat16* gp = p.gi + (row0 + i) * ldgi + d * 3 * H + unit;
+                gr[i] = __bfloat162float(gp[0]); gz[i] = __bfloat162float(gp[H]); gn[i] = __bfloat162float(gp[2 * H]);
+            }
+            float ar[8], az[8], an[8];
+            if (s > 0) {
+                if (ok) ok = tc::mbar_wait(mma_done, (s - 1) & 1, p.dbg, 0x600 + (s & 0xff));
+                tc::tcgen05_fence_after();
+                const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + col0;
+                tmem_ld8(ta, ar); tmem_ld8(ta + NB, az); tmem_ld8(ta + 2 * NB, an);
+                tc::tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { ar[i] = 0.f; az[i] = 0.f; an[i] = 0.f; }
+            }
+            const int buf = s & 1;
+            uint8_t* hb = sH + (size_t)buf * KC * H_CHUNK + (size_t)(unit >> 6) * H_CHUNK;
+            __nv_bfloat16 hv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float r = sigmoid_fast(gr[i] + ar[i]);
+                const float z = sigmoid_fast(gz[i] + az[i]);
+                const float hn = an[i] + bhn;
+                const float n = tanh_fast(fmaf(r, hn, gn[i]));
+                const float h = fmaf(z, hprev[i] - n, n);
+                hprev[i] = h;
+                hv[i] = __float2bfloat16(h);
+                *reinterpret_cast<__nv_bfloat16*>(hb + tc::sw128_offset(col0 + i, unit & 63)) = hv[i];
+                p.Yrow[(row0 + i) * ldy + d * H + unit] = hv[i];
+                __nv_bfloat16* gs = p.G + (row0 + i) * ldg + d * 4 * H + unit;
+                gs[0] = __float2bfloat16(r); gs[H] = __float2bfloat16(z); gs[2 * H] = __float2bfloat16(n);
+                gs[3 * H] = __float2bfloat16(hn);
+            }
+            *reinterpret_cast<uint4*>(p.YT + (int64_t)(d * H + unit) * R + row0) = *reinterpret_cast<uint4*>(hv);
+            if (s == T - 1 && p.hn_out) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) p.hn_out[((int64_t)d * B + tile * NB + col0 + i) * H + unit] = hprev[i];
+            }
+            // publish h_t: local tile first (generic -> async proxy), then the peers via DSMEM bulk copies
+            tc::tcgen05_fence_before();
+            tc::fence_proxy_async_smem();
+            epi_barrier();
+            if (threadIdx.x == 0 && s + 1 < T) {
+                tc::mbar_arrive(&h_full[buf]);
+                uint8_t* mine = sH + (size_t)buf * KC * H_CHUNK + (size_t)c * chunk_bytes_mine;
+                for (uint32_t peer = 0; peer < (uint32_t)CS; ++peer)
+                    if (peer != c) tc::bulk_s2cluster(mine, mine, chunk_bytes_mine, &h_full[buf], peer);
+            }
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (CS > 1) tc::cluster_sync_all();        // no CTA leaves while a peer may still target its smem
+    if (warp == EPI_WARPS) tc::tmem_dealloc(tmem, 64);
+}
+
+static inline cudaError_t launch_fwd(const FwdParams& p, cudaStream_t st) {
+    const int CS = p.H / UNITS;
+    const size_t smem = fwd_smem_bytes(p.H);
+    static size_t attr = 0;
+    if (attr < smem) {
+        cudaError_t e = cudaFuncSetAttribute(gru_scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = smem;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(p.D * (p.B / NB) * CS));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gru_scan_fwd_kernel, p);
+}
+
+// ---- weight image: W_hh fp32 [3H][H] (rows r|z|n) -> Wimg[c][g][kc][unit row][64] bf16, 128B-swizzled
+__global__ void pack_whh_image_kernel(const float* __restrict__ w_hh, __nv_bfloat16* __restrict__ img, int H) {
+    const int KC = H / 64, CS = H / UNITS;
+    const int64_t total = (int64_t)3 * H * H;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = i % H;
+        const int row = i / H;                 // g*H + unit
+        const int g = row / H, unit = row % H;
+        const int c = unit / UNITS, jr = unit % UNITS, kc = k / 64;
+        const size_t chunk = (((size_t)c * 3 + g) * KC + kc) * W_CHUNK;
+        *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(img) + chunk + tc::sw128_offset(jr, k & 63)) =
+            __float2bfloat16(w_hh[i]);
+    }
+    (void)CS;
+}
+
+
+// =================================================================================================
+// Backward scan (BPTT).  Same cluster / tiling; the resident operand is W_hh^T (A[unit k][q] = W_hh[q][k],
+// 128 rows x 3H, 192 KB at H=256) and the per-step product is
+//     D'[k, b] = sum_q W_hh[q, k] * dgh_{s-1}[b, q]                    (tcgen05.mma M=128 N=16, K = 3H)
+// i.e. the recurrent part of dh.  The epilogue thread of hidden unit k adds dY_t and the z-carry, forms the
+// gate derivatives from the stash, writes its three dgh values (bf16) into the [16 x 3H] operand tile of
+// the next step (locally + DSMEM bulk copy to the peers) and streams out dgi / dgh in row-major and
+// transposed form for the weight-gradient GEMMs; bias gradients accumulate in registers over all steps.
+// The operand tile is single-buffered (24 KB): a peer may only overwrite it after this CTA's MMA of the
+// current step has retired, which the epilogue leader signals with a remote mbarrier arrive.
+//   G, Yrow (h_{t-1}), dY fp32 [R][D*H]                                         (read)
+//   dgi_row bf16 [R][D*3H], dgiT / dghT bf16 [D*3H][R]                          (written)
+// =================================================================================================
+static inline size_t bwd_smem_bytes(int H) {
+    const int KC3 = 3 * H / 64;
+    return (size_t)KC3 * W_CHUNK + (size_t)KC3 * H_CHUNK + 1024 + 256;
+}
+
+struct BwdParams {
+    int B, T, H, D;
+    const __nv_bfloat16* WTimg;     // [D][CS][3H/64][128][64] swizzled images of W_hh^T slices
+    const __nv_bfloat16* G;
+    const __nv_bfloat16* Yrow;
+    const float* dY;                // [R][D*H]
+    const float* dh_init;           // [D][B][H] nullable: d(last hidden) of the top layer
+    __nv_bfloat16* dgi_row;
+    __nv_bfloat16* dgiT;
+    __nv_bfloat16* dghT;
+    float* db_ih;                   // grads of b_ih for direction 0; direction d at + d*dir_stride
+    float* db_hh;
+    int64_t dir_stride;
+    unsigned int* dbg;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int H = p.H, KC = H / 64, KC3 = 3 * KC, CS = H / UNITS, B = p.B, T = p.T, D = p.D;
+    uint8_t* sW = smem;                                    // [KC3][W_CHUNK]
+    uint8_t* sD = smem + (size_t)KC3 * W_CHUNK;            // [KC3][H_CHUNK]  dgh tile
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sD + (size_t)KC3 * H_CHUNK);
+    uint64_t* w_full = bars;
+    uint64_t* d_full = bars + 1;       // [2] alternate by step parity (same buffer)
+    uint64_t* mma_done = bars + 3;
+    uint64_t* peer_ready = bars + 4;   // [2] peers' "my MMA of step s retired, you may overwrite my tile"
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t c = CS > 1 ? tc::cluster_ctarank() : 0u;
+    const int cluster_id = blockIdx.x / CS;
+    const int ntiles = B / NB;
+    const int d = cluster_id / ntiles, tile = cluster_id % ntiles;
+    const int64_t R = (int64_t)T * B;
+
+    if (threadIdx.x == 0) {
+        tc::mbar_init(w_full, 1);
+        tc::mbar_init(&d_full[0], 2);
+        tc::mbar_init(&d_full[1], 2);
+        tc::mbar_init(mma_done, 1);
+        tc::mbar_init(&peer_ready[0], CS > 1 ? CS - 1 : 1);
+        tc::mbar_init(&peer_ready[1], CS > 1 ? CS - 1 : 1);
+        tc::fence_mbar_init();
+    }
+    if (warp == EPI_WARPS) tc::tmem_alloc(tmem_slot, 32);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (CS > 1) tc::cluster_sync_all();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t gate_bytes_mine = (uint32_t)(UNITS / 64) * H_CHUNK;     // per gate: 2 chunks = 4 KB
+
+    if (warp == EPI_WARPS + 1) {
+        if (tc::elect_one()) {
+            const uint32_t total = (uint32_t)(KC3 * W_CHUNK);
+            tc::mbar_arrive_expect_tx(w_full, total);
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.WTimg) + ((size_t)d * CS + c) * total;
+            for (int i = 0; i < KC3; ++i) tc::bulk_g2s(sW + (size_t)i * W_CHUNK, src + (size_t)i * W_CHUNK, W_CHUNK, w_full);
+        }
+    } else if (warp == EPI_WARPS) {
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc = tc::umma_idesc_bf16(UNITS, NB);
+            bool ok = tc::mbar_wait(w_full, 0, p.dbg, 0x700);
+            for (int s = 0; s < T; ++s) {
+                if (CS > 1) tc::mbar_arrive_expect_tx(&d_full[s & 1], (uint32_t)(CS - 1) * 3 * gate_bytes_mine);
+                else tc::mbar_arrive(&d_full[s & 1]);
+                if (s == 0) continue;
+                if (ok) ok = tc::mbar_wait_cluster(&d_full[(s - 1) & 1], ((s - 1) >> 1) & 1, p.dbg, 0x800 + (s & 0xff));
+                tc::tcgen05_fence_after();
+                const uint32_t db0 = tc::smem_u32(sD), wb = tc::smem_u32(sW);
+#pragma unroll 1
+                for (int kc = 0; kc < KC3; ++kc) {
+                    const uint64_t da = tc::umma_desc_k_sw128(wb + (uint32_t)kc * W_CHUNK);
+                    const uint64_t db = tc::umma_desc_k_sw128(db0 + (uint32_t)kc * H_CHUNK);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        tc::umma_bf16(tmem, da + 2 * kk, db + 2 * kk, idesc, (kc | kk) ? 1u : 0u);
+                }
+                tc::umma_commit(mma_done);
+            }
+        }
+    } else {
+        const int q = warp & 3, half = warp >> 2;
+        const int j = q * 32 + lane;
+        const int unit = (int)c * UNITS + j;
+        const int col0 = half * 8;
+        const int ldy = D * H, ldg = D * 4 * H, ldi = D * 3 * H;
+        float dhz[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            dhz[i] = p.dh_init ? p.dh_init[((int64_t)d * B + tile * NB + col0 + i) * H + unit] : 0.f;
+        float sb_r = 0.f, sb_z = 0.f, sb_n = 0.f, sb_nr = 0.f;
+        bool ok = true;
+        for (int s = 0; s < T; ++s) {
+            const int t = d == 0 ? T - 1 - s : s;
+            const bool first = d == 0 ? t == 0 : t == T - 1;         // first step of the FORWARD recurrence: h_prev = 0
+            const int64_t row0 = (int64_t)t * B + tile * NB + col0;
+            const int64_t prow0 = row0 + (d == 0 ? -(int64_t)B : (int64_t)B);
+            float vr[8], vz[8], vn[8], vhn[8], vhp[8], vdy[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const __nv_bfloat16* gp = p.G + (row0 + i) * ldg + d * 4 * H + unit;
+                vr[i] = __bfloat162float(gp[0]); vz[i] = __bfloat162float(gp[H]);
+                vn[i] = __bfloat162float(gp[2 * H]); vhn[i] = __bfloat162float(gp[3 * H]);
+                vhp[i] = first ? 0.f : __bfloat162float(p.Yrow[(prow0 + i) * ldy + d * H + unit]);
+                vdy[i] = p.dY[(row0 + i) * ldy + d * H + unit];
+            }
+            float acc[8];
+            if (s > 0) {
+                if (ok) ok = tc::mbar_wait(mma_done, (s - 1) & 1, p.dbg, 0x900 + (s & 0xff));
+                tc::tcgen05_fence_after();
+                tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + col0, acc);
+                tc::tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+            }
+            // this CTA's tile may now be overwritten by the peers (its MMA of this step has retired)
+            if (threadIdx.x == 0 && CS > 1)
+                for (uint32_t peer = 0; peer < (uint32_t)CS; ++peer)
+                    if (peer != c) tc::mbar_arrive_cluster(&peer_ready[s & 1], peer);
+            __nv_bfloat16 tr[8], tz[8], tn[8], tnr[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float dh = acc[i] + dhz[i] + vdy[i];
+                const float r = vr[i], z = vz[i], n = vn[i];
+                const float dan = dh * (1.f - z) * (1.f - n * n);
+                const float dar = dan * vhn[i] * r * (1.f - r);
+                const float daz = dh * (vhp[i] - n) * z * (1.f - z);
+                const float danr = dan * r;
+                dhz[i] = dh * z;
+                sb_r += dar; sb_z += daz; sb_n += dan; sb_nr += danr;
+                tr[i] = __float2bfloat16(dar); tz[i] = __float2bfloat16(daz);
+                tn[i] = __float2bfloat16(dan); tnr[i] = __float2bfloat16(danr);
+                const uint32_t so = tc::sw128_offset(col0 + i, unit & 63);
+                const int kc_u = unit >> 6;
+                *reinterpret_cast<__nv_bfloat16*>(sD + (size_t)(0 * KC + kc_u) * H_CHUNK + so) = tr[i];
+                *reinterpret_cast<__nv_bfloat16*>(sD + (size_t)(1 * KC + kc_u) * H_CHUNK + so) = tz[i];
+                *reinterpret_cast<__nv_bfloat16*>(sD + (size_t)(2 * KC + kc_u) * H_CHUNK + so) = tnr[i];
+                __nv_bfloat16* gi_o = p.dgi_row + (row0 + i) * ldi + d * 3 * H + unit;
+                gi_o[0] = tr[i]; gi_o[H] = tz[i]; gi_o[2 * H] = tn[i];
+            }
+            {
+                __nv_bfloat16* o = p.dgiT + (int64_t)(d * 3 * H + unit) * R + row0;
+                *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(tr);
+                *reinterpret_cast<uint4*>(o + (int64_t)H * R) = *reinterpret_cast<uint4*>(tz);
+                *reinterpret_cast<uint4*>(o + (int64_t)2 * H * R) = *reinterpret_cast<uint4*>(tn);
+                __nv_bfloat16* o2 = p.dghT + (int64_t)(d * 3 * H + unit) * R + row0;
+                *reinterpret_cast<uint4*>(o2) = *reinterpret_cast<uint4*>(tr);
+                *reinterpret_cast<uint4*>(o2 + (int64_t)H * R) = *reinterpret_cast<uint4*>(tz);
+                *reinterpret_cast<uint4*>(o2 + (int64_t)2 * H * R) = *reinterpret_cast<uint4*>(tnr);
+            }
+            tc::tcgen05_fence_before();
+            tc::fence_proxy_async_smem();
+            epi_barrier();
+            if (threadIdx.x == 0 && s + 1 < T) {
+                tc::mbar_arrive(&d_full[s & 1]);
+                if (CS > 1) {
+                    if (ok) ok = tc::mbar_wait_cluster(&peer_ready[s & 1], (s >> 1) & 1, p.dbg, 0xA00 + (s & 0xff));
+                    for (uint32_t peer = 0; peer < (uint32_t)CS; ++peer) {
+                        if (peer == c) continue;
+                        for (int g = 0; g < 3; ++g) {
+                            uint8_t* mine = sD + (size_t)(g * KC) * H_CHUNK + (size_t)c * gate_bytes_mine;
+                            tc::bulk_s2cluster(mine, mine, gate_bytes_mine, &d_full[s & 1], peer);
+                        }
+                    }
+                }
+            }
+        }
+        // bias gradients: sum the 8 columns of this thread; the two column halves and all tiles add atomically
+        float* dbi = p.db_ih + (int64_t)d * p.dir_stride;
+        float* dbh = p.db_hh + (int64_t)d * p.dir_stride;
+        atomicAdd(dbi + unit, sb_r); atomicAdd(dbi + H + unit, sb_z); atomicAdd(dbi + 2 * H + unit, sb_n);
+        atomicAdd(dbh + unit, sb_r); atomicAdd(dbh + H + unit, sb_z); atomicAdd(dbh + 2 * H + unit, sb_nr);
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (CS > 1) tc::cluster_sync_all();
+    if (warp == EPI_WARPS) tc::tmem_dealloc(tmem, 32);
+}
+
+static inline cudaError_t launch_bwd(const BwdParams& p, cudaStream_t st) {
+    const int CS = p.H / UNITS;
+    const size_t smem = bwd_smem_bytes(p.H);
+    static size_t attr = 0;
+    if (attr < smem) {
+        cudaError_t e = cudaFuncSetAttribute(gru_scan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = smem;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(p.D * (p.B / NB) * CS));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gru_scan_bwd_kernel, p);
+}
+
+// W_hh fp32 [3H][H] -> images of W_hh^T slices: img[c][q/64][unit k % 128][q % 64] = W_hh[q][128c + k]
+__global__ void pack_whhT_image_kernel(const float* __restrict__ w_hh, __nv_bfloat16* __restrict__ img, int H) {
+    const int KC3 = 3 * H / 64;
+    const int64_t total = (int64_t)3 * H * H;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = i % H;                   // hidden unit (column of W_hh)
+        const int qrow = i / H;                // gate row q
+        const int c = k / UNITS, kr = k % UNITS, kc = qrow / 64;
+        const size_t chunk = ((size_t)c * KC3 + kc) * W_CHUNK;
+        *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(img) + chunk + tc::sw128_offset(kr, qrow & 63)) =
+            __float2bfloat16(w_hh[i]);
+    }
+}
+
+}  // namespace tcs

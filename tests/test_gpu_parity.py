@@ -37,6 +37,11 @@ def precisions():
     return out
 
 
+def supported(precision, B, F, H, h0=False):
+    """BIGRU_PREC_BF16 covers H in {128, 256}, B % 16 == 0, F % 8 == 0, no initial hidden state."""
+    return precision == "fp32" or (H in (128, 256) and B % 16 == 0 and F % 8 == 0 and not h0)
+
+
 def rel(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
@@ -93,6 +98,8 @@ def test_golden_forward_backward_autograd(golden_dir, name):
     B, T, F, H, L, C, bidir = [int(v) for v in z["meta"]]
     d = dict(B=B, T=T, F=F, H=H, L=L, C=C, bidir=bool(bidir))
     for precision in precisions():
+        if not supported(precision, B, F, H, "h0" in z.files):
+            continue
         tol = TOL[precision]
         m = make_model(d, params_of(z), precision)
         m.train()
@@ -121,6 +128,8 @@ def test_golden_fused_train_step(golden_dir, name):
     B, T, F, H, L, C, bidir = [int(v) for v in z["meta"]]
     d = dict(B=B, T=T, F=F, H=H, L=L, C=C, bidir=bool(bidir))
     for precision in precisions():
+        if not supported(precision, B, F, H, "h0" in z.files):
+            continue
         tol = TOL[precision]
         m = make_model(d, params_of(z), precision)
         loss_fn, tgt = loss_from(z)
@@ -135,7 +144,11 @@ def test_golden_fused_train_step(golden_dir, name):
         assert abs(gn - float(z["grad_norm"])) < tol["grads"] * float(z["grad_norm"])
         upd_got, upd_ref = [], []
         for k, v in m.state_dict().items():
+            if "q:" + k not in z.files:
+                continue
             assert np.abs(v.cpu().numpy() - z["q:" + k]).max() < tol["step"], (precision, k)
+            if "q:" + k not in z.files:
+                continue                                  # buffers of the attached loss module
             upd_got.append((v.cpu().numpy() - z["p:" + k]).ravel())
             upd_ref.append((z["q:" + k] - z["p:" + k]).ravel())
         assert rel_l2(np.concatenate(upd_got), np.concatenate(upd_ref)) < tol["update"], precision
@@ -148,6 +161,8 @@ SWEEP = [  # B, T, F, H, L, C, bidir, h0
     (17, 9, 12, 40, 3, 4, True, False),
     (33, 6, 64, 64, 2, 3, False, False),
     (64, 16, 32, 128, 2, 3, True, False),
+    (48, 7, 40, 256, 2, 3, True, False),
+    (32, 5, 8, 128, 1, 2, False, False),
 ]
 
 
@@ -156,6 +171,8 @@ def test_sweep_against_c_oracle(cfg):
     B, T, F, H, L, C, bidir, use_h0 = cfg
     D = 2 if bidir else 1
     for precision in precisions():
+        if not supported(precision, B, F, H, use_h0):
+            continue
         tol = TOL[precision]
         torch.manual_seed(3)
         m = _pkg().BiGRU(H, F, C, L, 50, 0.0, False, bidir, precision=precision).cuda()
@@ -212,7 +229,7 @@ def test_c1_shape_against_torch_oracle():
 def test_shard_gradients_sum_to_full_batch():
     """Data-parallel property: the shard gradients of the global-mean loss add up to the full-batch
     gradient (what the single all-reduce computes)."""
-    B, T, F, H, L, C = 64, 10, 16, 32, 2, 3
+    B, T, F, H, L, C = 64, 10, 16, 128, 2, 3
     for precision in precisions():
         torch.manual_seed(1)
         m = _pkg().BiGRU(H, F, C, L, 50, 0.0, False, True, precision=precision).cuda()
@@ -252,10 +269,10 @@ def test_linearity_in_upstream_gradient():
 def test_dropout_modes():
     """Train-mode dropout: elementwise and channel-wise ('spatial', one mask per (b, f) over T) input
     masks, inter-layer dropout; same mask in backward (dx is zero exactly where the input was dropped)."""
-    B, T, F, H, L, C = 16, 12, 24, 32, 2, 3
-    for spatial in (False, True):
+    for precision, spatial in [(p, s) for p in precisions() for s in (False, True)]:
+        B, T, F, H, L, C = (16, 12, 24, 32, 2, 3) if precision == "fp32" else (16, 12, 24, 128, 2, 3)
         torch.manual_seed(4)
-        m = _pkg().BiGRU(H, F, C, L, 50, 0.5, spatial, True, precision="fp32").cuda()
+        m = _pkg().BiGRU(H, F, C, L, 50, 0.5, spatial, True, precision=precision).cuda()
         m.train()
         x = (torch.rand(B, T, F, device="cuda") + 0.5).requires_grad_(True)
         y1 = m(x)

@@ -1,0 +1,113 @@
+// Stand-alone bring-up test of the persistent tcgen05 GRU scan (forward).  tools/_bin/tc_scan_test
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include "../financial_market_data_analysis_b200/csrc/tc_scan.cuh"
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); return 1; } } while (0)
+static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
+static float frand() { return (rand() % 20001 - 10000) / 10000.f; }
+
+static int run_case(int B, int T, int H, int D, int reps) {
+    const int CS = H / 128; const long R = (long)T * B;
+    srand(B + 3 * T + H);
+    std::vector<float> whh((size_t)D * 3 * H * H), bhn((size_t)D * H), gi((size_t)R * D * 3 * H);
+    const float sc = 1.f / sqrtf((float)H);
+    for (auto& v : whh) v = frand() * sc;
+    for (auto& v : bhn) v = frand() * sc;
+    for (auto& v : gi) v = bf(frand() * 1.5f);
+    float* d_whh; float* d_bhn; __nv_bfloat16 *d_img, *d_gi, *d_Y, *d_YT, *d_G; float* d_hn; unsigned int* dbg;
+    const size_t img_elems = (size_t)D * 3 * H * H;
+    CK(cudaMalloc(&d_whh, whh.size() * 4)); CK(cudaMalloc(&d_bhn, bhn.size() * 4)); CK(cudaMalloc(&d_img, img_elems * 2));
+    CK(cudaMalloc(&d_gi, gi.size() * 2)); CK(cudaMalloc(&d_Y, (size_t)R * D * H * 2)); CK(cudaMalloc(&d_YT, (size_t)R * D * H * 2));
+    CK(cudaMalloc(&d_G, (size_t)R * D * 4 * H * 2)); CK(cudaMalloc(&d_hn, (size_t)D * B * H * 4)); CK(cudaMalloc(&dbg, 64));
+    std::vector<__nv_bfloat16> gih(gi.size());
+    for (size_t i = 0; i < gi.size(); ++i) gih[i] = __float2bfloat16(gi[i]);
+    CK(cudaMemcpy(d_whh, whh.data(), whh.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_bhn, bhn.data(), bhn.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_gi, gih.data(), gih.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dbg, 0, 64)); CK(cudaMemset(d_Y, 0, (size_t)R * D * H * 2));
+    for (int d = 0; d < D; ++d) {
+        tcs::pack_whh_image_kernel<<<256, 256>>>(d_whh + (size_t)d * 3 * H * H, d_img + (size_t)d * 3 * H * H, H);
+        CK(cudaGetLastError());
+    }
+    tcs::FwdParams p{};
+    p.B = B; p.T = T; p.H = H; p.D = D; p.Wimg = d_img; p.gi = d_gi; p.b_hn = d_bhn; p.Yrow = d_Y; p.YT = d_YT; p.G = d_G;
+    p.hn_out = d_hn; p.dbg = dbg;
+    CK(tcs::launch_fwd(p, 0));
+    CK(cudaDeviceSynchronize());
+    float ms = 0;
+    if (reps > 0) {
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        for (int i = 0; i < reps; ++i) CK(tcs::launch_fwd(p, 0));
+        cudaEventRecord(e1); CK(cudaDeviceSynchronize());
+        cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+    }
+    unsigned int h[8]; CK(cudaMemcpy(h, dbg, 32, cudaMemcpyDeviceToHost));
+    std::vector<__nv_bfloat16> Y((size_t)R * D * H), YT((size_t)R * D * H), G((size_t)R * D * 4 * H);
+    std::vector<float> hn((size_t)D * B * H);
+    CK(cudaMemcpy(Y.data(), d_Y, Y.size() * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(YT.data(), d_YT, YT.size() * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(G.data(), d_G, G.size() * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hn.data(), d_hn, hn.size() * 4, cudaMemcpyDeviceToHost));
+    // CPU reference with the same roundings: bf16 weights, bf16 h into the product, fp32 state
+    double eY = 0, eYT = 0, eG = 0, eHn = 0;
+    const int bcheck = B > 48 ? 48 : B;                     // first rows of the batch (several tiles) are enough
+    std::vector<float> wq(whh.size());
+    for (size_t i = 0; i < whh.size(); ++i) wq[i] = bf(whh[i]);
+    for (int d = 0; d < D; ++d)
+        for (int b = 0; b < bcheck; ++b) {
+            std::vector<float> hs(H, 0.f), hq(H, 0.f), hnew(H);
+            for (int s = 0; s < T; ++s) {
+                const int t = d == 0 ? s : T - 1 - s;
+                const long row = (long)t * B + b;
+                for (int j = 0; j < H; ++j) {
+                    double a[3] = {0, 0, 0};
+                    for (int g = 0; g < 3; ++g) {
+                        const float* w = &wq[((size_t)d * 3 * H + g * H + j) * H];
+                        double acc = 0;
+                        for (int k = 0; k < H; ++k) acc += (double)w[k] * hq[k];
+                        a[g] = acc;
+                    }
+                    const float* gp = &gi[row * D * 3 * H + d * 3 * H];
+                    const float r = 1.f / (1.f + expf(-(gp[j] + (float)a[0])));
+                    const float z = 1.f / (1.f + expf(-(gp[H + j] + (float)a[1])));
+                    const float hnv = (float)a[2] + bhn[d * H + j];
+                    const float n = tanhf(gp[2 * H + j] + r * hnv);
+                    hnew[j] = n + z * (hs[j] - n);
+                    const size_t gidx = (size_t)row * D * 4 * H + d * 4 * H + j;
+                    eG = fmax(eG, fabs(r - __bfloat162float(G[gidx])));
+                    eG = fmax(eG, fabs(z - __bfloat162float(G[gidx + H])));
+                    eG = fmax(eG, fabs(n - __bfloat162float(G[gidx + 2 * H])));
+                    eG = fmax(eG, fabs(hnv - __bfloat162float(G[gidx + 3 * H])));
+                }
+                for (int j = 0; j < H; ++j) {
+                    hs[j] = hnew[j]; hq[j] = bf(hnew[j]);
+                    eY = fmax(eY, fabs(hnew[j] - __bfloat162float(Y[(size_t)row * D * H + d * H + j])));
+                    eYT = fmax(eYT, fabs(hnew[j] - __bfloat162float(YT[(size_t)(d * H + j) * R + row])));
+                }
+            }
+            for (int j = 0; j < H; ++j) eHn = fmax(eHn, fabs(hs[j] - hn[((size_t)d * B + b) * H + j]));
+        }
+    const bool pass = h[0] == 0 && eY < 2e-2 && eYT < 2e-2 && eG < 3e-2 && eHn < 2e-2;
+    printf("%s scan_fwd B=%d T=%d H=%d D=%d (cluster %d, grid %d): errY=%.2e errYT=%.2e errG=%.2e errHn=%.2e dbg=%x blk=%u thr=%u a=%u  %.3f ms (%.2f us/step)\n",
+           pass ? "PASS" : "FAIL", B, T, H, D, CS, D * (B / 16) * CS, eY, eYT, eG, eHn, h[0], h[1], h[2], h[3], ms, ms * 1e3 / T);
+    cudaFree(d_whh); cudaFree(d_bhn); cudaFree(d_img); cudaFree(d_gi); cudaFree(d_Y); cudaFree(d_YT); cudaFree(d_G); cudaFree(d_hn); cudaFree(dbg);
+    return pass ? 0 : 2;
+}
+
+int main() {
+    int bad = 0;
+    bad += run_case(16, 1, 128, 1, 0);
+    bad += run_case(16, 4, 128, 1, 0);
+    bad += run_case(32, 6, 128, 2, 0);
+    bad += run_case(16, 2, 256, 1, 0);
+    bad += run_case(16, 5, 256, 1, 0);
+    bad += run_case(64, 9, 256, 2, 0);
+    bad += run_case(512, 128, 256, 2, 10);
+    bad += run_case(512, 64, 128, 2, 10);
+    printf(bad ? "SOME FAILED\n" : "ALL PASSED\n");
+    return bad ? 1 : 0;
+}
