@@ -83,6 +83,8 @@ def test_known_answer_vectors(golden_dir):
     """Shipped model_params.pt through the CUDA path."""
     z = np.load(os.path.join(golden_dir, "kat.npz"))
     for precision in precisions():
+        if not supported(precision, 1, 108, 8):
+            continue                                   # the shipped checkpoint has H=8: fp32 path only
         m = make_model(dict(H=8, F=108, C=4, L=1, bidir=True), params_of(z), precision, dropout=0.2)
         m.eval()
         for i in (1, 2, 3):
