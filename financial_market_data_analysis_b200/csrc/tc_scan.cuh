@@ -2,7 +2,9 @@
 //
 // One thread-block CLUSTER walks all T steps of one (direction, 16-row batch tile).  The cluster has
 // CS = H/128 CTAs; CTA c owns hidden units [128c, 128c+128) and keeps its slice of W_hh (3 gates x 128
-// rows x H, bf16, 128B-swizzled K-major = 192 KB at H=256) RESIDENT in shared memory for the whole scan.
+// rows x H, bf16 = 192 KB at H=256) RESIDENT IN TENSOR MEMORY for the whole scan: the weights are the
+// A operand of tcgen05.mma read straight from TMEM (lane = unit row, two bf16 per 32-bit column), so a
+// step moves only the 512-byte h slices of the B operand through shared memory.
 // Per step ("swap-AB": weights are the M side, the batch tile is the N=16 side):
 //     D_g[unit, b] = sum_k W_hg[unit, k] * h_{t-1}[b, k]        g in {r, z, n}   (tcgen05.mma M=128 N=16 K=16)
 // accumulators live in TMEM (3 x 16 columns); 8 epilogue warps read them back (tcgen05.ld), add the
@@ -17,7 +19,7 @@
 //   Yrow bf16 [R][D*H]    layer output                                        (written)
 //   YT   bf16 [D*H][R]    layer output transposed (wgrad operand)             (written)
 //   G    bf16 [R][D*4H]   r, z, n, hn = W_hn h + b_hn  (stash for backward)   (written)
-//   Wimg bf16 [D][CS][3][H/64][128 rows][64]  swizzled smem images of W_hh    (read once)
+//   Wimg bf16 [D][H units][3][H]  per-unit rows of W_hh (r|z|n), copied to TMEM   (read once)
 #pragma once
 #include "tc_common.cuh"
 
@@ -41,12 +43,55 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
 }
 
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+          "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+          "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]: A is read from tensor memory (lane = row, 2 bf16 per column)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// Weight slice -> TMEM.  Wpk holds, per unit row of this CTA, `row_elems` bf16 (the K extent of the A operand);
+// the 8 epilogue warps copy it to columns [a_col, a_col + row_elems/2): warp quarter = lane group, warp half =
+// column half, 32 columns (64 bf16 = 128 B of the row) per tcgen05.st.
+__device__ __forceinline__ void load_weights_to_tmem(const __nv_bfloat16* wrow_base, int row_elems, uint32_t tmem,
+                                                     uint32_t a_col, int warp, int lane) {
+    const int q = warp & 3, half = warp >> 2;
+    const int cols_half = row_elems / 4;                 // columns per half (row_elems/2 columns in total)
+    const uint4* src = reinterpret_cast<const uint4*>(wrow_base + (size_t)(q * 32 + lane) * row_elems + (size_t)half * (row_elems / 2));
+    for (int i = 0; i < cols_half / 32; ++i) {
+        uint32_t v[32];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint4 u = src[i * 8 + k];
+            v[4 * k] = u.x; v[4 * k + 1] = u.y; v[4 * k + 2] = u.z; v[4 * k + 3] = u.w;
+        }
+        tmem_st32(tmem + ((uint32_t)(q * 32) << 16) + a_col + (uint32_t)(half * cols_half + i * 32), v);
+    }
+    tmem_st_wait();
+}
+
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
 
 static inline size_t fwd_smem_bytes(int H) {
     const int KC = H / 64;
-    return (size_t)3 * KC * W_CHUNK + (size_t)2 * KC * H_CHUNK + 1024 + 256;
+    return (size_t)2 * KC * H_CHUNK + 1024 + 256;
 }
+constexpr uint32_t FWD_A_COL = 64;        // accumulators in columns [0, 48), weights from column 64
+__host__ __device__ static inline uint32_t fwd_tmem_cols(int H) { return 64 + 3 * H / 2 <= 256 ? 256u : 512u; }
 
 struct FwdParams {
     int B, T, H, D;
@@ -64,10 +109,8 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int H = p.H, KC = H / 64, CS = H / UNITS, B = p.B, T = p.T, D = p.D;
-    uint8_t* sW = smem;                                    // [3][KC][W_CHUNK]
-    uint8_t* sH = smem + (size_t)3 * KC * W_CHUNK;         // [2][KC][H_CHUNK]
+    uint8_t* sH = smem;                                    // [2][KC][H_CHUNK]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sH + (size_t)2 * KC * H_CHUNK);
-    uint64_t* w_full = bars;
     uint64_t* h_full = bars + 1;       // [2]
     uint64_t* mma_done = bars + 3;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
@@ -80,33 +123,30 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
     const int64_t R = (int64_t)T * B;
 
     if (threadIdx.x == 0) {
-        tc::mbar_init(w_full, 1);
         tc::mbar_init(&h_full[0], 2);
         tc::mbar_init(&h_full[1], 2);
         tc::mbar_init(mma_done, 1);
         tc::fence_mbar_init();
     }
-    if (warp == EPI_WARPS) tc::tmem_alloc(tmem_slot, 64);
+    if (warp == EPI_WARPS) tc::tmem_alloc(tmem_slot, fwd_tmem_cols(H));
     tc::tcgen05_fence_before();
     __syncthreads();
     if (CS > 1) tc::cluster_sync_all();        // every CTA's barriers exist before any peer signals them
     tc::tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t chunk_bytes_mine = (uint32_t)(UNITS / 64) * H_CHUNK;    // the 2 K-chunks this CTA produces
+    // W_hh slice of this CTA -> tensor memory (stays there for all T steps)
+    if (warp < EPI_WARPS)
+        load_weights_to_tmem(p.Wimg + ((size_t)d * CS + c) * UNITS * 3 * H, 3 * H, tmem, FWD_A_COL, warp, lane);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
 
-    if (warp == EPI_WARPS + 1) {
-        // ---- loader: W_hh slice image -> smem (bulk TMA copies, 16 KB each)
-        if (tc::elect_one()) {
-            const uint32_t total = (uint32_t)(3 * KC * W_CHUNK);
-            tc::mbar_arrive_expect_tx(w_full, total);
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Wimg) + ((size_t)d * CS + c) * total;
-            for (int i = 0; i < 3 * KC; ++i) tc::bulk_g2s(sW + (size_t)i * W_CHUNK, src + (size_t)i * W_CHUNK, W_CHUNK, w_full);
-        }
-    } else if (warp == EPI_WARPS) {
+    if (warp == EPI_WARPS) {
         // ---- MMA issuer
         if (tc::elect_one()) {
             constexpr uint32_t idesc = tc::umma_idesc_bf16(UNITS, NB);
-            bool ok = tc::mbar_wait(w_full, 0, p.dbg, 0x400);
+            bool ok = true;
             for (int s = 0; s < T; ++s) {                  // after a watchdog hit: keep signalling, stop waiting
                 if (CS > 1) tc::mbar_arrive_expect_tx(&h_full[s & 1], (uint32_t)(CS - 1) * chunk_bytes_mine);
                 else tc::mbar_arrive(&h_full[s & 1]);
@@ -115,16 +155,15 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
                 if (ok) ok = tc::mbar_wait_cluster(&h_full[pb], ((s - 1) >> 1) & 1, p.dbg, 0x500 + (s & 0xff));
                 tc::tcgen05_fence_after();
                 const uint32_t hb = tc::smem_u32(sH + (size_t)pb * KC * H_CHUNK);
-                const uint32_t wb = tc::smem_u32(sW);
 #pragma unroll 1
                 for (int g = 0; g < 3; ++g) {
+                    const uint32_t ta = tmem + FWD_A_COL + (uint32_t)(g * (H / 2));     // gate g: H/2 columns per row
 #pragma unroll 1
                     for (int kc = 0; kc < KC; ++kc) {
-                        const uint64_t da = tc::umma_desc_k_sw128(wb + (uint32_t)(g * KC + kc) * W_CHUNK);
                         const uint64_t db = tc::umma_desc_k_sw128(hb + (uint32_t)kc * H_CHUNK);
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            tc::umma_bf16(tmem + g * NB, da + 2 * kk, db + 2 * kk, idesc, (kc | kk) ? 1u : 0u);
+                        for (int kk = 0; kk < 4; ++kk)       // K = 16 bf16 = 8 TMEM columns of A, 32 B of B
+                            umma_bf16_ts(tmem + g * NB, ta + (uint32_t)((kc * 4 + kk) * 8), db + 2 * kk, idesc, (kc | kk) ? 1u : 0u);
                     }
                 }
                 tc::umma_commit(mma_done);
@@ -200,7 +239,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
     tc::tcgen05_fence_before();
     __syncthreads();
     if (CS > 1) tc::cluster_sync_all();        // no CTA leaves while a peer may still target its smem
-    if (warp == EPI_WARPS) tc::tmem_dealloc(tmem, 64);
+    if (warp == EPI_WARPS) tc::tmem_dealloc(tmem, fwd_tmem_cols(H));
 }
 
 static inline cudaError_t launch_fwd(const FwdParams& p, cudaStream_t st) {
@@ -224,22 +263,16 @@ static inline cudaError_t launch_fwd(const FwdParams& p, cudaStream_t st) {
     return cudaLaunchKernelEx(&cfg, gru_scan_fwd_kernel, p);
 }
 
-// ---- weight image: W_hh fp32 [3H][H] (rows r|z|n) -> Wimg[c][g][kc][unit row][64] bf16, 128B-swizzled
+// ---- packed weights: W_hh fp32 [3H][H] (rows r|z|n) -> Wpk[unit u][g][k] bf16 (row of unit u = its three gate rows)
 __global__ void pack_whh_image_kernel(const float* __restrict__ w_hh, __nv_bfloat16* __restrict__ img, int H) {
-    const int KC = H / 64, CS = H / UNITS;
     const int64_t total = (int64_t)3 * H * H;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int k = i % H;
         const int row = i / H;                 // g*H + unit
         const int g = row / H, unit = row % H;
-        const int c = unit / UNITS, jr = unit % UNITS, kc = k / 64;
-        const size_t chunk = (((size_t)c * 3 + g) * KC + kc) * W_CHUNK;
-        *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(img) + chunk + tc::sw128_offset(jr, k & 63)) =
-            __float2bfloat16(w_hh[i]);
+        img[((int64_t)unit * 3 + g) * H + k] = __float2bfloat16(w_hh[i]);
     }
-    (void)CS;
 }
-
 
 // =================================================================================================
 // Backward scan (BPTT).  Same cluster / tiling; the resident operand is W_hh^T (A[unit k][q] = W_hh[q][k],
@@ -256,12 +289,14 @@ __global__ void pack_whh_image_kernel(const float* __restrict__ w_hh, __nv_bfloa
 // =================================================================================================
 static inline size_t bwd_smem_bytes(int H) {
     const int KC3 = 3 * H / 64;
-    return (size_t)KC3 * W_CHUNK + (size_t)KC3 * H_CHUNK + 1024 + 256;
+    return (size_t)KC3 * H_CHUNK + 1024 + 256;
 }
+constexpr uint32_t BWD_A_COL = 32;        // accumulator in columns [0, 16), W_hh^T from column 32
+__host__ __device__ static inline uint32_t bwd_tmem_cols(int H) { return 32 + 3 * H / 2 <= 256 ? 256u : 512u; }
 
 struct BwdParams {
     int B, T, H, D;
-    const __nv_bfloat16* WTimg;     // [D][CS][3H/64][128][64] swizzled images of W_hh^T slices
+    const __nv_bfloat16* WTimg;     // [D][H units][3H]  rows of W_hh^T, copied to TMEM
     const __nv_bfloat16* G;
     const __nv_bfloat16* Yrow;
     const float* dY;                // [R][D*H]
@@ -279,10 +314,8 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int H = p.H, KC = H / 64, KC3 = 3 * KC, CS = H / UNITS, B = p.B, T = p.T, D = p.D;
-    uint8_t* sW = smem;                                    // [KC3][W_CHUNK]
-    uint8_t* sD = smem + (size_t)KC3 * W_CHUNK;            // [KC3][H_CHUNK]  dgh tile
+    uint8_t* sD = smem;                                    // [KC3][H_CHUNK]  dgh tile
     uint64_t* bars = reinterpret_cast<uint64_t*>(sD + (size_t)KC3 * H_CHUNK);
-    uint64_t* w_full = bars;
     uint64_t* d_full = bars + 1;       // [2] alternate by step parity (same buffer)
     uint64_t* mma_done = bars + 3;
     uint64_t* peer_ready = bars + 4;   // [2] peers' "my MMA of step s retired, you may overwrite my tile"
@@ -296,7 +329,6 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
     const int64_t R = (int64_t)T * B;
 
     if (threadIdx.x == 0) {
-        tc::mbar_init(w_full, 1);
         tc::mbar_init(&d_full[0], 2);
         tc::mbar_init(&d_full[1], 2);
         tc::mbar_init(mma_done, 1);
@@ -304,39 +336,36 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
         tc::mbar_init(&peer_ready[1], CS > 1 ? CS - 1 : 1);
         tc::fence_mbar_init();
     }
-    if (warp == EPI_WARPS) tc::tmem_alloc(tmem_slot, 32);
+    if (warp == EPI_WARPS) tc::tmem_alloc(tmem_slot, bwd_tmem_cols(H));
     tc::tcgen05_fence_before();
     __syncthreads();
     if (CS > 1) tc::cluster_sync_all();
     tc::tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t gate_bytes_mine = (uint32_t)(UNITS / 64) * H_CHUNK;     // per gate: 2 chunks = 4 KB
+    if (warp < EPI_WARPS)
+        load_weights_to_tmem(p.WTimg + ((size_t)d * CS + c) * UNITS * 3 * H, 3 * H, tmem, BWD_A_COL, warp, lane);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
 
-    if (warp == EPI_WARPS + 1) {
-        if (tc::elect_one()) {
-            const uint32_t total = (uint32_t)(KC3 * W_CHUNK);
-            tc::mbar_arrive_expect_tx(w_full, total);
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.WTimg) + ((size_t)d * CS + c) * total;
-            for (int i = 0; i < KC3; ++i) tc::bulk_g2s(sW + (size_t)i * W_CHUNK, src + (size_t)i * W_CHUNK, W_CHUNK, w_full);
-        }
-    } else if (warp == EPI_WARPS) {
+    if (warp == EPI_WARPS) {
         if (tc::elect_one()) {
             constexpr uint32_t idesc = tc::umma_idesc_bf16(UNITS, NB);
-            bool ok = tc::mbar_wait(w_full, 0, p.dbg, 0x700);
+            bool ok = true;
             for (int s = 0; s < T; ++s) {
                 if (CS > 1) tc::mbar_arrive_expect_tx(&d_full[s & 1], (uint32_t)(CS - 1) * 3 * gate_bytes_mine);
                 else tc::mbar_arrive(&d_full[s & 1]);
                 if (s == 0) continue;
                 if (ok) ok = tc::mbar_wait_cluster(&d_full[(s - 1) & 1], ((s - 1) >> 1) & 1, p.dbg, 0x800 + (s & 0xff));
                 tc::tcgen05_fence_after();
-                const uint32_t db0 = tc::smem_u32(sD), wb = tc::smem_u32(sW);
+                const uint32_t db0 = tc::smem_u32(sD);
 #pragma unroll 1
                 for (int kc = 0; kc < KC3; ++kc) {
-                    const uint64_t da = tc::umma_desc_k_sw128(wb + (uint32_t)kc * W_CHUNK);
                     const uint64_t db = tc::umma_desc_k_sw128(db0 + (uint32_t)kc * H_CHUNK);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
-                        tc::umma_bf16(tmem, da + 2 * kk, db + 2 * kk, idesc, (kc | kk) ? 1u : 0u);
+                        umma_bf16_ts(tmem, tmem + BWD_A_COL + (uint32_t)((kc * 4 + kk) * 8), db + 2 * kk, idesc, (kc | kk) ? 1u : 0u);
                 }
                 tc::umma_commit(mma_done);
             }
@@ -438,7 +467,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
     tc::tcgen05_fence_before();
     __syncthreads();
     if (CS > 1) tc::cluster_sync_all();
-    if (warp == EPI_WARPS) tc::tmem_dealloc(tmem, 32);
+    if (warp == EPI_WARPS) tc::tmem_dealloc(tmem, bwd_tmem_cols(H));
 }
 
 static inline cudaError_t launch_bwd(const BwdParams& p, cudaStream_t st) {
@@ -462,17 +491,13 @@ static inline cudaError_t launch_bwd(const BwdParams& p, cudaStream_t st) {
     return cudaLaunchKernelEx(&cfg, gru_scan_bwd_kernel, p);
 }
 
-// W_hh fp32 [3H][H] -> images of W_hh^T slices: img[c][q/64][unit k % 128][q % 64] = W_hh[q][128c + k]
+// W_hh fp32 [3H][H] -> packed W_hh^T: WTpk[unit k][q] = W_hh[q][k]   (row of unit k = column k of W_hh, 3H long)
 __global__ void pack_whhT_image_kernel(const float* __restrict__ w_hh, __nv_bfloat16* __restrict__ img, int H) {
-    const int KC3 = 3 * H / 64;
     const int64_t total = (int64_t)3 * H * H;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int k = i % H;                   // hidden unit (column of W_hh)
         const int qrow = i / H;                // gate row q
-        const int c = k / UNITS, kr = k % UNITS, kc = qrow / 64;
-        const size_t chunk = ((size_t)c * KC3 + kc) * W_CHUNK;
-        *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(img) + chunk + tc::sw128_offset(kr, qrow & 63)) =
-            __float2bfloat16(w_hh[i]);
+        img[(int64_t)k * 3 * H + qrow] = __float2bfloat16(w_hh[i]);
     }
 }
 
