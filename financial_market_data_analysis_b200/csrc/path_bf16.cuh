@@ -116,17 +116,17 @@ __global__ void dropout_rows_kernel(const bf16_t* __restrict__ Y, bf16_t* __rest
         XT[(int64_t)cidx * R + r] = o;
     }
 }
-// gradient of the same dropout, in place on fp32 [R][cols] (time-major rows)
-__global__ void dropout_grad_rows_kernel(float* __restrict__ dX, int64_t R, int cols, int B, int T, float pdrop,
+// gradient of the same dropout, in place on the TRANSPOSED fp32 gradient [cols][R]
+__global__ void dropout_grad_rows_kernel(float* __restrict__ dXT, int64_t R, int cols, int B, int T, float pdrop,
                                          uint64_t seed, uint32_t stream) {
     const float scale = 1.f / (1.f - pdrop);
     const int64_t total = R * cols;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int cidx = i % cols;
-        const int64_t r = i / cols;
+        const int64_t r = i % R;
+        const int cidx = i / R;
         const int64_t b = r % B, t = r / B;
         const uint64_t key = ((uint64_t)b * T + t) * cols + cidx;
-        dX[i] = bigru_uniform(seed, stream, key) < pdrop ? 0.f : dX[i] * scale;
+        dXT[i] = bigru_uniform(seed, stream, key) < pdrop ? 0.f : dXT[i] * scale;
     }
 }
 
@@ -172,39 +172,46 @@ __global__ void head_pool_tm_kernel(const bf16_t* __restrict__ Y, float* __restr
     c[j] = last; c[H + j] = mx; c[2 * H + j] = sum / (float)T;
     arg[idx] = am;
 }
-// dY (time-major fp32 [R][D*H]) of the top layer and the initial dh carry [D][B][H]
-__global__ void head_bwd_dy_tm_kernel(const float* __restrict__ dcat, const int* __restrict__ arg, float* __restrict__ dY,
+// dY^T (fp32 [D*H][R], time-major columns) of the top layer and the initial dh carry [D][B][H]
+__global__ void head_bwd_dy_tm_kernel(const float* __restrict__ dcat, const int* __restrict__ arg, float* __restrict__ dYT,
                                       float* __restrict__ dhinit, int B, int T, int H, int D) {
+    const int64_t R = (int64_t)B * T;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)B * T * H) return;
-    const int j = idx % H;
-    const int b = (idx / H) % B;
-    const int t = idx / ((int64_t)H * B);
+    if (idx >= R * H) return;
+    const int64_t r = idx % R;
+    const int j = idx / R;
+    const int b = r % B, t = r / B;
     const float* dc = dcat + (int64_t)b * 3 * H;
     const float v = dc[2 * H + j] / (float)T + (arg[(int64_t)b * H + j] == t ? dc[H + j] : 0.f);
-    float* o = dY + ((int64_t)t * B + b) * D * H;
-    o[j] = v;
-    if (D == 2) o[H + j] = v;
+    dYT[(int64_t)j * R + r] = v;
+    if (D == 2) dYT[(int64_t)(H + j) * R + r] = v;
     if (t == 0) {
         dhinit[(int64_t)b * H + j] = dc[j];
         if (D == 2) dhinit[((int64_t)B + b) * H + j] = dc[j];
     }
 }
-// dX of layer 0 from time-major fp32 [R][F] back to the caller's [B][T][F] (+ input-dropout mask)
-__global__ void dx_to_batch_major_kernel(const float* __restrict__ dXtm, float* __restrict__ dx, int B, int T, int F,
+// dX^T of layer 0 (fp32 [F][R]) back to the caller's [B][T][F] (+ input-dropout mask); 32x32 smem transpose
+__global__ void dx_to_batch_major_kernel(const float* __restrict__ dXT, float* __restrict__ dx, int B, int T, int F,
                                          float pdrop, int spatial, uint64_t seed) {
+    __shared__ float tile[32][33];
+    const int t = blockIdx.z, b0 = blockIdx.y * 32, f0 = blockIdx.x * 32;
+    const int64_t R = (int64_t)T * B;
     const float scale = pdrop > 0.f ? 1.f / (1.f - pdrop) : 1.f;
-    const int64_t total = (int64_t)B * T * F;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int f = i % F;
-        const int64_t bt = i / F;
-        const int64_t t = bt % T, b = bt / T;
-        float v = dXtm[(t * B + b) * F + f];
-        if (pdrop > 0.f) {
-            const uint64_t key = spatial ? (uint64_t)b * F + f : (uint64_t)i;
-            v = bigru_uniform(seed, 0u, key) < pdrop ? 0.f : v * scale;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int f = f0 + i, b = b0 + threadIdx.x;
+        tile[i][threadIdx.x] = (b < B && f < F) ? dXT[(int64_t)f * R + (int64_t)t * B + b] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int b = b0 + i, f = f0 + threadIdx.x;
+        if (b < B && f < F) {
+            float v = tile[threadIdx.x][i];
+            if (pdrop > 0.f) {
+                const uint64_t key = spatial ? (uint64_t)b * F + f : ((uint64_t)b * T + t) * F + f;
+                v = bigru_uniform(seed, 0u, key) < pdrop ? 0.f : v * scale;
+            }
+            dx[((int64_t)b * T + t) * F + f] = v;
         }
-        dx[i] = v;
     }
 }
 
@@ -277,15 +284,15 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
                 Xrow = (const bf16_t*)(S + L.Yrow[l - 1]);
             }
         }
-        // 3. input projection for all t, both directions:  gi[R][D*3H] = X W_ih^T + bias
+        // 3. input projection for all t, both directions, written transposed:  giT[D*3H][R] = W_ih X^T + bias(row)
         tcg::Params g{};
-        g.M = (int)R; g.N = D * 3 * H; g.K = I; g.batch = 1; g.splitk = 1; g.mode = tcg::OUT_BF16;
-        g.C = W + L.gi; g.ldc = D * 3 * H; g.bias = (const float*)(S + L.bfold[l]); g.dbg = dbg;
-        TRY(tc_gemm(Xrow, R, I, S + L.Wih[l], D * 3 * H, I, g, st));
+        g.M = D * 3 * H; g.N = (int)R; g.K = I; g.batch = 1; g.splitk = 1; g.mode = tcg::OUT_BF16;
+        g.C = W + L.gi; g.ldc = R; g.bias = (const float*)(S + L.bfold[l]); g.bias_per_row = 1; g.dbg = dbg;
+        TRY(tc_gemm(S + L.Wih[l], D * 3 * H, I, Xrow, R, I, g, st));
         // 4. recurrence
         tcs::FwdParams f{};
         f.B = B; f.T = T; f.H = H; f.D = D;
-        f.Wimg = (const bf16_t*)(S + L.Wimg[l]); f.gi = (const bf16_t*)(W + L.gi); f.b_hn = (const float*)(S + L.bhn[l]);
+        f.Wimg = (const bf16_t*)(S + L.Wimg[l]); f.giT = (const bf16_t*)(W + L.gi); f.b_hn = (const float*)(S + L.bhn[l]);
         f.Yrow = (bf16_t*)(S + L.Yrow[l]); f.YT = (bf16_t*)(S + L.YT[l]); f.G = (bf16_t*)(S + L.G[l]);
         f.hn_out = hn ? hn + (int64_t)l * D * B * H : nullptr; f.dbg = dbg;
         {
@@ -335,8 +342,8 @@ static int backward_bf16(const bigru_plan& p, const float* params, const float* 
         // 1. BPTT scan
         tcs::BwdParams b{};
         b.B = B; b.T = T; b.H = H; b.D = D;
-        b.WTimg = (const bf16_t*)(S + L.WTimg[l]); b.G = (const bf16_t*)(S + L.G[l]); b.Yrow = (const bf16_t*)(S + L.Yrow[l]);
-        b.dY = dY; b.dh_init = l == p.L - 1 ? dhinit : nullptr;
+        b.WTimg = (const bf16_t*)(S + L.WTimg[l]); b.G = (const bf16_t*)(S + L.G[l]); b.YT = (const bf16_t*)(S + L.YT[l]);
+        b.dYT = dY; b.dh_init = l == p.L - 1 ? dhinit : nullptr;
         b.dgi_row = (bf16_t*)(W + L.gi); b.dgiT = (bf16_t*)(W + L.dgiT); b.dghT = (bf16_t*)(W + L.dghT);
         b.db_ih = grads + p.off_bih(l, 0); b.db_hh = grads + p.off_bhh(l, 0); b.dir_stride = p.ld_block(l); b.dbg = dbg;
         {
@@ -369,18 +376,20 @@ static int backward_bf16(const bigru_plan& p, const float* params, const float* 
             g.dbg = dbg;
             TRY(tc_gemm(W + L.dghT, (int64_t)D * 3 * H, R, S + L.YT[l], (int64_t)D * H, R, g, st));
         }
-        // 4. dX = dgi_row [R][D*3H] x W_ih (both directions concatenated along K)
+        // 4. dX^T [I][R] = W_ih^T (both directions concatenated along K = D*3H) x dgi_row^T
         const bool need_dx = l > 0 || dx != nullptr;
         if (need_dx) {
             tcg::Params g{};
-            g.M = (int)R; g.N = I; g.K = D * 3 * H; g.batch = 1; g.splitk = 1; g.mode = tcg::OUT_F32;
-            g.C = dYnext; g.ldc = I; g.dbg = dbg;
-            TRY(tc_gemm(W + L.gi, R, (int64_t)D * 3 * H, S + L.WihT[l], I, (int64_t)D * 3 * H, g, st));
+            g.M = I; g.N = (int)R; g.K = D * 3 * H; g.batch = 1; g.splitk = 1; g.mode = tcg::OUT_F32;
+            g.C = dYnext; g.ldc = R; g.dbg = dbg;
+            TRY(tc_gemm(S + L.WihT[l], I, (int64_t)D * 3 * H, W + L.gi, R, (int64_t)D * 3 * H, g, st));
             if (l > 0 && dropped)
                 KLAUNCH(KC_MISC, 0.0, 0.0, st, dropout_grad_rows_kernel<<<148 * 8, 256, 0, st>>>(dYnext, R, I, B, T, drop, seed, (uint32_t)l));
-            if (l == 0)
-                KLAUNCH(KC_MISC, 0.0, 0.0, st, dx_to_batch_major_kernel<<<148 * 8, 256, 0, st>>>(dYnext, dx, B, T, I,
-                                                                                            do_drop ? drop : 0.f, spatial, seed));
+            if (l == 0) {
+                dim3 grid((I + 31) / 32, (B + 31) / 32, T);
+                KLAUNCH(KC_MISC, 0.0, 0.0, st, dx_to_batch_major_kernel<<<grid, dim3(32, 8), 0, st>>>(dYnext, dx, B, T, I,
+                                                                                               do_drop ? drop : 0.f, spatial, seed));
+            }
         }
         float* tmp = dY; dY = dYnext; dYnext = tmp;
     }

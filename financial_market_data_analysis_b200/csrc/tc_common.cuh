@@ -61,16 +61,32 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// bounded wait; returns false on timeout (and records it)
+// bounded wait (wall-clock, %globaltimer): returns false after BIGRU_WAIT_NS and records the site
+#ifndef BIGRU_WAIT_NS
+#define BIGRU_WAIT_NS 2000000000ull
+#endif
+__device__ __forceinline__ unsigned long long gtime_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, unsigned int* dbg, unsigned int code) {
-    for (uint32_t i = 0; i < BIGRU_SPIN_LIMIT; ++i)
+    if (mbar_try_wait(bar, parity)) return true;
+    const unsigned long long t0 = gtime_ns();
+    for (uint32_t i = 0;; ++i) {
         if (mbar_try_wait(bar, parity)) return true;
+        if ((i & 63u) == 63u && gtime_ns() - t0 > BIGRU_WAIT_NS) break;
+    }
     report_timeout(dbg, code, parity, 0);
     return false;
 }
 __device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity, unsigned int* dbg, unsigned int code) {
-    for (uint32_t i = 0; i < BIGRU_SPIN_LIMIT; ++i)
+    if (mbar_try_wait_cluster(bar, parity)) return true;
+    const unsigned long long t0 = gtime_ns();
+    for (uint32_t i = 0;; ++i) {
         if (mbar_try_wait_cluster(bar, parity)) return true;
+        if ((i & 63u) == 63u && gtime_ns() - t0 > BIGRU_WAIT_NS) break;
+    }
     report_timeout(dbg, code, parity, 1);
     return false;
 }
@@ -123,6 +139,18 @@ __device__ __forceinline__ void bulk_s2cluster(void* dst_local_equiv, const void
         "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         ::"r"(rdst), "r"(smem_u32(src)), "r"(bytes), "r"(rbar) : "memory");
 }
+
+// TMA tile store / reduce-add smem -> global (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- TMEM ---------------------------------------------------------------------------------------
 // one full warp; writes the base address to *slot (shared)
@@ -225,7 +253,19 @@ static inline PFN_encodeTiled get_encode_tiled() {
     return fn;
 }
 
-// bf16 tensor, dims[0] innermost (contiguous); strides in BYTES for dims 1..rank-1; 128B swizzle.
+// dims[0] innermost (contiguous); strides in BYTES for dims 1..rank-1; 128B swizzle.
+static inline int make_tmap_typed(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                                  const uint64_t* strides_bytes, const uint32_t* box) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return -1;
+    cuuint64_t gdim[5]; cuuint64_t gstr[5]; cuuint32_t bx[5]; cuuint32_t es[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
 static inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                                  const uint64_t* strides_bytes, const uint32_t* box) {
     PFN_encodeTiled enc = get_encode_tiled();

@@ -12,6 +12,7 @@
 // the time-shifted h_{t-1} operand of dW_hh without materialising it.
 #pragma once
 #include "tc_common.cuh"
+#include <cstring>
 
 namespace tcg {
 
@@ -30,13 +31,16 @@ struct Params {
     void* C; int64_t ldc;     // row stride in elements
     int64_t zC;               // element offset of batch z in C
     int a_row_off[4], b_row_off[4], b_k_off[4];
-    const float* bias;        // per output column n (nullable), batch stride zBias
+    const float* bias;        // per output column n - or per row m when bias_per_row - (nullable), batch stride zBias
     int64_t zBias;
+    int bias_per_row;
+    int tma_store;            // 1: epilogue stages the tile in smem and writes it with TMA (store / reduce-add)
     unsigned int* dbg;        // watchdog record (nullable)
 };
 
 __global__ void __launch_bounds__(THREADS, 2)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC0, const __grid_constant__ CUtensorMap tmC1, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
@@ -104,7 +108,69 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         bool ok = tc::mbar_wait(accum, 0, p.dbg, 0x300);
         tc::tcgen05_fence_after();
         const float* bias = p.bias ? p.bias + z * p.zBias : nullptr;
-        if (ok) {
+        const float brow = (bias && p.bias_per_row && m < p.M) ? bias[m] : 0.f;
+        if (ok && p.tma_store) {
+            // ---- staged epilogue: TMEM -> registers -> 128B-swizzled smem boxes -> TMA store / reduce-add.
+            // The pipeline stages are free (every MMA has retired), so they serve as the staging buffer:
+            // bf16: 2 boxes of [128 rows x 64 cols], fp32: 4 boxes of [128 rows x 32 cols], 16 KB each.
+            const int ml = q * 32 + lane;
+            const uint32_t sw = (uint32_t)(ml & 7);
+            const bool is_bf16 = p.mode == OUT_BF16;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                if (nkb > 0) {
+                    tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c * 32, v);
+                    tc::tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0u;
+                }
+                const int nb = n0 + c * 32;
+                if (bias && ks == 0) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float bb = p.bias_per_row ? brow : ((nb + i < p.N) ? bias[nb + i] : 0.f);
+                        v[i] = __float_as_uint(__uint_as_float(v[i]) + bb);
+                    }
+                }
+                if (is_bf16) {
+                    uint8_t* box = smem + (size_t)(c >> 1) * 16384 + (size_t)ml * 128;
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[k4 * 8 + 2 * j]), __uint_as_float(v[k4 * 8 + 2 * j + 1]));
+                            w[j] = *reinterpret_cast<uint32_t*>(&h2);
+                        }
+                        const uint32_t chunk = ((uint32_t)((c & 1) * 4 + k4)) ^ sw;
+                        *reinterpret_cast<uint4*>(box + chunk * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                } else {
+                    uint8_t* box = smem + (size_t)c * 16384 + (size_t)ml * 128;
+#pragma unroll
+                    for (int k4 = 0; k4 < 8; ++k4) {
+                        const uint32_t chunk = ((uint32_t)k4) ^ sw;
+                        *reinterpret_cast<uint4*>(box + chunk * 16) = make_uint4(v[k4 * 4], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
+                    }
+                }
+            }
+            tc::fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp == 2 && tc::elect_one()) {
+                const CUtensorMap* tmC = z == 0 ? &tmC0 : &tmC1;
+                const int nboxes = is_bf16 ? BN / 64 : BN / 32;
+                const int bw = is_bf16 ? 64 : 32;
+                for (int b = 0; b < nboxes; ++b) {
+                    if (n0 + b * bw >= p.N) break;
+                    if (p.mode == OUT_ATOMIC_F32) tc::tma_reduce_add_2d(tmC, smem + (size_t)b * 16384, n0 + b * bw, m0);
+                    else tc::tma_store_2d(tmC, smem + (size_t)b * 16384, n0 + b * bw, m0);
+                }
+                tc::tma_store_commit();
+                tc::tma_store_wait_all();
+            }
+        } else if (ok) {
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t v[32];
@@ -126,7 +192,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
                                     float a = __uint_as_float(v[i + 2 * j]), b = __uint_as_float(v[i + 2 * j + 1]);
-                                    if (bias) { a += bias[nb + i + 2 * j]; b += bias[nb + i + 2 * j + 1]; }
+                                    if (bias) {
+                                        if (p.bias_per_row) { a += brow; b += brow; }
+                                        else { a += bias[nb + i + 2 * j]; b += bias[nb + i + 2 * j + 1]; }
+                                    }
                                     __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
                                     w[j] = *reinterpret_cast<uint32_t*>(&h2);
                                 }
@@ -135,7 +204,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         } else {
                             for (int i = 0; i < 32 && nb + i < p.N; ++i) {
                                 float a = __uint_as_float(v[i]);
-                                if (bias) a += bias[nb + i];
+                                if (bias) a += p.bias_per_row ? brow : bias[nb + i];
                                 crow[i] = __float2bfloat16(a);
                             }
                         }
@@ -143,7 +212,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         float* crow = reinterpret_cast<float*>(p.C) + z * p.zC + (int64_t)m * p.ldc + nb;
                         for (int i = 0; i < 32 && nb + i < p.N; ++i) {
                             float a = __uint_as_float(v[i]);
-                            if (bias && ks == 0) a += bias[nb + i];
+                            if (bias && ks == 0) a += p.bias_per_row ? brow : bias[nb + i];
                             if (p.mode == OUT_ATOMIC_F32) atomicAdd(crow + i, a);
                             else crow[i] = a;
                         }
@@ -165,15 +234,36 @@ static inline int make_operand_map(CUtensorMap* m, const void* base, uint64_t ro
     return make_tmap_bf16(m, base, 2, dims, strides, box);
 }
 
-static inline cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cudaStream_t st) {
+// output tile map: rows M (stride ldc elements), 128B-swizzled boxes of 128 rows x 128 bytes
+static inline int make_output_map(CUtensorMap* m, void* base, int mode, uint64_t M, uint64_t N, uint64_t ldc) {
+    const bool bf = mode == OUT_BF16;
+    const uint64_t dims[2] = {N, M};
+    const uint64_t strides[1] = {ldc * (bf ? 2u : 4u)};
+    const uint32_t box[2] = {bf ? 64u : 32u, 128u};
+    return make_tmap_typed(m, bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, 2, dims, strides, box);
+}
+
+static inline cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p_in, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
+    Params p = p_in;
+    CUtensorMap tmC[2];
+    memset(tmC, 0, sizeof(tmC));
+    // TMA epilogue needs 16-byte aligned rows and base; otherwise the direct-store epilogue is used
+    const size_t es = p.mode == OUT_BF16 ? 2 : 4;
+    bool tma_ok = p.batch <= 2 && ((p.ldc * es) % 16 == 0) && ((p.zC * es) % 16 == 0) && ((uintptr_t)p.C % 16 == 0);
+    if (tma_ok) {
+        for (int z = 0; z < p.batch; ++z)
+            if (make_output_map(&tmC[z], (uint8_t*)p.C + (size_t)z * p.zC * es, p.mode, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldc) != 0) tma_ok = false;
+        if (p.batch == 1) tmC[1] = tmC[0];
+    }
+    p.tma_store = tma_ok ? 1 : 0;
     dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.batch * p.splitk);
-    gemm_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
+    gemm_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmB, tmC[0], tmC[1], p);
     return cudaGetLastError();
 }
 

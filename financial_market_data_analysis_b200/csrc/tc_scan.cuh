@@ -15,10 +15,10 @@
 // per step is the layer output (row-major and transposed, for the next layer's GEMMs) and the gate stash.
 //
 // Layouts (time-major rows r = t*B + b, R = T*B):
-//   gi   bf16 [R][D*3H]   input projection incl. b_ih (+ b_hh for r,z)        (read)
+//   giT  bf16 [D*3H][R]   input projection, transposed, incl. b_ih (+ b_hh for r,z)   (read: 16 B per gate/thread)
 //   Yrow bf16 [R][D*H]    layer output                                        (written)
-//   YT   bf16 [D*H][R]    layer output transposed (wgrad operand)             (written)
-//   G    bf16 [R][D*4H]   r, z, n, hn = W_hn h + b_hn  (stash for backward)   (written)
+//   YT   bf16 [D*H][R]    layer output transposed (wgrad operand, h_{t-1} of the backward scan)   (written)
+//   G    bf16 thread-private stash: [d][tile][t][cta][thread][r0..7 z0..7 n0..7 hn0..7]  (64 B per thread-step)
 //   Wimg bf16 [D][H units][3][H]  per-unit rows of W_hh (r|z|n), copied to TMEM   (read once)
 #pragma once
 #include "tc_common.cuh"
@@ -28,7 +28,7 @@ namespace tcs {
 constexpr int NB = 16;            // batch rows per tile = UMMA N
 constexpr int UNITS = 128;        // hidden units per CTA = UMMA M
 constexpr int EPI_WARPS = 8;
-constexpr int THREADS = (EPI_WARPS + 2) * 32;    // + MMA/control warp + loader warp
+constexpr int THREADS = (EPI_WARPS + 1) * 32;    // + MMA/control warp
 constexpr int W_CHUNK = UNITS * 128;             // bytes of one [128 x 64] bf16 chunk
 constexpr int H_CHUNK = NB * 128;                // bytes of one [16 x 64] bf16 chunk
 
@@ -84,6 +84,11 @@ __device__ __forceinline__ void load_weights_to_tmem(const __nv_bfloat16* wrow_b
     tmem_st_wait();
 }
 
+// element offset of the 256-thread x 32-value stash block of (direction, tile, time step, CTA-in-cluster)
+__device__ __forceinline__ size_t stash_index(int d, int tile, int t, int c, int ntiles, int T, int CS) {
+    return ((((size_t)d * ntiles + tile) * T + t) * CS + c) * (size_t)(EPI_WARPS * 32 * 32);
+}
+
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
 
 static inline size_t fwd_smem_bytes(int H) {
@@ -96,7 +101,7 @@ __host__ __device__ static inline uint32_t fwd_tmem_cols(int H) { return 64 + 3 
 struct FwdParams {
     int B, T, H, D;
     const __nv_bfloat16* Wimg;
-    const __nv_bfloat16* gi;
+    const __nv_bfloat16* giT;
     const float* b_hn;            // [D][H]
     __nv_bfloat16* Yrow;
     __nv_bfloat16* YT;
@@ -169,26 +174,47 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
                 tc::umma_commit(mma_done);
             }
         }
-    } else {
+    } else if (warp < EPI_WARPS) {
         // ---- epilogue: thread = hidden unit (TMEM lane), 8 of the 16 batch columns
         const int q = warp & 3, half = warp >> 2;
         const int j = q * 32 + lane;
         const int unit = (int)c * UNITS + j;
         const int col0 = half * 8;
         const float bhn = p.b_hn[d * H + unit];
-        const int ldgi = D * 3 * H, ldy = D * H, ldg = D * 4 * H;
+        const int ldy = D * H;
         float hprev[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) hprev[i] = 0.f;
         bool ok = true;
+        // gi is streamed from HBM and does not depend on the recurrence: keep the loads two steps ahead of
+        // their use so that DRAM latency never sits on the step chain
+        const __nv_bfloat16* gbase = p.giT + (int64_t)(d * 3 * H + unit) * R + tile * NB + col0;
+        auto gi_load = [&](uint4 (&dst)[3], int step) {
+            const int tt = d == 0 ? step : T - 1 - step;
+            const __nv_bfloat16* gp = gbase + (int64_t)tt * B;                  // 8 consecutive rows = 16 B
+            dst[0] = *reinterpret_cast<const uint4*>(gp);
+            dst[1] = *reinterpret_cast<const uint4*>(gp + (int64_t)H * R);
+            dst[2] = *reinterpret_cast<const uint4*>(gp + (int64_t)2 * H * R);
+        };
+        uint4 pf0[3], pf1[3];
+        gi_load(pf0, 0);
+        if (T > 1) gi_load(pf1, 1); else { pf1[0] = pf0[0]; pf1[1] = pf0[1]; pf1[2] = pf0[2]; }
         for (int s = 0; s < T; ++s) {
             const int t = d == 0 ? s : T - 1 - s;
             const int64_t row0 = (int64_t)t * B + tile * NB + col0;
             float gr[8], gz[8], gn[8];
+            {
+                const __nv_bfloat16* t8 = reinterpret_cast<const __nv_bfloat16*>(&pf0[0]);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const __nv_bfloat16* gp = p.gi + (row0 + i) * ldgi + d * 3 * H + unit;
-                gr[i] = __bfloat162float(gp[0]); gz[i] = __bfloat162float(gp[H]); gn[i] = __bfloat162float(gp[2 * H]);
+                for (int i = 0; i < 8; ++i) gr[i] = __bfloat162float(t8[i]);
+                t8 = reinterpret_cast<const __nv_bfloat16*>(&pf0[1]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) gz[i] = __bfloat162float(t8[i]);
+                t8 = reinterpret_cast<const __nv_bfloat16*>(&pf0[2]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) gn[i] = __bfloat162float(t8[i]);
+                pf0[0] = pf1[0]; pf0[1] = pf1[1]; pf0[2] = pf1[2];
+                if (s + 2 < T) gi_load(pf1, s + 2);
             }
             float ar[8], az[8], an[8];
             if (s > 0) {
@@ -203,7 +229,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
             }
             const int buf = s & 1;
             uint8_t* hb = sH + (size_t)buf * KC * H_CHUNK + (size_t)(unit >> 6) * H_CHUNK;
-            __nv_bfloat16 hv[8];
+            __nv_bfloat16 hv[8], sr[8], sz[8], sn[8], shn[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float r = sigmoid_fast(gr[i] + ar[i]);
@@ -213,11 +239,14 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
                 const float h = fmaf(z, hprev[i] - n, n);
                 hprev[i] = h;
                 hv[i] = __float2bfloat16(h);
+                sr[i] = __float2bfloat16(r); sz[i] = __float2bfloat16(z); sn[i] = __float2bfloat16(n); shn[i] = __float2bfloat16(hn);
                 *reinterpret_cast<__nv_bfloat16*>(hb + tc::sw128_offset(col0 + i, unit & 63)) = hv[i];
                 p.Yrow[(row0 + i) * ldy + d * H + unit] = hv[i];
-                __nv_bfloat16* gs = p.G + (row0 + i) * ldg + d * 4 * H + unit;
-                gs[0] = __float2bfloat16(r); gs[H] = __float2bfloat16(z); gs[2 * H] = __float2bfloat16(n);
-                gs[3 * H] = __float2bfloat16(hn);
+            }
+            {
+                uint4* gs = reinterpret_cast<uint4*>(p.G + stash_index(d, tile, t, (int)c, ntiles, T, CS) + (size_t)threadIdx.x * 32);
+                gs[0] = *reinterpret_cast<uint4*>(sr); gs[1] = *reinterpret_cast<uint4*>(sz);
+                gs[2] = *reinterpret_cast<uint4*>(sn); gs[3] = *reinterpret_cast<uint4*>(shn);
             }
             *reinterpret_cast<uint4*>(p.YT + (int64_t)(d * H + unit) * R + row0) = *reinterpret_cast<uint4*>(hv);
             if (s == T - 1 && p.hn_out) {
@@ -284,7 +313,7 @@ __global__ void pack_whh_image_kernel(const float* __restrict__ w_hh, __nv_bfloa
 // transposed form for the weight-gradient GEMMs; bias gradients accumulate in registers over all steps.
 // The operand tile is single-buffered (24 KB): a peer may only overwrite it after this CTA's MMA of the
 // current step has retired, which the epilogue leader signals with a remote mbarrier arrive.
-//   G, Yrow (h_{t-1}), dY fp32 [R][D*H]                                         (read)
+//   G (thread-private stash), YT (h_{t-1}, transposed), dYT fp32 [D*H][R]       (read, 16-byte vectors)
 //   dgi_row bf16 [R][D*3H], dgiT / dghT bf16 [D*3H][R]                          (written)
 // =================================================================================================
 static inline size_t bwd_smem_bytes(int H) {
@@ -298,8 +327,8 @@ struct BwdParams {
     int B, T, H, D;
     const __nv_bfloat16* WTimg;     // [D][H units][3H]  rows of W_hh^T, copied to TMEM
     const __nv_bfloat16* G;
-    const __nv_bfloat16* Yrow;
-    const float* dY;                // [R][D*H]
+    const __nv_bfloat16* YT;        // [D*H][R]
+    const float* dYT;               // [D*H][R]
     const float* dh_init;           // [D][B][H] nullable: d(last hidden) of the top layer
     __nv_bfloat16* dgi_row;
     __nv_bfloat16* dgiT;
@@ -310,7 +339,7 @@ struct BwdParams {
     unsigned int* dbg;
 };
 
-__global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParams p) {
+__global__ void __maxnreg__(216) gru_scan_bwd_kernel(const BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int H = p.H, KC = H / 64, KC3 = 3 * KC, CS = H / UNITS, B = p.B, T = p.T, D = p.D;
@@ -370,31 +399,58 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
                 tc::umma_commit(mma_done);
             }
         }
-    } else {
+    } else if (warp < EPI_WARPS) {
         const int q = warp & 3, half = warp >> 2;
         const int j = q * 32 + lane;
         const int unit = (int)c * UNITS + j;
         const int col0 = half * 8;
-        const int ldy = D * H, ldg = D * 4 * H, ldi = D * 3 * H;
+        const int ldi = D * 3 * H;
         float dhz[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
             dhz[i] = p.dh_init ? p.dh_init[((int64_t)d * B + tile * NB + col0 + i) * H + unit] : 0.f;
         float sb_r = 0.f, sb_z = 0.f, sb_n = 0.f, sb_nr = 0.f;
         bool ok = true;
+        // stash, h_{t-1} and dY do not depend on the recurrence: loads run two steps ahead of their use
+        struct Pre { uint4 g[4]; uint4 hp; float4 dy0, dy1; };
+        auto pre_load = [&](Pre& q_, int step) {
+            const int tt = d == 0 ? T - 1 - step : step;
+            const bool fst = d == 0 ? tt == 0 : tt == T - 1;
+            const int64_t r0 = (int64_t)tt * B + tile * NB + col0;
+            const uint4* gs = reinterpret_cast<const uint4*>(p.G + stash_index(d, tile, tt, (int)c, ntiles, T, CS) + (size_t)threadIdx.x * 32);
+            q_.g[0] = gs[0]; q_.g[1] = gs[1]; q_.g[2] = gs[2]; q_.g[3] = gs[3];
+            if (fst) q_.hp = make_uint4(0u, 0u, 0u, 0u);                     // bf16 zeros: h_prev = 0 at the first forward step
+            else q_.hp = *reinterpret_cast<const uint4*>(p.YT + (int64_t)(d * H + unit) * R + r0 + (d == 0 ? -(int64_t)B : (int64_t)B));
+            const float4* dyp = reinterpret_cast<const float4*>(p.dYT + (int64_t)(d * H + unit) * R + r0);
+            q_.dy0 = dyp[0]; q_.dy1 = dyp[1];
+        };
+        Pre pa, pb;
+        pre_load(pa, 0);
+        if (T > 1) pre_load(pb, 1); else pb = pa;
         for (int s = 0; s < T; ++s) {
             const int t = d == 0 ? T - 1 - s : s;
-            const bool first = d == 0 ? t == 0 : t == T - 1;         // first step of the FORWARD recurrence: h_prev = 0
             const int64_t row0 = (int64_t)t * B + tile * NB + col0;
-            const int64_t prow0 = row0 + (d == 0 ? -(int64_t)B : (int64_t)B);
             float vr[8], vz[8], vn[8], vhn[8], vhp[8], vdy[8];
+            {
+                const __nv_bfloat16* t8 = reinterpret_cast<const __nv_bfloat16*>(&pa.g[0]);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const __nv_bfloat16* gp = p.G + (row0 + i) * ldg + d * 4 * H + unit;
-                vr[i] = __bfloat162float(gp[0]); vz[i] = __bfloat162float(gp[H]);
-                vn[i] = __bfloat162float(gp[2 * H]); vhn[i] = __bfloat162float(gp[3 * H]);
-                vhp[i] = first ? 0.f : __bfloat162float(p.Yrow[(prow0 + i) * ldy + d * H + unit]);
-                vdy[i] = p.dY[(row0 + i) * ldy + d * H + unit];
+                for (int i = 0; i < 8; ++i) vr[i] = __bfloat162float(t8[i]);
+                t8 = reinterpret_cast<const __nv_bfloat16*>(&pa.g[1]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vz[i] = __bfloat162float(t8[i]);
+                t8 = reinterpret_cast<const __nv_bfloat16*>(&pa.g[2]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vn[i] = __bfloat162float(t8[i]);
+                t8 = reinterpret_cast<const __nv_bfloat16*>(&pa.g[3]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vhn[i] = __bfloat162float(t8[i]);
+                t8 = reinterpret_cast<const __nv_bfloat16*>(&pa.hp);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vhp[i] = __bfloat162float(t8[i]);
+                vdy[0] = pa.dy0.x; vdy[1] = pa.dy0.y; vdy[2] = pa.dy0.z; vdy[3] = pa.dy0.w;
+                vdy[4] = pa.dy1.x; vdy[5] = pa.dy1.y; vdy[6] = pa.dy1.z; vdy[7] = pa.dy1.w;
+                pa = pb;
+                if (s + 2 < T) pre_load(pb, s + 2);
             }
             float acc[8];
             if (s > 0) {

@@ -76,6 +76,7 @@ static int run_case(int M, int N, int K, int mode, int splitk, int kshift, bool 
 }
 
 int main() {
+    setvbuf(stdout, NULL, _IONBF, 0);
     int bad = 0;
     bad += run_case(128, 128, 64, tcg::OUT_F32, 1, 0, false, 0, 0);
     bad += run_case(128, 128, 256, tcg::OUT_F32, 1, 0, true, 0, 0);

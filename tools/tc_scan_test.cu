@@ -22,8 +22,9 @@ static int run_case(int B, int T, int H, int D, int reps) {
     CK(cudaMalloc(&d_whh, whh.size() * 4)); CK(cudaMalloc(&d_bhn, bhn.size() * 4)); CK(cudaMalloc(&d_img, img_elems * 2));
     CK(cudaMalloc(&d_gi, gi.size() * 2)); CK(cudaMalloc(&d_Y, (size_t)R * D * H * 2)); CK(cudaMalloc(&d_YT, (size_t)R * D * H * 2));
     CK(cudaMalloc(&d_G, (size_t)R * D * 4 * H * 2)); CK(cudaMalloc(&d_hn, (size_t)D * B * H * 4)); CK(cudaMalloc(&dbg, 64));
-    std::vector<__nv_bfloat16> gih(gi.size());
-    for (size_t i = 0; i < gi.size(); ++i) gih[i] = __float2bfloat16(gi[i]);
+    std::vector<__nv_bfloat16> gih(gi.size());        // device copy is TRANSPOSED: giT[D*3H][R]
+    for (long r = 0; r < R; ++r)
+        for (int q = 0; q < D * 3 * H; ++q) gih[(size_t)q * R + r] = __float2bfloat16(gi[(size_t)r * D * 3 * H + q]);
     CK(cudaMemcpy(d_whh, whh.data(), whh.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_bhn, bhn.data(), bhn.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_gi, gih.data(), gih.size() * 2, cudaMemcpyHostToDevice));
@@ -33,7 +34,7 @@ static int run_case(int B, int T, int H, int D, int reps) {
         CK(cudaGetLastError());
     }
     tcs::FwdParams p{};
-    p.B = B; p.T = T; p.H = H; p.D = D; p.Wimg = d_img; p.gi = d_gi; p.b_hn = d_bhn; p.Yrow = d_Y; p.YT = d_YT; p.G = d_G;
+    p.B = B; p.T = T; p.H = H; p.D = D; p.Wimg = d_img; p.giT = d_gi; p.b_hn = d_bhn; p.Yrow = d_Y; p.YT = d_YT; p.G = d_G;
     p.hn_out = d_hn; p.dbg = dbg;
     CK(tcs::launch_fwd(p, 0));
     CK(cudaDeviceSynchronize());
@@ -77,11 +78,14 @@ static int run_case(int B, int T, int H, int D, int reps) {
                     const float hnv = (float)a[2] + bhn[d * H + j];
                     const float n = tanhf(gp[2 * H + j] + r * hnv);
                     hnew[j] = n + z * (hs[j] - n);
-                    const size_t gidx = (size_t)row * D * 4 * H + d * 4 * H + j;
+                    // thread-private stash: [d][tile][t][cta][thread = warp*32+lane][gate][8 columns]
+                    const int cta = j / 128, jj = j % 128, tile = b / 16, bb = b % 16;
+                    const int tid = ((jj / 32) + 4 * (bb / 8)) * 32 + (jj % 32);
+                    const size_t gidx = (((((size_t)d * (B / 16) + tile) * T + t) * CS + cta) * 256 + tid) * 32 + (bb % 8);
                     eG = fmax(eG, fabs(r - __bfloat162float(G[gidx])));
-                    eG = fmax(eG, fabs(z - __bfloat162float(G[gidx + H])));
-                    eG = fmax(eG, fabs(n - __bfloat162float(G[gidx + 2 * H])));
-                    eG = fmax(eG, fabs(hnv - __bfloat162float(G[gidx + 3 * H])));
+                    eG = fmax(eG, fabs(z - __bfloat162float(G[gidx + 8])));
+                    eG = fmax(eG, fabs(n - __bfloat162float(G[gidx + 16])));
+                    eG = fmax(eG, fabs(hnv - __bfloat162float(G[gidx + 24])));
                 }
                 for (int j = 0; j < H; ++j) {
                     hs[j] = hnew[j]; hq[j] = bf(hnew[j]);
@@ -99,6 +103,7 @@ static int run_case(int B, int T, int H, int D, int reps) {
 }
 
 int main() {
+    setvbuf(stdout, NULL, _IONBF, 0);
     int bad = 0;
     bad += run_case(16, 1, 128, 1, 0);
     bad += run_case(16, 4, 128, 1, 0);
