@@ -339,7 +339,7 @@ struct BwdParams {
     unsigned int* dbg;
 };
 
-__global__ void __maxnreg__(216) gru_scan_bwd_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int H = p.H, KC = H / 64, KC3 = 3 * KC, CS = H / UNITS, B = p.B, T = p.T, D = p.D;
