@@ -24,7 +24,7 @@ static int bf16_plan_check(const bigru_plan& p) {
 }
 
 struct Bf16Layout {            // byte offsets, 1024-aligned
-    size_t Yrow[16], YT[16], G[16], Xrow[16], XT[16];            // stash: activations
+    size_t Yrow[16], YT[16], YB[16], G[16], Xrow[16], XT[16];    // stash: activations
     size_t Wih[16], WihT[16], Wimg[16], WTimg[16], bfold[16], bhn[16];   // stash: packed weights
     size_t cat, arg, dbg, stash_total;
     size_t gi, dgiT, dghT, dYa, dYb, dcat, dhinit, scratch_total;
@@ -38,6 +38,7 @@ static Bf16Layout bf16_layout(const bigru_plan& p) {
         const size_t I = p.in_size(l);
         L.Yrow[l] = o; o = al(o + R * DH * 2);
         L.YT[l] = o; o = al(o + R * DH * 2);
+        L.YB[l] = o; o = al(o + R * DH * 2);
         L.G[l] = o; o = al(o + R * D * 4 * H * 2);
         L.Xrow[l] = o; o = al(o + R * I * 2);
         L.XT[l] = o; o = al(o + R * I * 2);
@@ -116,17 +117,24 @@ __global__ void dropout_rows_kernel(const bf16_t* __restrict__ Y, bf16_t* __rest
         XT[(int64_t)cidx * R + r] = o;
     }
 }
-// gradient of the same dropout, in place on the TRANSPOSED fp32 gradient [cols][R]
-__global__ void dropout_grad_rows_kernel(float* __restrict__ dXT, int64_t R, int cols, int B, int T, float pdrop,
+// gradient of the same dropout, in place on the BLOCKED fp32 gradient [d][tile][t][cta][thread][8] (see tc_gemm.cuh)
+__global__ void dropout_grad_rows_kernel(float* __restrict__ dYB, int64_t R, int cols, int B, int T, int H, float pdrop,
                                          uint64_t seed, uint32_t stream) {
     const float scale = 1.f / (1.f - pdrop);
     const int64_t total = R * cols;
+    const int CS = H / 128, ntl = B / 16;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i % R;
-        const int cidx = i / R;
-        const int64_t b = r % B, t = r / B;
-        const uint64_t key = ((uint64_t)b * T + t) * cols + cidx;
-        dXT[i] = bigru_uniform(seed, stream, key) < pdrop ? 0.f : dXT[i] * scale;
+        const int i8 = i & 7;
+        int64_t e = i >> 3;
+        const int tid = e % 256; e /= 256;
+        const int c = e % CS; e /= CS;
+        const int t = e % T; e /= T;
+        const int tile = e % ntl;
+        const int d = e / ntl;
+        const int unit = c * 128 + ((tid >> 5) & 3) * 32 + (tid & 31);
+        const int64_t b = tile * 16 + (tid >> 7) * 8 + i8;
+        const uint64_t key = ((uint64_t)b * T + t) * cols + (uint64_t)(d * H + unit);
+        dYB[i] = bigru_uniform(seed, stream, key) < pdrop ? 0.f : dYB[i] * scale;
     }
 }
 
@@ -172,22 +180,36 @@ __global__ void head_pool_tm_kernel(const bf16_t* __restrict__ Y, float* __restr
     c[j] = last; c[H + j] = mx; c[2 * H + j] = sum / (float)T;
     arg[idx] = am;
 }
-// dY^T (fp32 [D*H][R], time-major columns) of the top layer and the initial dh carry [D][B][H]
-__global__ void head_bwd_dy_tm_kernel(const float* __restrict__ dcat, const int* __restrict__ arg, float* __restrict__ dYT,
+// blocked dY (fp32, layout of tc_gemm OUT_SCAN_F32 with G = 1) of the top layer and the initial dh carry [D][B][H]
+__global__ void head_bwd_dy_tm_kernel(const float* __restrict__ dcat, const int* __restrict__ arg, float* __restrict__ dYB,
                                       float* __restrict__ dhinit, int B, int T, int H, int D) {
-    const int64_t R = (int64_t)B * T;
+    // one thread per (tile, t, cta, tid): writes its 8 values for both directions
+    const int CS = H / 128, ntl = B / 16;
+    const int64_t nthreads = (int64_t)ntl * T * CS * 256;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= R * H) return;
-    const int64_t r = idx % R;
-    const int j = idx / R;
-    const int b = r % B, t = r / B;
-    const float* dc = dcat + (int64_t)b * 3 * H;
-    const float v = dc[2 * H + j] / (float)T + (arg[(int64_t)b * H + j] == t ? dc[H + j] : 0.f);
-    dYT[(int64_t)j * R + r] = v;
-    if (D == 2) dYT[(int64_t)(H + j) * R + r] = v;
-    if (t == 0) {
-        dhinit[(int64_t)b * H + j] = dc[j];
-        if (D == 2) dhinit[((int64_t)B + b) * H + j] = dc[j];
+    if (idx >= nthreads) return;
+    int64_t e = idx;
+    const int tid = e % 256; e /= 256;
+    const int c = e % CS; e /= CS;
+    const int t = e % T;
+    const int tile = e / T;
+    const int unit = c * 128 + ((tid >> 5) & 3) * 32 + (tid & 31);
+    const int b0 = tile * 16 + (tid >> 7) * 8;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int b = b0 + i;
+        const float* dc = dcat + (int64_t)b * 3 * H;
+        v[i] = dc[2 * H + unit] / (float)T + (arg[(int64_t)b * H + unit] == t ? dc[H + unit] : 0.f);
+        if (t == 0) {
+            dhinit[(int64_t)b * H + unit] = dc[unit];
+            if (D == 2) dhinit[((int64_t)B + b) * H + unit] = dc[unit];
+        }
+    }
+    for (int d = 0; d < D; ++d) {
+        float4* o = reinterpret_cast<float4*>(dYB + ((((int64_t)d * ntl + tile) * T + t) * CS + c) * 256 * 8 + (int64_t)tid * 8);
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[1] = make_float4(v[4], v[5], v[6], v[7]);
     }
 }
 // dX^T of layer 0 (fp32 [F][R]) back to the caller's [B][T][F] (+ input-dropout mask); 32x32 smem transpose
@@ -284,16 +306,17 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
                 Xrow = (const bf16_t*)(S + L.Yrow[l - 1]);
             }
         }
-        // 3. input projection for all t, both directions, written transposed:  giT[D*3H][R] = W_ih X^T + bias(row)
+        // 3. input projection for all t, both directions, written in the scan kernel's blocked layout:  W_ih X^T + bias(row)
         tcg::Params g{};
-        g.M = D * 3 * H; g.N = (int)R; g.K = I; g.batch = 1; g.splitk = 1; g.mode = tcg::OUT_BF16;
+        g.M = D * 3 * H; g.N = (int)R; g.K = I; g.batch = 1; g.splitk = 1; g.mode = tcg::OUT_SCAN_BF16;
+        g.blk = tcg::ScanBlk{T, B, H, 3};
         g.C = W + L.gi; g.ldc = R; g.bias = (const float*)(S + L.bfold[l]); g.bias_per_row = 1; g.dbg = dbg;
         TRY(tc_gemm(S + L.Wih[l], D * 3 * H, I, Xrow, R, I, g, st));
         // 4. recurrence
         tcs::FwdParams f{};
         f.B = B; f.T = T; f.H = H; f.D = D;
-        f.Wimg = (const bf16_t*)(S + L.Wimg[l]); f.giT = (const bf16_t*)(W + L.gi); f.b_hn = (const float*)(S + L.bhn[l]);
-        f.Yrow = (bf16_t*)(S + L.Yrow[l]); f.YT = (bf16_t*)(S + L.YT[l]); f.G = (bf16_t*)(S + L.G[l]);
+        f.Wimg = (const bf16_t*)(S + L.Wimg[l]); f.giB = (const bf16_t*)(W + L.gi); f.b_hn = (const float*)(S + L.bhn[l]);
+        f.Yrow = (bf16_t*)(S + L.Yrow[l]); f.YT = (bf16_t*)(S + L.YT[l]); f.G = (bf16_t*)(S + L.G[l]); f.YB = (bf16_t*)(S + L.YB[l]);
         f.hn_out = hn ? hn + (int64_t)l * D * B * H : nullptr; f.dbg = dbg;
         {
             ProfScope ps(KC_TC_SCAN_FWD, 2.0 * 3 * H * H * (double)R * D, 0.0, st);
@@ -335,15 +358,15 @@ static int backward_bf16(const bigru_plan& p, const float* params, const float* 
     float* dY = (float*)(W + L.dYa);
     float* dYnext = (float*)(W + L.dYb);
     float* dhinit = (float*)(W + L.dhinit);
-    KLAUNCH(KC_HEAD, 0.0, 0.0, st, head_bwd_dy_tm_kernel<<<nblk2(R * H, 256), 256, 0, st>>>(dcat, (const int*)(S + L.arg), dY,
+    KLAUNCH(KC_HEAD, 0.0, 0.0, st, head_bwd_dy_tm_kernel<<<nblk2(R * H / 8, 256), 256, 0, st>>>(dcat, (const int*)(S + L.arg), dY,
                                                                                            dhinit, B, T, H, D));
     for (int l = p.L - 1; l >= 0; --l) {
         const int I = (int)p.in_size(l);
         // 1. BPTT scan
         tcs::BwdParams b{};
         b.B = B; b.T = T; b.H = H; b.D = D;
-        b.WTimg = (const bf16_t*)(S + L.WTimg[l]); b.G = (const bf16_t*)(S + L.G[l]); b.YT = (const bf16_t*)(S + L.YT[l]);
-        b.dYT = dY; b.dh_init = l == p.L - 1 ? dhinit : nullptr;
+        b.WTimg = (const bf16_t*)(S + L.WTimg[l]); b.G = (const bf16_t*)(S + L.G[l]); b.YB = (const bf16_t*)(S + L.YB[l]);
+        b.dYB = dY; b.dh_init = l == p.L - 1 ? dhinit : nullptr;
         b.dgi_row = (bf16_t*)(W + L.gi); b.dgiT = (bf16_t*)(W + L.dgiT); b.dghT = (bf16_t*)(W + L.dghT);
         b.db_ih = grads + p.off_bih(l, 0); b.db_hh = grads + p.off_bhh(l, 0); b.dir_stride = p.ld_block(l); b.dbg = dbg;
         {
@@ -376,15 +399,18 @@ static int backward_bf16(const bigru_plan& p, const float* params, const float* 
             g.dbg = dbg;
             TRY(tc_gemm(W + L.dghT, (int64_t)D * 3 * H, R, S + L.YT[l], (int64_t)D * H, R, g, st));
         }
-        // 4. dX^T [I][R] = W_ih^T (both directions concatenated along K = D*3H) x dgi_row^T
+        // 4. dX^T = W_ih^T (both directions concatenated along K = D*3H) x dgi_row^T.  For l > 0 it is written directly in
+        //    the blocked layout the next backward scan reads; for layer 0 (caller wants dx) as [F][R] and then re-laid.
         const bool need_dx = l > 0 || dx != nullptr;
         if (need_dx) {
             tcg::Params g{};
-            g.M = I; g.N = (int)R; g.K = D * 3 * H; g.batch = 1; g.splitk = 1; g.mode = tcg::OUT_F32;
+            g.M = I; g.N = (int)R; g.K = D * 3 * H; g.batch = 1; g.splitk = 1;
+            g.mode = l > 0 ? tcg::OUT_SCAN_F32 : tcg::OUT_F32;
+            g.blk = tcg::ScanBlk{T, B, H, 1};
             g.C = dYnext; g.ldc = R; g.dbg = dbg;
             TRY(tc_gemm(S + L.WihT[l], I, (int64_t)D * 3 * H, W + L.gi, R, (int64_t)D * 3 * H, g, st));
             if (l > 0 && dropped)
-                KLAUNCH(KC_MISC, 0.0, 0.0, st, dropout_grad_rows_kernel<<<148 * 8, 256, 0, st>>>(dYnext, R, I, B, T, drop, seed, (uint32_t)l));
+                KLAUNCH(KC_MISC, 0.0, 0.0, st, dropout_grad_rows_kernel<<<148 * 8, 256, 0, st>>>(dYnext, R, I, B, T, H, drop, seed, (uint32_t)l));
             if (l == 0) {
                 dim3 grid((I + 31) / 32, (B + 31) / 32, T);
                 KLAUNCH(KC_MISC, 0.0, 0.0, st, dx_to_batch_major_kernel<<<grid, dim3(32, 8), 0, st>>>(dYnext, dx, B, T, I,

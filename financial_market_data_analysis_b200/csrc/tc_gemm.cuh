@@ -22,7 +22,15 @@ constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
 constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int THREADS = 192;
 
-enum { OUT_F32 = 0, OUT_BF16 = 1, OUT_ATOMIC_F32 = 2 };
+enum { OUT_F32 = 0, OUT_BF16 = 1, OUT_ATOMIC_F32 = 2, OUT_SCAN_BF16 = 3, OUT_SCAN_F32 = 4 };
+
+// "scan-private" blocked output (modes OUT_SCAN_*): rows m = (d, g, unit), columns n = (t, b) are scattered
+// so that every thread of the recurrence kernel finds the values of one time step in one contiguous run:
+//   elem(m, n) = (((((d*ntiles + tile)*T + t)*CS + c)*G + g)*256 + tid)*8 + i        (gate-major inside a block)
+//   tile = b/16, c = unit/128, tid = ((unit%128)/32 + 4*((b%16)/8))*32 + unit%32, i = b%8
+// so one (direction, tile, step, CTA) block is G*4 KB contiguous (one bulk copy for the scan kernel) and a warp of
+// this epilogue (32 consecutive units, fixed b-run) writes 512 contiguous bytes.
+struct ScanBlk { int T, B, H, G; };
 
 struct Params {
     int M, N, K;              // K = full reduction length (split across splitk slices)
@@ -34,6 +42,7 @@ struct Params {
     const float* bias;        // per output column n - or per row m when bias_per_row - (nullable), batch stride zBias
     int64_t zBias;
     int bias_per_row;
+    ScanBlk blk;              // OUT_SCAN_* geometry
     int tma_store;            // 1: epilogue stages the tile in smem and writes it with TMA (store / reduce-add)
     unsigned int* dbg;        // watchdog record (nullable)
 };
@@ -182,7 +191,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     for (int i = 0; i < 32; ++i) v[i] = 0u;
                 }
                 const int nb = n0 + c * 32;
-                if (m < p.M && nb < p.N) {
+                if (m < p.M && nb < p.N && p.mode >= OUT_SCAN_BF16) {
+                    // blocked store: 8 consecutive b (one thread-run of the scan kernel) = one 16/32-byte store
+                    const int H = p.blk.H, G = p.blk.G, Bb = p.blk.B, Tt = p.blk.T;
+                    const int dd = m / (G * H), gg = (m / H) % G, unit = m % H;
+                    const int CSs = H / 128, cc = unit / 128, ju = unit % 128;
+                    const int ntl = Bb / 16;
+#pragma unroll
+                    for (int i8 = 0; i8 < 32; i8 += 8) {
+                        const int n = nb + i8;
+                        if (n >= p.N) break;
+                        const int t = n / Bb, b = n % Bb;
+                        const int tile = b >> 4, half = (b >> 3) & 1;
+                        const int tid = ((ju >> 5) + 4 * half) * 32 + (ju & 31);
+                        const size_t e = ((((((size_t)dd * ntl + tile) * Tt + t) * CSs + cc) * G + gg) * 256 + tid) * 8;
+                        float f[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[i8 + j]) + (bias ? (p.bias_per_row ? brow : bias[n + j]) : 0.f);
+                        if (p.mode == OUT_SCAN_BF16) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                                w[j] = *reinterpret_cast<uint32_t*>(&h2);
+                            }
+                            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + e) = make_uint4(w[0], w[1], w[2], w[3]);
+                        } else {
+                            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + e);
+                            o[0] = make_float4(f[0], f[1], f[2], f[3]);
+                            o[1] = make_float4(f[4], f[5], f[6], f[7]);
+                        }
+                    }
+                } else if (m < p.M && nb < p.N) {
                     if (p.mode == OUT_BF16) {
                         __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + z * p.zC + (int64_t)m * p.ldc + nb;
                         if (nb + 32 <= p.N && (p.ldc % 8 == 0)) {
@@ -255,7 +295,7 @@ static inline cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB,
     memset(tmC, 0, sizeof(tmC));
     // TMA epilogue needs 16-byte aligned rows and base; otherwise the direct-store epilogue is used
     const size_t es = p.mode == OUT_BF16 ? 2 : 4;
-    bool tma_ok = p.batch <= 2 && ((p.ldc * es) % 16 == 0) && ((p.zC * es) % 16 == 0) && ((uintptr_t)p.C % 16 == 0);
+    bool tma_ok = p.mode < OUT_SCAN_BF16 && p.batch <= 2 && ((p.ldc * es) % 16 == 0) && ((p.zC * es) % 16 == 0) && ((uintptr_t)p.C % 16 == 0);
     if (tma_ok) {
         for (int z = 0; z < p.batch; ++z)
             if (make_output_map(&tmC[z], (uint8_t*)p.C + (size_t)z * p.zC * es, p.mode, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldc) != 0) tma_ok = false;

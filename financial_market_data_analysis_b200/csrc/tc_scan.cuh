@@ -15,10 +15,14 @@
 // per step is the layer output (row-major and transposed, for the next layer's GEMMs) and the gate stash.
 //
 // Layouts (time-major rows r = t*B + b, R = T*B):
-//   giT  bf16 [D*3H][R]   input projection, transposed, incl. b_ih (+ b_hh for r,z)   (read: 16 B per gate/thread)
+// Blocked ("scan-private") layouts: block (d, tile, t, cta) = (((d*ntiles + tile)*T + t)*CS + cta); inside a block
+// [gate][thread 0..255][8 batch columns], so a block is one contiguous run that a single cp.async.bulk prefetches
+// into a shared-memory ring several steps ahead (per-step HBM latency never sits on the step chain):
+//   giB  bf16 [block][3][256][8]   input projection incl. b_ih (+ b_hh for r,z), written by tc_gemm OUT_SCAN_BF16 (read)
+//   G    bf16 [block][4][256][8]   r, z, n, hn = W_hn h + b_hn  (stash for backward)              (written)
+//   YB   bf16 [block][256][8]      h_t (h_{t-1} of the backward scan)                            (written)
 //   Yrow bf16 [R][D*H]    layer output                                        (written)
 //   YT   bf16 [D*H][R]    layer output transposed (wgrad operand, h_{t-1} of the backward scan)   (written)
-//   G    bf16 thread-private stash: [d][tile][t][cta][thread][r0..7 z0..7 n0..7 hn0..7]  (64 B per thread-step)
 //   Wimg bf16 [D][H units][3][H]  per-unit rows of W_hh (r|z|n), copied to TMEM   (read once)
 #pragma once
 #include "tc_common.cuh"
@@ -28,7 +32,7 @@ namespace tcs {
 constexpr int NB = 16;            // batch rows per tile = UMMA N
 constexpr int UNITS = 128;        // hidden units per CTA = UMMA M
 constexpr int EPI_WARPS = 8;
-constexpr int THREADS = (EPI_WARPS + 1) * 32;    // + MMA/control warp
+constexpr int THREADS = (EPI_WARPS + 2) * 32;    // + MMA/control warp + input-prefetch warp
 constexpr int W_CHUNK = UNITS * 128;             // bytes of one [128 x 64] bf16 chunk
 constexpr int H_CHUNK = NB * 128;                // bytes of one [16 x 64] bf16 chunk
 
@@ -84,16 +88,24 @@ __device__ __forceinline__ void load_weights_to_tmem(const __nv_bfloat16* wrow_b
     tmem_st_wait();
 }
 
-// element offset of the 256-thread x 32-value stash block of (direction, tile, time step, CTA-in-cluster)
-__device__ __forceinline__ size_t stash_index(int d, int tile, int t, int c, int ntiles, int T, int CS) {
-    return ((((size_t)d * ntiles + tile) * T + t) * CS + c) * (size_t)(EPI_WARPS * 32 * 32);
+// block index of (direction, tile, time step, CTA-in-cluster)
+__device__ __forceinline__ size_t blk_index(int d, int tile, int t, int c, int ntiles, int T, int CS) {
+    return (((size_t)d * ntiles + tile) * T + t) * CS + c;
 }
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
 
+constexpr int GI_BLOCK = 3 * 256 * 16;    // bytes of one giB block
+constexpr int G_BLOCK = 4 * 256 * 16;     // bytes of one stash block
+constexpr int YB_BLOCK = 256 * 16;        // bytes of one blocked-h block
+constexpr int DY_BLOCK = 256 * 32;        // bytes of one blocked fp32 dY block
+constexpr int NSF = 4;                    // forward input ring depth
+constexpr int NSB = 3;                    // backward input ring depth
+constexpr int BWD_STAGE = G_BLOCK + YB_BLOCK + DY_BLOCK;
+
 static inline size_t fwd_smem_bytes(int H) {
     const int KC = H / 64;
-    return (size_t)2 * KC * H_CHUNK + 1024 + 256;
+    return (size_t)2 * KC * H_CHUNK + (size_t)NSF * GI_BLOCK + 1024 + 256;
 }
 constexpr uint32_t FWD_A_COL = 64;        // accumulators in columns [0, 48), weights from column 64
 __host__ __device__ static inline uint32_t fwd_tmem_cols(int H) { return 64 + 3 * H / 2 <= 256 ? 256u : 512u; }
@@ -101,11 +113,12 @@ __host__ __device__ static inline uint32_t fwd_tmem_cols(int H) { return 64 + 3 
 struct FwdParams {
     int B, T, H, D;
     const __nv_bfloat16* Wimg;
-    const __nv_bfloat16* giT;
+    const __nv_bfloat16* giB;
     const float* b_hn;            // [D][H]
     __nv_bfloat16* Yrow;
     __nv_bfloat16* YT;
     __nv_bfloat16* G;
+    __nv_bfloat16* YB;
     float* hn_out;                // [D][B][H] fp32, nullable
     unsigned int* dbg;
 };
@@ -114,11 +127,14 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int H = p.H, KC = H / 64, CS = H / UNITS, B = p.B, T = p.T, D = p.D;
-    uint8_t* sH = smem;                                    // [2][KC][H_CHUNK]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sH + (size_t)2 * KC * H_CHUNK);
-    uint64_t* h_full = bars + 1;       // [2]
-    uint64_t* mma_done = bars + 3;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    uint8_t* sH = smem;                                    // [2][KC][H_CHUNK]  h operand tiles
+    uint8_t* sIn = sH + (size_t)2 * KC * H_CHUNK;          // [NSF][GI_BLOCK]   prefetched gi blocks
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + (size_t)NSF * GI_BLOCK);
+    uint64_t* h_full = bars;           // [2]
+    uint64_t* mma_done = bars + 2;
+    uint64_t* in_full = bars + 3;      // [NSF]
+    uint64_t* in_empty = bars + 3 + NSF;   // [NSF]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + 2 * NSF);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t c = CS > 1 ? tc::cluster_ctarank() : 0u;
@@ -131,6 +147,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
         tc::mbar_init(&h_full[0], 2);
         tc::mbar_init(&h_full[1], 2);
         tc::mbar_init(mma_done, 1);
+        for (int i = 0; i < NSF; ++i) { tc::mbar_init(&in_full[i], 1); tc::mbar_init(&in_empty[i], EPI_WARPS); }
         tc::fence_mbar_init();
     }
     if (warp == EPI_WARPS) tc::tmem_alloc(tmem_slot, fwd_tmem_cols(H));
@@ -147,7 +164,21 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
     __syncthreads();
     tc::tcgen05_fence_after();
 
-    if (warp == EPI_WARPS) {
+    if (warp == EPI_WARPS + 1) {
+        // ---- input prefetch: one bulk copy (12 KB) per step into the ring, up to NSF steps ahead
+        if (tc::elect_one()) {
+            bool ok = true;
+            for (int s = 0; s < T; ++s) {
+                const int st = s % NSF;
+                if (s >= NSF && ok) ok = tc::mbar_wait(&in_empty[st], ((s / NSF) - 1) & 1, p.dbg, 0x300 + (s & 0xff));
+                const int t = d == 0 ? s : T - 1 - s;
+                tc::mbar_arrive_expect_tx(&in_full[st], GI_BLOCK);
+                tc::bulk_g2s(sIn + (size_t)st * GI_BLOCK,
+                             reinterpret_cast<const uint8_t*>(p.giB) + blk_index(d, tile, t, (int)c, ntiles, T, CS) * GI_BLOCK,
+                             GI_BLOCK, &in_full[st]);
+            }
+        }
+    } else if (warp == EPI_WARPS) {
         // ---- MMA issuer
         if (tc::elect_one()) {
             constexpr uint32_t idesc = tc::umma_idesc_bf16(UNITS, NB);
@@ -157,7 +188,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
                 else tc::mbar_arrive(&h_full[s & 1]);
                 if (s == 0) continue;                      // h_{-1} = 0: nothing to multiply
                 const int pb = (s - 1) & 1;
-                if (ok) ok = tc::mbar_wait_cluster(&h_full[pb], ((s - 1) >> 1) & 1, p.dbg, 0x500 + (s & 0xff));
+                if (ok) ok = tc::mbar_wait(&h_full[pb], ((s - 1) >> 1) & 1, p.dbg, 0x500 + (s & 0xff));
                 tc::tcgen05_fence_after();
                 const uint32_t hb = tc::smem_u32(sH + (size_t)pb * KC * H_CHUNK);
 #pragma unroll 1
@@ -180,41 +211,35 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
         const int j = q * 32 + lane;
         const int unit = (int)c * UNITS + j;
         const int col0 = half * 8;
+        const int tid = threadIdx.x;
         const float bhn = p.b_hn[d * H + unit];
         const int ldy = D * H;
         float hprev[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) hprev[i] = 0.f;
         bool ok = true;
-        // gi is streamed from HBM and does not depend on the recurrence: keep the loads two steps ahead of
-        // their use so that DRAM latency never sits on the step chain
-        const __nv_bfloat16* gbase = p.giT + (int64_t)(d * 3 * H + unit) * R + tile * NB + col0;
-        auto gi_load = [&](uint4 (&dst)[3], int step) {
-            const int tt = d == 0 ? step : T - 1 - step;
-            const __nv_bfloat16* gp = gbase + (int64_t)tt * B;                  // 8 consecutive rows = 16 B
-            dst[0] = *reinterpret_cast<const uint4*>(gp);
-            dst[1] = *reinterpret_cast<const uint4*>(gp + (int64_t)H * R);
-            dst[2] = *reinterpret_cast<const uint4*>(gp + (int64_t)2 * H * R);
-        };
-        uint4 pf0[3], pf1[3];
-        gi_load(pf0, 0);
-        if (T > 1) gi_load(pf1, 1); else { pf1[0] = pf0[0]; pf1[1] = pf0[1]; pf1[2] = pf0[2]; }
         for (int s = 0; s < T; ++s) {
             const int t = d == 0 ? s : T - 1 - s;
             const int64_t row0 = (int64_t)t * B + tile * NB + col0;
+            const size_t blk = blk_index(d, tile, t, (int)c, ntiles, T, CS);
+            // this step's gi from the prefetch ring
             float gr[8], gz[8], gn[8];
             {
-                const __nv_bfloat16* t8 = reinterpret_cast<const __nv_bfloat16*>(&pf0[0]);
+                const int st = s % NSF;
+                if (ok) ok = tc::mbar_wait(&in_full[st], (s / NSF) & 1, p.dbg, 0x200 + (s & 0xff));
+                const uint4* gp = reinterpret_cast<const uint4*>(sIn + (size_t)st * GI_BLOCK) + tid;
+                const uint4 u0 = gp[0], u1 = gp[256], u2 = gp[512];
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&in_empty[st]);
+                const __nv_bfloat16* t8 = reinterpret_cast<const __nv_bfloat16*>(&u0);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) gr[i] = __bfloat162float(t8[i]);
-                t8 = reinterpret_cast<const __nv_bfloat16*>(&pf0[1]);
+                t8 = reinterpret_cast<const __nv_bfloat16*>(&u1);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) gz[i] = __bfloat162float(t8[i]);
-                t8 = reinterpret_cast<const __nv_bfloat16*>(&pf0[2]);
+                t8 = reinterpret_cast<const __nv_bfloat16*>(&u2);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) gn[i] = __bfloat162float(t8[i]);
-                pf0[0] = pf1[0]; pf0[1] = pf1[1]; pf0[2] = pf1[2];
-                if (s + 2 < T) gi_load(pf1, s + 2);
             }
             float ar[8], az[8], an[8];
             if (s > 0) {
@@ -241,19 +266,9 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
                 hv[i] = __float2bfloat16(h);
                 sr[i] = __float2bfloat16(r); sz[i] = __float2bfloat16(z); sn[i] = __float2bfloat16(n); shn[i] = __float2bfloat16(hn);
                 *reinterpret_cast<__nv_bfloat16*>(hb + tc::sw128_offset(col0 + i, unit & 63)) = hv[i];
-                p.Yrow[(row0 + i) * ldy + d * H + unit] = hv[i];
             }
-            {
-                uint4* gs = reinterpret_cast<uint4*>(p.G + stash_index(d, tile, t, (int)c, ntiles, T, CS) + (size_t)threadIdx.x * 32);
-                gs[0] = *reinterpret_cast<uint4*>(sr); gs[1] = *reinterpret_cast<uint4*>(sz);
-                gs[2] = *reinterpret_cast<uint4*>(sn); gs[3] = *reinterpret_cast<uint4*>(shn);
-            }
-            *reinterpret_cast<uint4*>(p.YT + (int64_t)(d * H + unit) * R + row0) = *reinterpret_cast<uint4*>(hv);
-            if (s == T - 1 && p.hn_out) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) p.hn_out[((int64_t)d * B + tile * NB + col0 + i) * H + unit] = hprev[i];
-            }
-            // publish h_t: local tile first (generic -> async proxy), then the peers via DSMEM bulk copies
+            // publish h_t first (this is the step chain): local tile (generic -> async proxy), then the peers
+            // via DSMEM bulk copies; everything that only feeds HBM is issued afterwards, off the chain
             tc::tcgen05_fence_before();
             tc::fence_proxy_async_smem();
             epi_barrier();
@@ -262,6 +277,19 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
                 uint8_t* mine = sH + (size_t)buf * KC * H_CHUNK + (size_t)c * chunk_bytes_mine;
                 for (uint32_t peer = 0; peer < (uint32_t)CS; ++peer)
                     if (peer != c) tc::bulk_s2cluster(mine, mine, chunk_bytes_mine, &h_full[buf], peer);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) p.Yrow[(row0 + i) * ldy + d * H + unit] = hv[i];
+            {
+                uint4* gs = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.G) + blk * G_BLOCK) + tid;
+                gs[0] = *reinterpret_cast<uint4*>(sr); gs[256] = *reinterpret_cast<uint4*>(sz);
+                gs[512] = *reinterpret_cast<uint4*>(sn); gs[768] = *reinterpret_cast<uint4*>(shn);
+            }
+            *reinterpret_cast<uint4*>(p.YT + (int64_t)(d * H + unit) * R + row0) = *reinterpret_cast<uint4*>(hv);
+            reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.YB) + blk * YB_BLOCK)[tid] = *reinterpret_cast<uint4*>(hv);
+            if (s == T - 1 && p.hn_out) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) p.hn_out[((int64_t)d * B + tile * NB + col0 + i) * H + unit] = hprev[i];
             }
         }
     }
@@ -304,8 +332,8 @@ __global__ void pack_whh_image_kernel(const float* __restrict__ w_hh, __nv_bfloa
 }
 
 // =================================================================================================
-// Backward scan (BPTT).  Same cluster / tiling; the resident operand is W_hh^T (A[unit k][q] = W_hh[q][k],
-// 128 rows x 3H, 192 KB at H=256) and the per-step product is
+// Backward scan (BPTT).  Same cluster / tiling; the TMEM-resident operand is W_hh^T (A[unit k][q] = W_hh[q][k],
+// 128 rows x 3H) and the per-step product is
 //     D'[k, b] = sum_q W_hh[q, k] * dgh_{s-1}[b, q]                    (tcgen05.mma M=128 N=16, K = 3H)
 // i.e. the recurrent part of dh.  The epilogue thread of hidden unit k adds dY_t and the z-carry, forms the
 // gate derivatives from the stash, writes its three dgh values (bf16) into the [16 x 3H] operand tile of
@@ -313,12 +341,12 @@ __global__ void pack_whh_image_kernel(const float* __restrict__ w_hh, __nv_bfloa
 // transposed form for the weight-gradient GEMMs; bias gradients accumulate in registers over all steps.
 // The operand tile is single-buffered (24 KB): a peer may only overwrite it after this CTA's MMA of the
 // current step has retired, which the epilogue leader signals with a remote mbarrier arrive.
-//   G (thread-private stash), YT (h_{t-1}, transposed), dYT fp32 [D*H][R]       (read, 16-byte vectors)
+// Per-step inputs (stash G, blocked h_{t-1} YB, blocked fp32 dY) come through a 3-stage bulk-copy ring.
 //   dgi_row bf16 [R][D*3H], dgiT / dghT bf16 [D*3H][R]                          (written)
 // =================================================================================================
 static inline size_t bwd_smem_bytes(int H) {
     const int KC3 = 3 * H / 64;
-    return (size_t)KC3 * H_CHUNK + 1024 + 256;
+    return (size_t)KC3 * H_CHUNK + (size_t)NSB * BWD_STAGE + 1024 + 256;
 }
 constexpr uint32_t BWD_A_COL = 32;        // accumulator in columns [0, 16), W_hh^T from column 32
 __host__ __device__ static inline uint32_t bwd_tmem_cols(int H) { return 32 + 3 * H / 2 <= 256 ? 256u : 512u; }
@@ -327,8 +355,8 @@ struct BwdParams {
     int B, T, H, D;
     const __nv_bfloat16* WTimg;     // [D][H units][3H]  rows of W_hh^T, copied to TMEM
     const __nv_bfloat16* G;
-    const __nv_bfloat16* YT;        // [D*H][R]
-    const float* dYT;               // [D*H][R]
+    const __nv_bfloat16* YB;        // blocked h (see forward)
+    const float* dYB;               // blocked fp32 dY: [block][256][8]
     const float* dh_init;           // [D][B][H] nullable: d(last hidden) of the top layer
     __nv_bfloat16* dgi_row;
     __nv_bfloat16* dgiT;
@@ -343,12 +371,15 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int H = p.H, KC = H / 64, KC3 = 3 * KC, CS = H / UNITS, B = p.B, T = p.T, D = p.D;
-    uint8_t* sD = smem;                                    // [KC3][H_CHUNK]  dgh tile
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sD + (size_t)KC3 * H_CHUNK);
-    uint64_t* d_full = bars + 1;       // [2] alternate by step parity (same buffer)
-    uint64_t* mma_done = bars + 3;
-    uint64_t* peer_ready = bars + 4;   // [2] peers' "my MMA of step s retired, you may overwrite my tile"
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    uint8_t* sD = smem;                                    // [KC3][H_CHUNK]  dgh operand tile
+    uint8_t* sIn = sD + (size_t)KC3 * H_CHUNK;             // [NSB][G | YB | dY]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + (size_t)NSB * BWD_STAGE);
+    uint64_t* d_full = bars;           // [2] alternate by step parity (same buffer)
+    uint64_t* mma_done = bars + 2;
+    uint64_t* peer_ready = bars + 3;   // [2] peers' "my MMA of step s retired, you may overwrite my tile"
+    uint64_t* in_full = bars + 5;      // [NSB]
+    uint64_t* in_empty = bars + 5 + NSB;   // [NSB]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * NSB);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t c = CS > 1 ? tc::cluster_ctarank() : 0u;
@@ -363,6 +394,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
         tc::mbar_init(mma_done, 1);
         tc::mbar_init(&peer_ready[0], CS > 1 ? CS - 1 : 1);
         tc::mbar_init(&peer_ready[1], CS > 1 ? CS - 1 : 1);
+        for (int i = 0; i < NSB; ++i) { tc::mbar_init(&in_full[i], 1); tc::mbar_init(&in_empty[i], EPI_WARPS); }
         tc::fence_mbar_init();
     }
     if (warp == EPI_WARPS) tc::tmem_alloc(tmem_slot, bwd_tmem_cols(H));
@@ -378,7 +410,27 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
     __syncthreads();
     tc::tcgen05_fence_after();
 
-    if (warp == EPI_WARPS) {
+    if (warp == EPI_WARPS + 1) {
+        // ---- input prefetch ring: stash + blocked h_{t-1} + blocked dY of each step, up to NSB steps ahead
+        if (tc::elect_one()) {
+            bool ok = true;
+            for (int s = 0; s < T; ++s) {
+                const int st = s % NSB;
+                if (s >= NSB && ok) ok = tc::mbar_wait(&in_empty[st], ((s / NSB) - 1) & 1, p.dbg, 0x300 + (s & 0xff));
+                const int t = d == 0 ? T - 1 - s : s;
+                const bool first = d == 0 ? t == 0 : t == T - 1;         // first step of the FORWARD recurrence: h_prev = 0
+                uint8_t* dst = sIn + (size_t)st * BWD_STAGE;
+                tc::mbar_arrive_expect_tx(&in_full[st], (uint32_t)(G_BLOCK + DY_BLOCK + (first ? 0 : YB_BLOCK)));
+                const size_t blk = blk_index(d, tile, t, (int)c, ntiles, T, CS);
+                tc::bulk_g2s(dst, reinterpret_cast<const uint8_t*>(p.G) + blk * G_BLOCK, G_BLOCK, &in_full[st]);
+                tc::bulk_g2s(dst + G_BLOCK + YB_BLOCK, reinterpret_cast<const uint8_t*>(p.dYB) + blk * DY_BLOCK, DY_BLOCK, &in_full[st]);
+                if (!first) {
+                    const size_t pblk = blk_index(d, tile, d == 0 ? t - 1 : t + 1, (int)c, ntiles, T, CS);
+                    tc::bulk_g2s(dst + G_BLOCK, reinterpret_cast<const uint8_t*>(p.YB) + pblk * YB_BLOCK, YB_BLOCK, &in_full[st]);
+                }
+            }
+        }
+    } else if (warp == EPI_WARPS) {
         if (tc::elect_one()) {
             constexpr uint32_t idesc = tc::umma_idesc_bf16(UNITS, NB);
             bool ok = true;
@@ -386,7 +438,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
                 if (CS > 1) tc::mbar_arrive_expect_tx(&d_full[s & 1], (uint32_t)(CS - 1) * 3 * gate_bytes_mine);
                 else tc::mbar_arrive(&d_full[s & 1]);
                 if (s == 0) continue;
-                if (ok) ok = tc::mbar_wait_cluster(&d_full[(s - 1) & 1], ((s - 1) >> 1) & 1, p.dbg, 0x800 + (s & 0xff));
+                if (ok) ok = tc::mbar_wait(&d_full[(s - 1) & 1], ((s - 1) >> 1) & 1, p.dbg, 0x800 + (s & 0xff));
                 tc::tcgen05_fence_after();
                 const uint32_t db0 = tc::smem_u32(sD);
 #pragma unroll 1
@@ -404,6 +456,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
         const int j = q * 32 + lane;
         const int unit = (int)c * UNITS + j;
         const int col0 = half * 8;
+        const int tid = threadIdx.x;
         const int ldi = D * 3 * H;
         float dhz[8];
 #pragma unroll
@@ -411,46 +464,38 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
             dhz[i] = p.dh_init ? p.dh_init[((int64_t)d * B + tile * NB + col0 + i) * H + unit] : 0.f;
         float sb_r = 0.f, sb_z = 0.f, sb_n = 0.f, sb_nr = 0.f;
         bool ok = true;
-        // stash, h_{t-1} and dY do not depend on the recurrence: loads run two steps ahead of their use
-        struct Pre { uint4 g[4]; uint4 hp; float4 dy0, dy1; };
-        auto pre_load = [&](Pre& q_, int step) {
-            const int tt = d == 0 ? T - 1 - step : step;
-            const bool fst = d == 0 ? tt == 0 : tt == T - 1;
-            const int64_t r0 = (int64_t)tt * B + tile * NB + col0;
-            const uint4* gs = reinterpret_cast<const uint4*>(p.G + stash_index(d, tile, tt, (int)c, ntiles, T, CS) + (size_t)threadIdx.x * 32);
-            q_.g[0] = gs[0]; q_.g[1] = gs[1]; q_.g[2] = gs[2]; q_.g[3] = gs[3];
-            if (fst) q_.hp = make_uint4(0u, 0u, 0u, 0u);                     // bf16 zeros: h_prev = 0 at the first forward step
-            else q_.hp = *reinterpret_cast<const uint4*>(p.YT + (int64_t)(d * H + unit) * R + r0 + (d == 0 ? -(int64_t)B : (int64_t)B));
-            const float4* dyp = reinterpret_cast<const float4*>(p.dYT + (int64_t)(d * H + unit) * R + r0);
-            q_.dy0 = dyp[0]; q_.dy1 = dyp[1];
-        };
-        Pre pa, pb;
-        pre_load(pa, 0);
-        if (T > 1) pre_load(pb, 1); else pb = pa;
         for (int s = 0; s < T; ++s) {
             const int t = d == 0 ? T - 1 - s : s;
+            const bool first = d == 0 ? t == 0 : t == T - 1;
             const int64_t row0 = (int64_t)t * B + tile * NB + col0;
             float vr[8], vz[8], vn[8], vhn[8], vhp[8], vdy[8];
             {
-                const __nv_bfloat16* t8 = reinterpret_cast<const __nv_bfloat16*>(&pa.g[0]);
+                const int st = s % NSB;
+                if (ok) ok = tc::mbar_wait(&in_full[st], (s / NSB) & 1, p.dbg, 0x200 + (s & 0xff));
+                const uint8_t* base = sIn + (size_t)st * BWD_STAGE;
+                const uint4* gp = reinterpret_cast<const uint4*>(base) + tid;
+                const uint4 u0 = gp[0], u1 = gp[256], u2 = gp[512], u3 = gp[768];
+                const uint4 uh = first ? make_uint4(0u, 0u, 0u, 0u) : reinterpret_cast<const uint4*>(base + G_BLOCK)[tid];
+                const float4* dyp = reinterpret_cast<const float4*>(base + G_BLOCK + YB_BLOCK) + 2 * tid;
+                const float4 a = dyp[0], b = dyp[1];
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&in_empty[st]);
+                const __nv_bfloat16* t8 = reinterpret_cast<const __nv_bfloat16*>(&u0);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) vr[i] = __bfloat162float(t8[i]);
-                t8 = reinterpret_cast<const __nv_bfloat16*>(&pa.g[1]);
+                t8 = reinterpret_cast<const __nv_bfloat16*>(&u1);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) vz[i] = __bfloat162float(t8[i]);
-                t8 = reinterpret_cast<const __nv_bfloat16*>(&pa.g[2]);
+                t8 = reinterpret_cast<const __nv_bfloat16*>(&u2);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) vn[i] = __bfloat162float(t8[i]);
-                t8 = reinterpret_cast<const __nv_bfloat16*>(&pa.g[3]);
+                t8 = reinterpret_cast<const __nv_bfloat16*>(&u3);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) vhn[i] = __bfloat162float(t8[i]);
-                t8 = reinterpret_cast<const __nv_bfloat16*>(&pa.hp);
+                t8 = reinterpret_cast<const __nv_bfloat16*>(&uh);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) vhp[i] = __bfloat162float(t8[i]);
-                vdy[0] = pa.dy0.x; vdy[1] = pa.dy0.y; vdy[2] = pa.dy0.z; vdy[3] = pa.dy0.w;
-                vdy[4] = pa.dy1.x; vdy[5] = pa.dy1.y; vdy[6] = pa.dy1.z; vdy[7] = pa.dy1.w;
-                pa = pb;
-                if (s + 2 < T) pre_load(pb, s + 2);
+                vdy[0] = a.x; vdy[1] = a.y; vdy[2] = a.z; vdy[3] = a.w; vdy[4] = b.x; vdy[5] = b.y; vdy[6] = b.z; vdy[7] = b.w;
             }
             float acc[8];
             if (s > 0) {
@@ -484,6 +529,26 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
                 *reinterpret_cast<__nv_bfloat16*>(sD + (size_t)(0 * KC + kc_u) * H_CHUNK + so) = tr[i];
                 *reinterpret_cast<__nv_bfloat16*>(sD + (size_t)(1 * KC + kc_u) * H_CHUNK + so) = tz[i];
                 *reinterpret_cast<__nv_bfloat16*>(sD + (size_t)(2 * KC + kc_u) * H_CHUNK + so) = tnr[i];
+            }
+            // publish dgh_s first (the step chain); HBM stores follow, off the chain
+            tc::tcgen05_fence_before();
+            tc::fence_proxy_async_smem();
+            epi_barrier();
+            if (threadIdx.x == 0 && s + 1 < T) {
+                tc::mbar_arrive(&d_full[s & 1]);
+                if (CS > 1) {
+                    if (ok) ok = tc::mbar_wait(&peer_ready[s & 1], (s >> 1) & 1, p.dbg, 0xA00 + (s & 0xff));
+                    for (uint32_t peer = 0; peer < (uint32_t)CS; ++peer) {
+                        if (peer == c) continue;
+                        for (int g = 0; g < 3; ++g) {
+                            uint8_t* mine = sD + (size_t)(g * KC) * H_CHUNK + (size_t)c * gate_bytes_mine;
+                            tc::bulk_s2cluster(mine, mine, gate_bytes_mine, &d_full[s & 1], peer);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
                 __nv_bfloat16* gi_o = p.dgi_row + (row0 + i) * ldi + d * 3 * H + unit;
                 gi_o[0] = tr[i]; gi_o[H] = tz[i]; gi_o[2 * H] = tn[i];
             }
@@ -496,22 +561,6 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
                 *reinterpret_cast<uint4*>(o2) = *reinterpret_cast<uint4*>(tr);
                 *reinterpret_cast<uint4*>(o2 + (int64_t)H * R) = *reinterpret_cast<uint4*>(tz);
                 *reinterpret_cast<uint4*>(o2 + (int64_t)2 * H * R) = *reinterpret_cast<uint4*>(tnr);
-            }
-            tc::tcgen05_fence_before();
-            tc::fence_proxy_async_smem();
-            epi_barrier();
-            if (threadIdx.x == 0 && s + 1 < T) {
-                tc::mbar_arrive(&d_full[s & 1]);
-                if (CS > 1) {
-                    if (ok) ok = tc::mbar_wait_cluster(&peer_ready[s & 1], (s >> 1) & 1, p.dbg, 0xA00 + (s & 0xff));
-                    for (uint32_t peer = 0; peer < (uint32_t)CS; ++peer) {
-                        if (peer == c) continue;
-                        for (int g = 0; g < 3; ++g) {
-                            uint8_t* mine = sD + (size_t)(g * KC) * H_CHUNK + (size_t)c * gate_bytes_mine;
-                            tc::bulk_s2cluster(mine, mine, gate_bytes_mine, &d_full[s & 1], peer);
-                        }
-                    }
-                }
             }
         }
         // bias gradients: sum the 8 columns of this thread; the two column halves and all tiles add atomically

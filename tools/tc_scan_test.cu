@@ -22,9 +22,15 @@ static int run_case(int B, int T, int H, int D, int reps) {
     CK(cudaMalloc(&d_whh, whh.size() * 4)); CK(cudaMalloc(&d_bhn, bhn.size() * 4)); CK(cudaMalloc(&d_img, img_elems * 2));
     CK(cudaMalloc(&d_gi, gi.size() * 2)); CK(cudaMalloc(&d_Y, (size_t)R * D * H * 2)); CK(cudaMalloc(&d_YT, (size_t)R * D * H * 2));
     CK(cudaMalloc(&d_G, (size_t)R * D * 4 * H * 2)); CK(cudaMalloc(&d_hn, (size_t)D * B * H * 4)); CK(cudaMalloc(&dbg, 64));
-    std::vector<__nv_bfloat16> gih(gi.size());        // device copy is TRANSPOSED: giT[D*3H][R]
+    std::vector<__nv_bfloat16> gih(gi.size());        // device copy is BLOCKED: [d][tile][t][cta][thread][gate][8]
     for (long r = 0; r < R; ++r)
-        for (int q = 0; q < D * 3 * H; ++q) gih[(size_t)q * R + r] = __float2bfloat16(gi[(size_t)r * D * 3 * H + q]);
+        for (int q = 0; q < D * 3 * H; ++q) {
+            const int dd = q / (3 * H), g = (q / H) % 3, unit = q % H, t = (int)(r / B), b = (int)(r % B);
+            const int tile = b / 16, half = (b % 16) / 8, i = b % 8, cta = unit / 128, ju = unit % 128;
+            const int tid = ((ju / 32) + 4 * half) * 32 + (ju % 32);
+            const size_t e = ((((size_t)dd * (B / 16) + tile) * T + t) * CS + cta) * 256 + tid;
+            gih[(((e / 256) * 3 + g) * 256 + tid) * 8 + i] = __float2bfloat16(gi[(size_t)r * D * 3 * H + q]);
+        }
     CK(cudaMemcpy(d_whh, whh.data(), whh.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_bhn, bhn.data(), bhn.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_gi, gih.data(), gih.size() * 2, cudaMemcpyHostToDevice));
@@ -34,7 +40,8 @@ static int run_case(int B, int T, int H, int D, int reps) {
         CK(cudaGetLastError());
     }
     tcs::FwdParams p{};
-    p.B = B; p.T = T; p.H = H; p.D = D; p.Wimg = d_img; p.giT = d_gi; p.b_hn = d_bhn; p.Yrow = d_Y; p.YT = d_YT; p.G = d_G;
+    p.B = B; p.T = T; p.H = H; p.D = D; p.Wimg = d_img; p.giB = d_gi; p.b_hn = d_bhn; p.Yrow = d_Y; p.YT = d_YT; p.G = d_G;
+    __nv_bfloat16* d_YB; CK(cudaMalloc(&d_YB, (size_t)R * D * H * 2)); p.YB = d_YB;
     p.hn_out = d_hn; p.dbg = dbg;
     CK(tcs::launch_fwd(p, 0));
     CK(cudaDeviceSynchronize());
@@ -81,11 +88,12 @@ static int run_case(int B, int T, int H, int D, int reps) {
                     // thread-private stash: [d][tile][t][cta][thread = warp*32+lane][gate][8 columns]
                     const int cta = j / 128, jj = j % 128, tile = b / 16, bb = b % 16;
                     const int tid = ((jj / 32) + 4 * (bb / 8)) * 32 + (jj % 32);
-                    const size_t gidx = (((((size_t)d * (B / 16) + tile) * T + t) * CS + cta) * 256 + tid) * 32 + (bb % 8);
+                    const size_t blk = (((size_t)d * (B / 16) + tile) * T + t) * CS + cta;       // [block][gate][thread][8]
+                    const size_t gidx = (blk * 4 * 256 + tid) * 8 + (bb % 8);
                     eG = fmax(eG, fabs(r - __bfloat162float(G[gidx])));
-                    eG = fmax(eG, fabs(z - __bfloat162float(G[gidx + 8])));
-                    eG = fmax(eG, fabs(n - __bfloat162float(G[gidx + 16])));
-                    eG = fmax(eG, fabs(hnv - __bfloat162float(G[gidx + 24])));
+                    eG = fmax(eG, fabs(z - __bfloat162float(G[gidx + 256 * 8])));
+                    eG = fmax(eG, fabs(n - __bfloat162float(G[gidx + 2 * 256 * 8])));
+                    eG = fmax(eG, fabs(hnv - __bfloat162float(G[gidx + 3 * 256 * 8])));
                 }
                 for (int j = 0; j < H; ++j) {
                     hs[j] = hnew[j]; hq[j] = bf(hnew[j]);
