@@ -130,11 +130,12 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
     uint8_t* sH = smem;                                    // [2][KC][H_CHUNK]  h operand tiles
     uint8_t* sIn = sH + (size_t)2 * KC * H_CHUNK;          // [NSF][GI_BLOCK]   prefetched gi blocks
     uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + (size_t)NSF * GI_BLOCK);
-    uint64_t* h_full = bars;           // [2]
+    uint64_t* h_full = bars;           // [2]  peers' h chunks landed (tx bytes), armed by the control thread
     uint64_t* mma_done = bars + 2;
-    uint64_t* in_full = bars + 3;      // [NSF]
-    uint64_t* in_empty = bars + 3 + NSF;   // [NSF]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + 2 * NSF);
+    uint64_t* epi_done = bars + 3;     // one arrival per epilogue warp: local h chunk written
+    uint64_t* in_full = bars + 4;      // [NSF]
+    uint64_t* in_empty = bars + 4 + NSF;   // [NSF]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * NSF);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t c = CS > 1 ? tc::cluster_ctarank() : 0u;
@@ -144,9 +145,10 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
     const int64_t R = (int64_t)T * B;
 
     if (threadIdx.x == 0) {
-        tc::mbar_init(&h_full[0], 2);
-        tc::mbar_init(&h_full[1], 2);
+        tc::mbar_init(&h_full[0], 1);
+        tc::mbar_init(&h_full[1], 1);
         tc::mbar_init(mma_done, 1);
+        tc::mbar_init(epi_done, EPI_WARPS);
         for (int i = 0; i < NSF; ++i) { tc::mbar_init(&in_full[i], 1); tc::mbar_init(&in_empty[i], EPI_WARPS); }
         tc::fence_mbar_init();
     }
@@ -179,16 +181,23 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
             }
         }
     } else if (warp == EPI_WARPS) {
-        // ---- MMA issuer
+        // ---- control thread: sequences the step chain.  h_{s-1} is complete when the 8 epilogue warps have
+        // written the local chunk (epi_done) and the peers' chunks have landed (h_full, DSMEM bulk copies that
+        // this thread also issues for the local chunk); then it issues the 48 MMAs of step s.
         if (tc::elect_one()) {
             constexpr uint32_t idesc = tc::umma_idesc_bf16(UNITS, NB);
             bool ok = true;
-            for (int s = 0; s < T; ++s) {                  // after a watchdog hit: keep signalling, stop waiting
-                if (CS > 1) tc::mbar_arrive_expect_tx(&h_full[s & 1], (uint32_t)(CS - 1) * chunk_bytes_mine);
-                else tc::mbar_arrive(&h_full[s & 1]);
-                if (s == 0) continue;                      // h_{-1} = 0: nothing to multiply
+            if (CS > 1 && T > 1) tc::mbar_arrive_expect_tx(&h_full[0], (uint32_t)(CS - 1) * chunk_bytes_mine);
+            for (int s = 1; s < T; ++s) {                  // after a watchdog hit: keep signalling, stop waiting
                 const int pb = (s - 1) & 1;
-                if (ok) ok = tc::mbar_wait(&h_full[pb], ((s - 1) >> 1) & 1, p.dbg, 0x500 + (s & 0xff));
+                if (ok) ok = tc::mbar_wait(epi_done, (s - 1) & 1, p.dbg, 0x400 + (s & 0xff));
+                if (CS > 1) {
+                    uint8_t* mine = sH + (size_t)pb * KC * H_CHUNK + (size_t)c * chunk_bytes_mine;
+                    for (uint32_t peer = 0; peer < (uint32_t)CS; ++peer)
+                        if (peer != c) tc::bulk_s2cluster(mine, mine, chunk_bytes_mine, &h_full[pb], peer);
+                    if (ok) ok = tc::mbar_wait(&h_full[pb], ((s - 1) >> 1) & 1, p.dbg, 0x500 + (s & 0xff));
+                    if (s + 1 < T) tc::mbar_arrive_expect_tx(&h_full[s & 1], (uint32_t)(CS - 1) * chunk_bytes_mine);
+                }
                 tc::tcgen05_fence_after();
                 const uint32_t hb = tc::smem_u32(sH + (size_t)pb * KC * H_CHUNK);
 #pragma unroll 1
@@ -267,17 +276,12 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
                 sr[i] = __float2bfloat16(r); sz[i] = __float2bfloat16(z); sn[i] = __float2bfloat16(n); shn[i] = __float2bfloat16(hn);
                 *reinterpret_cast<__nv_bfloat16*>(hb + tc::sw128_offset(col0 + i, unit & 63)) = hv[i];
             }
-            // publish h_t first (this is the step chain): local tile (generic -> async proxy), then the peers
-            // via DSMEM bulk copies; everything that only feeds HBM is issued afterwards, off the chain
+            // hand h_t to the control thread (this is the step chain): smem writes -> async proxy, one arrival per
+            // warp; everything that only feeds HBM is issued afterwards, off the chain
             tc::tcgen05_fence_before();
             tc::fence_proxy_async_smem();
-            epi_barrier();
-            if (threadIdx.x == 0 && s + 1 < T) {
-                tc::mbar_arrive(&h_full[buf]);
-                uint8_t* mine = sH + (size_t)buf * KC * H_CHUNK + (size_t)c * chunk_bytes_mine;
-                for (uint32_t peer = 0; peer < (uint32_t)CS; ++peer)
-                    if (peer != c) tc::bulk_s2cluster(mine, mine, chunk_bytes_mine, &h_full[buf], peer);
-            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(epi_done);
 #pragma unroll
             for (int i = 0; i < 8; ++i) p.Yrow[(row0 + i) * ldy + d * H + unit] = hv[i];
             {
@@ -339,14 +343,14 @@ __global__ void pack_whh_image_kernel(const float* __restrict__ w_hh, __nv_bfloa
 // gate derivatives from the stash, writes its three dgh values (bf16) into the [16 x 3H] operand tile of
 // the next step (locally + DSMEM bulk copy to the peers) and streams out dgi / dgh in row-major and
 // transposed form for the weight-gradient GEMMs; bias gradients accumulate in registers over all steps.
-// The operand tile is single-buffered (24 KB): a peer may only overwrite it after this CTA's MMA of the
-// current step has retired, which the epilogue leader signals with a remote mbarrier arrive.
+// The [16 x 3H] operand tile is double-buffered (2 x 24 KB); the control thread publishes it exactly as in the
+// forward kernel.
 // Per-step inputs (stash G, blocked h_{t-1} YB, blocked fp32 dY) come through a 3-stage bulk-copy ring.
 //   dgi_row bf16 [R][D*3H], dgiT / dghT bf16 [D*3H][R]                          (written)
 // =================================================================================================
 static inline size_t bwd_smem_bytes(int H) {
     const int KC3 = 3 * H / 64;
-    return (size_t)KC3 * H_CHUNK + (size_t)NSB * BWD_STAGE + 1024 + 256;
+    return (size_t)2 * KC3 * H_CHUNK + (size_t)NSB * BWD_STAGE + 1024 + 256;
 }
 constexpr uint32_t BWD_A_COL = 32;        // accumulator in columns [0, 16), W_hh^T from column 32
 __host__ __device__ static inline uint32_t bwd_tmem_cols(int H) { return 32 + 3 * H / 2 <= 256 ? 256u : 512u; }
@@ -371,15 +375,15 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int H = p.H, KC = H / 64, KC3 = 3 * KC, CS = H / UNITS, B = p.B, T = p.T, D = p.D;
-    uint8_t* sD = smem;                                    // [KC3][H_CHUNK]  dgh operand tile
-    uint8_t* sIn = sD + (size_t)KC3 * H_CHUNK;             // [NSB][G | YB | dY]
+    uint8_t* sD = smem;                                    // [2][KC3][H_CHUNK]  dgh operand tiles
+    uint8_t* sIn = sD + (size_t)2 * KC3 * H_CHUNK;         // [NSB][G | YB | dY]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + (size_t)NSB * BWD_STAGE);
-    uint64_t* d_full = bars;           // [2] alternate by step parity (same buffer)
+    uint64_t* d_full = bars;           // [2]  peers' dgh chunks landed
     uint64_t* mma_done = bars + 2;
-    uint64_t* peer_ready = bars + 3;   // [2] peers' "my MMA of step s retired, you may overwrite my tile"
-    uint64_t* in_full = bars + 5;      // [NSB]
-    uint64_t* in_empty = bars + 5 + NSB;   // [NSB]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * NSB);
+    uint64_t* epi_done = bars + 3;
+    uint64_t* in_full = bars + 4;      // [NSB]
+    uint64_t* in_empty = bars + 4 + NSB;   // [NSB]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * NSB);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t c = CS > 1 ? tc::cluster_ctarank() : 0u;
@@ -389,11 +393,10 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
     const int64_t R = (int64_t)T * B;
 
     if (threadIdx.x == 0) {
-        tc::mbar_init(&d_full[0], 2);
-        tc::mbar_init(&d_full[1], 2);
+        tc::mbar_init(&d_full[0], 1);
+        tc::mbar_init(&d_full[1], 1);
         tc::mbar_init(mma_done, 1);
-        tc::mbar_init(&peer_ready[0], CS > 1 ? CS - 1 : 1);
-        tc::mbar_init(&peer_ready[1], CS > 1 ? CS - 1 : 1);
+        tc::mbar_init(epi_done, EPI_WARPS);
         for (int i = 0; i < NSB; ++i) { tc::mbar_init(&in_full[i], 1); tc::mbar_init(&in_empty[i], EPI_WARPS); }
         tc::fence_mbar_init();
     }
@@ -431,16 +434,28 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
             }
         }
     } else if (warp == EPI_WARPS) {
+        // ---- control thread (see forward kernel)
         if (tc::elect_one()) {
             constexpr uint32_t idesc = tc::umma_idesc_bf16(UNITS, NB);
             bool ok = true;
-            for (int s = 0; s < T; ++s) {
-                if (CS > 1) tc::mbar_arrive_expect_tx(&d_full[s & 1], (uint32_t)(CS - 1) * 3 * gate_bytes_mine);
-                else tc::mbar_arrive(&d_full[s & 1]);
-                if (s == 0) continue;
-                if (ok) ok = tc::mbar_wait(&d_full[(s - 1) & 1], ((s - 1) >> 1) & 1, p.dbg, 0x800 + (s & 0xff));
+            if (CS > 1 && T > 1) tc::mbar_arrive_expect_tx(&d_full[0], (uint32_t)(CS - 1) * 3 * gate_bytes_mine);
+            for (int s = 1; s < T; ++s) {
+                const int pb = (s - 1) & 1;
+                uint8_t* tileb = sD + (size_t)pb * KC3 * H_CHUNK;
+                if (ok) ok = tc::mbar_wait(epi_done, (s - 1) & 1, p.dbg, 0x700 + (s & 0xff));
+                if (CS > 1) {
+                    for (uint32_t peer = 0; peer < (uint32_t)CS; ++peer) {
+                        if (peer == c) continue;
+                        for (int g = 0; g < 3; ++g) {
+                            uint8_t* mine = tileb + (size_t)(g * KC) * H_CHUNK + (size_t)c * gate_bytes_mine;
+                            tc::bulk_s2cluster(mine, mine, gate_bytes_mine, &d_full[pb], peer);
+                        }
+                    }
+                    if (ok) ok = tc::mbar_wait(&d_full[pb], ((s - 1) >> 1) & 1, p.dbg, 0x800 + (s & 0xff));
+                    if (s + 1 < T) tc::mbar_arrive_expect_tx(&d_full[s & 1], (uint32_t)(CS - 1) * 3 * gate_bytes_mine);
+                }
                 tc::tcgen05_fence_after();
-                const uint32_t db0 = tc::smem_u32(sD);
+                const uint32_t db0 = tc::smem_u32(tileb);
 #pragma unroll 1
                 for (int kc = 0; kc < KC3; ++kc) {
                     const uint64_t db = tc::umma_desc_k_sw128(db0 + (uint32_t)kc * H_CHUNK);
@@ -507,10 +522,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[i] = 0.f;
             }
-            // this CTA's tile may now be overwritten by the peers (its MMA of this step has retired)
-            if (threadIdx.x == 0 && CS > 1)
-                for (uint32_t peer = 0; peer < (uint32_t)CS; ++peer)
-                    if (peer != c) tc::mbar_arrive_cluster(&peer_ready[s & 1], peer);
+            uint8_t* tileb = sD + (size_t)(s & 1) * KC3 * H_CHUNK;
             __nv_bfloat16 tr[8], tz[8], tn[8], tnr[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -526,27 +538,15 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
                 tn[i] = __float2bfloat16(dan); tnr[i] = __float2bfloat16(danr);
                 const uint32_t so = tc::sw128_offset(col0 + i, unit & 63);
                 const int kc_u = unit >> 6;
-                *reinterpret_cast<__nv_bfloat16*>(sD + (size_t)(0 * KC + kc_u) * H_CHUNK + so) = tr[i];
-                *reinterpret_cast<__nv_bfloat16*>(sD + (size_t)(1 * KC + kc_u) * H_CHUNK + so) = tz[i];
-                *reinterpret_cast<__nv_bfloat16*>(sD + (size_t)(2 * KC + kc_u) * H_CHUNK + so) = tnr[i];
+                *reinterpret_cast<__nv_bfloat16*>(tileb + (size_t)(0 * KC + kc_u) * H_CHUNK + so) = tr[i];
+                *reinterpret_cast<__nv_bfloat16*>(tileb + (size_t)(1 * KC + kc_u) * H_CHUNK + so) = tz[i];
+                *reinterpret_cast<__nv_bfloat16*>(tileb + (size_t)(2 * KC + kc_u) * H_CHUNK + so) = tnr[i];
             }
-            // publish dgh_s first (the step chain); HBM stores follow, off the chain
+            // hand dgh_s to the control thread (the step chain); HBM stores follow, off the chain
             tc::tcgen05_fence_before();
             tc::fence_proxy_async_smem();
-            epi_barrier();
-            if (threadIdx.x == 0 && s + 1 < T) {
-                tc::mbar_arrive(&d_full[s & 1]);
-                if (CS > 1) {
-                    if (ok) ok = tc::mbar_wait(&peer_ready[s & 1], (s >> 1) & 1, p.dbg, 0xA00 + (s & 0xff));
-                    for (uint32_t peer = 0; peer < (uint32_t)CS; ++peer) {
-                        if (peer == c) continue;
-                        for (int g = 0; g < 3; ++g) {
-                            uint8_t* mine = sD + (size_t)(g * KC) * H_CHUNK + (size_t)c * gate_bytes_mine;
-                            tc::bulk_s2cluster(mine, mine, gate_bytes_mine, &d_full[s & 1], peer);
-                        }
-                    }
-                }
-            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(epi_done);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 __nv_bfloat16* gi_o = p.dgi_row + (row0 + i) * ldi + d * 3 * H + unit;
