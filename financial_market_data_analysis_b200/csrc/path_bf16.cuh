@@ -24,10 +24,10 @@ static int bf16_plan_check(const bigru_plan& p) {
 }
 
 struct Bf16Layout {            // byte offsets, 1024-aligned
-    size_t Yrow[16], YT[16], YB[16], G[16], Xrow[16], XT[16];    // stash: activations
+    size_t Yrow[16], YB[16], G[16], Xrow[16];                    // stash: activations
     size_t Wih[16], WihT[16], Wimg[16], WTimg[16], bfold[16], bhn[16];   // stash: packed weights
     size_t cat, arg, dbg, stash_total;
-    size_t gi, dgiT, dghT, dYa, dYb, dcat, dhinit, scratch_total;
+    size_t gi, dghn, dYa, dYb, dcat, dhinit, scratch_total;
 };
 static inline size_t al(size_t x) { return (x + 1023) & ~(size_t)1023; }
 static Bf16Layout bf16_layout(const bigru_plan& p) {
@@ -37,11 +37,9 @@ static Bf16Layout bf16_layout(const bigru_plan& p) {
     for (int l = 0; l < p.L; ++l) {
         const size_t I = p.in_size(l);
         L.Yrow[l] = o; o = al(o + R * DH * 2);
-        L.YT[l] = o; o = al(o + R * DH * 2);
         L.YB[l] = o; o = al(o + R * DH * 2);
         L.G[l] = o; o = al(o + R * D * 4 * H * 2);
         L.Xrow[l] = o; o = al(o + R * I * 2);
-        L.XT[l] = o; o = al(o + R * I * 2);
         L.Wih[l] = o; o = al(o + D * 3 * H * I * 2);
         L.WihT[l] = o; o = al(o + D * 3 * H * I * 2);
         L.Wimg[l] = o; o = al(o + D * 3 * H * H * 2);
@@ -56,8 +54,7 @@ static Bf16Layout bf16_layout(const bigru_plan& p) {
     o = 0;
     const size_t wide = DH > (size_t)p.F ? DH : (size_t)p.F;
     L.gi = o; o = al(o + R * D * 3 * H * 2);
-    L.dgiT = o; o = al(o + R * D * 3 * H * 2);
-    L.dghT = o; o = al(o + R * D * 3 * H * 2);
+    L.dghn = o; o = al(o + R * D * H * 2);
     L.dYa = o; o = al(o + R * wide * 4);
     L.dYb = o; o = al(o + R * wide * 4);
     L.dcat = o; o = al(o + (size_t)p.B * 3 * H * 4);
@@ -73,37 +70,27 @@ static void bf16_workspace(const bigru_plan& p, size_t* a, size_t* b) {
 // ---------------------------------------------------------------------------------------------------
 // small kernels of this path
 // ---------------------------------------------------------------------------------------------------
-// x fp32 [B][T][F] -> Xrow bf16 [(t*B+b)][F] and XT bf16 [F][(t*B+b)], optional input dropout.
-// 32x32 tiles over (b, f) for a fixed t so that both the row-major and the transposed write coalesce.
-__global__ void cast_x_kernel(const float* __restrict__ x, bf16_t* __restrict__ Xrow, bf16_t* __restrict__ XT,
-                              int B, int T, int F, float pdrop, int spatial, uint64_t seed) {
-    __shared__ float tile[32][33];
-    const int t = blockIdx.z, b0 = blockIdx.y * 32, f0 = blockIdx.x * 32;
-    const int64_t R = (int64_t)T * B;
+// x fp32 [B][T][F] -> Xrow bf16 [(t*B+b)][F] (time-major rows), optional input dropout.
+__global__ void cast_x_kernel(const float* __restrict__ x, bf16_t* __restrict__ Xrow, int B, int T, int F, float pdrop,
+                              int spatial, uint64_t seed) {
     const float scale = pdrop > 0.f ? 1.f / (1.f - pdrop) : 1.f;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int b = b0 + i, f = f0 + threadIdx.x;
-        float v = 0.f;
-        if (b < B && f < F) {
-            v = x[((int64_t)b * T + t) * F + f];
-            if (pdrop > 0.f) {
-                const uint64_t key = spatial ? (uint64_t)b * F + f : ((uint64_t)b * T + t) * F + f;
-                v = bigru_uniform(seed, 0u, key) < pdrop ? 0.f : v * scale;
-            }
-            Xrow[((int64_t)t * B + b) * F + f] = __float2bfloat16(v);
+    const int64_t total = (int64_t)B * T * F;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int f = i % F;
+        const int64_t r = i / F;                 // output row t*B + b
+        const int64_t b = r % B, t = r / B;
+        float v = x[(b * T + t) * F + f];
+        if (pdrop > 0.f) {
+            const uint64_t key = spatial ? (uint64_t)b * F + f : ((uint64_t)b * T + t) * F + f;
+            v = bigru_uniform(seed, 0u, key) < pdrop ? 0.f : v * scale;
         }
-        tile[i][threadIdx.x] = v;
-    }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int f = f0 + i, b = b0 + threadIdx.x;
-        if (b < B && f < F) XT[(int64_t)f * R + (int64_t)t * B + b] = __float2bfloat16(tile[threadIdx.x][i]);
+        Xrow[i] = __float2bfloat16(v);
     }
 }
 
-// inter-layer dropout: Yrow -> Xrow (masked) and XT (masked, transposed); rows x cols = R x DH
-__global__ void dropout_rows_kernel(const bf16_t* __restrict__ Y, bf16_t* __restrict__ Xrow, bf16_t* __restrict__ XT,
-                                    int64_t R, int cols, int B, int T, float pdrop, uint64_t seed, uint32_t stream) {
+// inter-layer dropout: Yrow -> Xrow (masked); rows x cols = R x DH
+__global__ void dropout_rows_kernel(const bf16_t* __restrict__ Y, bf16_t* __restrict__ Xrow, int64_t R, int cols, int B, int T,
+                                    float pdrop, uint64_t seed, uint32_t stream) {
     const float scale = 1.f / (1.f - pdrop);
     const int64_t total = R * cols;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -112,9 +99,7 @@ __global__ void dropout_rows_kernel(const bf16_t* __restrict__ Y, bf16_t* __rest
         const int64_t b = r % B, t = r / B;
         const uint64_t key = ((uint64_t)b * T + t) * cols + cidx;          // batch-major key, as the fp32 path
         const float v = bigru_uniform(seed, stream, key) < pdrop ? 0.f : __bfloat162float(Y[i]) * scale;
-        const bf16_t o = __float2bfloat16(v);
-        Xrow[i] = o;
-        XT[(int64_t)cidx * R + r] = o;
+        Xrow[i] = __float2bfloat16(v);
     }
 }
 // gradient of the same dropout, in place on the BLOCKED fp32 gradient [d][tile][t][cta][thread][8] (see tc_gemm.cuh)
@@ -240,11 +225,15 @@ __global__ void dx_to_batch_major_kernel(const float* __restrict__ dXT, float* _
 // ---------------------------------------------------------------------------------------------------
 // GEMM helper with accounting
 // ---------------------------------------------------------------------------------------------------
+// A / B operand descriptions: K-major [rows][K] (ld = row stride) or MN-major [K rows][MN] (p.a_mn / p.b_mn set)
 static int tc_gemm(const void* A, int64_t a_rows, int64_t lda, const void* Bm, int64_t b_rows, int64_t ldb,
                    tcg::Params& p, cudaStream_t st) {
     CUtensorMap tA, tB;
-    if (tcg::make_operand_map(&tA, A, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda) ||
-        tcg::make_operand_map(&tB, Bm, (uint64_t)b_rows, (uint64_t)p.K, (uint64_t)ldb)) {
+    const int ea = p.a_mn ? tcg::make_operand_map_mn(&tA, A, (uint64_t)p.K, (uint64_t)a_rows, (uint64_t)lda)
+                          : tcg::make_operand_map(&tA, A, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda);
+    const int eb = p.b_mn ? tcg::make_operand_map_mn(&tB, Bm, (uint64_t)p.K, (uint64_t)b_rows, (uint64_t)ldb)
+                          : tcg::make_operand_map(&tB, Bm, (uint64_t)b_rows, (uint64_t)p.K, (uint64_t)ldb);
+    if (ea || eb) {
         bigru_set_error("cuTensorMapEncodeTiled failed (rows %lld/%lld K %d ld %lld/%lld)", (long long)a_rows,
                         (long long)b_rows, p.K, (long long)lda, (long long)ldb);
         return BIGRU_ERR_CUDA;
@@ -287,21 +276,17 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
                                                (float*)(S + L.bhn[l]), H, d));
         }
     }
-    // 2. layer-0 input: cast + transpose (+ input dropout)
-    {
-        dim3 grid((F + 31) / 32, (B + 31) / 32, T);
-        KLAUNCH(KC_PACK, 0.0, 6.0 * R * F, st, cast_x_kernel<<<grid, dim3(32, 8), 0, st>>>(
-                                                   x, (bf16_t*)(S + L.Xrow[0]), (bf16_t*)(S + L.XT[0]), B, T, F,
-                                                   do_drop ? drop : 0.f, spatial, seed));
-    }
+    // 2. layer-0 input: cast to bf16, time-major rows (+ input dropout)
+    KLAUNCH(KC_PACK, 0.0, 6.0 * R * F, st, cast_x_kernel<<<148 * 8, 256, 0, st>>>(x, (bf16_t*)(S + L.Xrow[0]), B, T, F,
+                                                                                   do_drop ? drop : 0.f, spatial, seed));
     for (int l = 0; l < p.L; ++l) {
         const int I = (int)p.in_size(l);
         const bf16_t* Xrow = (const bf16_t*)(S + L.Xrow[l]);
         if (l > 0) {
             if (do_drop) {
                 KLAUNCH(KC_MISC, 0.0, 0.0, st, dropout_rows_kernel<<<148 * 8, 256, 0, st>>>(
-                                                   (const bf16_t*)(S + L.Yrow[l - 1]), (bf16_t*)(S + L.Xrow[l]),
-                                                   (bf16_t*)(S + L.XT[l]), R, I, B, T, drop, seed, (uint32_t)l));
+                                                   (const bf16_t*)(S + L.Yrow[l - 1]), (bf16_t*)(S + L.Xrow[l]), R, I, B, T,
+                                                   drop, seed, (uint32_t)l));
             } else {
                 Xrow = (const bf16_t*)(S + L.Yrow[l - 1]);
             }
@@ -316,7 +301,7 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
         tcs::FwdParams f{};
         f.B = B; f.T = T; f.H = H; f.D = D;
         f.Wimg = (const bf16_t*)(S + L.Wimg[l]); f.giB = (const bf16_t*)(W + L.gi); f.b_hn = (const float*)(S + L.bhn[l]);
-        f.Yrow = (bf16_t*)(S + L.Yrow[l]); f.YT = (bf16_t*)(S + L.YT[l]); f.G = (bf16_t*)(S + L.G[l]); f.YB = (bf16_t*)(S + L.YB[l]);
+        f.Yrow = (bf16_t*)(S + L.Yrow[l]); f.G = (bf16_t*)(S + L.G[l]); f.YB = (bf16_t*)(S + L.YB[l]);
         f.hn_out = hn ? hn + (int64_t)l * D * B * H : nullptr; f.dbg = dbg;
         {
             ProfScope ps(KC_TC_SCAN_FWD, 2.0 * 3 * H * H * (double)R * D, 0.0, st);
@@ -367,37 +352,43 @@ static int backward_bf16(const bigru_plan& p, const float* params, const float* 
         b.B = B; b.T = T; b.H = H; b.D = D;
         b.WTimg = (const bf16_t*)(S + L.WTimg[l]); b.G = (const bf16_t*)(S + L.G[l]); b.YB = (const bf16_t*)(S + L.YB[l]);
         b.dYB = dY; b.dh_init = l == p.L - 1 ? dhinit : nullptr;
-        b.dgi_row = (bf16_t*)(W + L.gi); b.dgiT = (bf16_t*)(W + L.dgiT); b.dghT = (bf16_t*)(W + L.dghT);
+        b.dgi_row = (bf16_t*)(W + L.gi); b.dghn_row = (bf16_t*)(W + L.dghn);
         b.db_ih = grads + p.off_bih(l, 0); b.db_hh = grads + p.off_bhh(l, 0); b.dir_stride = p.ld_block(l); b.dbg = dbg;
         {
             ProfScope ps(KC_TC_SCAN_BWD, 2.0 * 3 * H * H * (double)R * D, 0.0, st);
             CUDA_TRY(tcs::launch_bwd(b, st));
         }
-        // layer input as the projection saw it
+        // layer input as the projection saw it (row-major, time-major rows)
         const bool dropped = do_drop && (l == 0 || p.L > 1);
-        const bf16_t* XT = (l == 0 || dropped) ? (const bf16_t*)(S + L.XT[l]) : (const bf16_t*)(S + L.YT[l - 1]);
-        // 2. dW_ih[d] = dgi[d]^T X   (M=3H, N=I, K=R), both directions in one launch, split-K + fp32 atomics
+        const bf16_t* Xin = (l == 0 || dropped) ? (const bf16_t*)(S + L.Xrow[l]) : (const bf16_t*)(S + L.Yrow[l - 1]);
+        // 2. dW_ih[d] = dgi[d]^T X   (M=3H, N=I, K=R): both operands are the row-major activations read MN-major,
+        //    both directions in one launch, split-K with TMA reduce-add
         {
             tcg::Params g{};
-            g.M = 3 * H; g.N = I; g.K = (int)R; g.batch = D; g.mode = tcg::OUT_ATOMIC_F32;
+            g.M = 3 * H; g.N = I; g.K = (int)R; g.batch = D; g.mode = tcg::OUT_ATOMIC_F32; g.a_mn = 1; g.b_mn = 1;
             const int tiles = ((3 * H + 127) / 128) * ((I + 127) / 128) * D;
             g.splitk = (int)std::max<int64_t>(1, std::min<int64_t>((R + 63) / 64, (148 * 3 + tiles - 1) / tiles));
             g.C = grads + p.off_wih(l, 0); g.ldc = I; g.zC = p.ld_block(l);
             for (int d = 0; d < D; ++d) { g.a_row_off[d] = d * 3 * H; g.b_row_off[d] = 0; g.b_k_off[d] = 0; }
             g.dbg = dbg;
-            TRY(tc_gemm(W + L.dgiT, (int64_t)D * 3 * H, R, XT, I, R, g, st));
+            TRY(tc_gemm(W + L.gi, (int64_t)D * 3 * H, (int64_t)D * 3 * H, Xin, I, I, g, st));
         }
-        // 3. dW_hh[d] = dgh[d]^T H_prev  with H_prev(t) = Y(t-1) (dir 0) / Y(t+1) (dir 1): a K-coordinate shift of
-        //    +-B rows on the transposed output; out-of-range columns read as zero (h_prev = 0 at the first step)
-        {
+        // 3. dW_hh[d] = dgh[d]^T H_prev  with H_prev(t) = Y(t-1) (dir 0) / Y(t+1) (dir 1): a shift of -+B ROWS of the
+        //    time-major output; rows outside [0, R) read as zero through TMA (h_prev = 0 at the first step).
+        //    dgh = [da_r | da_z] (columns of dgi_row) and da_n*r (dghn_row): two launches.
+        for (int part = 0; part < 2; ++part) {
             tcg::Params g{};
-            g.M = 3 * H; g.N = H; g.K = (int)R; g.batch = D; g.mode = tcg::OUT_ATOMIC_F32;
-            const int tiles = ((3 * H + 127) / 128) * ((H + 127) / 128) * D;
-            g.splitk = (int)std::max<int64_t>(1, std::min<int64_t>((R + 63) / 64, (148 * 3 + tiles - 1) / tiles));
-            g.C = grads + p.off_whh(l, 0); g.ldc = H; g.zC = p.ld_block(l);
-            for (int d = 0; d < D; ++d) { g.a_row_off[d] = d * 3 * H; g.b_row_off[d] = d * H; g.b_k_off[d] = d == 0 ? -B : B; }
+            g.M = part == 0 ? 2 * H : H; g.N = H; g.K = (int)R; g.batch = D; g.mode = tcg::OUT_ATOMIC_F32; g.a_mn = 1; g.b_mn = 1;
+            const int tiles = ((g.M + 127) / 128) * ((H + 127) / 128) * D;
+            g.splitk = (int)std::max<int64_t>(1, std::min<int64_t>((R + 63) / 64, (148 * 2 + tiles - 1) / tiles));
+            g.C = grads + p.off_whh(l, 0) + (part == 0 ? 0 : (int64_t)2 * H * H); g.ldc = H; g.zC = p.ld_block(l);
+            for (int d = 0; d < D; ++d) {
+                g.a_row_off[d] = part == 0 ? d * 3 * H : d * H;
+                g.b_row_off[d] = d * H; g.b_k_off[d] = d == 0 ? -B : B;
+            }
             g.dbg = dbg;
-            TRY(tc_gemm(W + L.dghT, (int64_t)D * 3 * H, R, S + L.YT[l], (int64_t)D * H, R, g, st));
+            if (part == 0) TRY(tc_gemm(W + L.gi, (int64_t)D * 3 * H, (int64_t)D * 3 * H, S + L.Yrow[l], (int64_t)D * H, (int64_t)D * H, g, st));
+            else TRY(tc_gemm(W + L.dghn, (int64_t)D * H, (int64_t)D * H, S + L.Yrow[l], (int64_t)D * H, (int64_t)D * H, g, st));
         }
         // 4. dX^T = W_ih^T (both directions concatenated along K = D*3H) x dgi_row^T.  For l > 0 it is written directly in
         //    the blocked layout the next backward scan reads; for layer 0 (caller wants dx) as [F][R] and then re-laid.

@@ -175,9 +175,22 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
     return d;
 }
-// kind::f16 instruction descriptor: bf16 x bf16 -> f32, both operands K-major (cute::UMMA::InstrDescriptor)
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
-    return (1u << 4)            // c_format = F32
+// MN-major operand tile, 128-byte swizzle: the operand is stored [K rows][MN contiguous]; one TMA box is
+// 64 (MN, 128 B) x 64 (K rows).  Canonical layout ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in elements: an atom is
+// 8 K-rows x 128 B = 1024 B (SBO between 8-row groups), the next 64-wide MN block is a whole box further (LBO).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> f32 (cute::UMMA::InstrDescriptor); operands K-major unless flagged
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn = 0, uint32_t b_mn = 0) {
+    return (a_mn << 15) | (b_mn << 16)   // a_major / b_major: 1 = MN-major
+         | (1u << 4)            // c_format = F32
          | (1u << 7)            // a_format = BF16
          | (1u << 10)           // b_format = BF16
          | ((N >> 3) << 17)     // n_dim

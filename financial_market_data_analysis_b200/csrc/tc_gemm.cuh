@@ -39,6 +39,7 @@ struct Params {
     void* C; int64_t ldc;     // row stride in elements
     int64_t zC;               // element offset of batch z in C
     int a_row_off[4], b_row_off[4], b_k_off[4];
+    int a_mn, b_mn;           // 1: operand stored [K rows][MN contiguous] (MN-major), tensor map box 64(MN) x 64(K)
     const float* bias;        // per output column n - or per row m when bias_per_row - (nullable), batch stride zBias
     int64_t zBias;
     int bias_per_row;
@@ -89,23 +90,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (!tc::mbar_wait(&empty[s], ph ^ 1, p.dbg, 0x100 + s)) break;
                 tc::mbar_arrive_expect_tx(&full[s], A_BYTES + B_BYTES);
                 const int k = (kb0 + i) * BK;
-                tc::tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], k, p.a_row_off[z] + m0);
-                tc::tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], k + p.b_k_off[z], p.b_row_off[z] + n0);
+                if (p.a_mn) {        // two boxes of 64 (MN) x 64 (K rows)
+                    tc::tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], p.a_row_off[z] + m0, k);
+                    tc::tma_load_2d(sA + s * A_BYTES + A_BYTES / 2, &tmA, &full[s], p.a_row_off[z] + m0 + 64, k);
+                } else tc::tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], k, p.a_row_off[z] + m0);
+                if (p.b_mn) {
+                    tc::tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], p.b_row_off[z] + n0, k + p.b_k_off[z]);
+                    tc::tma_load_2d(sB + s * B_BYTES + B_BYTES / 2, &tmB, &full[s], p.b_row_off[z] + n0 + 64, k + p.b_k_off[z]);
+                } else tc::tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], k + p.b_k_off[z], p.b_row_off[z] + n0);
             }
         }
     } else if (warp == 1) {
         if (tc::elect_one()) {
-            constexpr uint32_t idesc = tc::umma_idesc_bf16(BM, BN);
+            const uint32_t idesc = tc::umma_idesc_bf16(BM, BN, (uint32_t)p.a_mn, (uint32_t)p.b_mn);
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
                 if (!tc::mbar_wait(&full[s], ph, p.dbg, 0x200 + s)) break;
                 tc::tcgen05_fence_after();
-                const uint64_t da = tc::umma_desc_k_sw128(tc::smem_u32(sA + s * A_BYTES));
-                const uint64_t db = tc::umma_desc_k_sw128(tc::smem_u32(sB + s * B_BYTES));
+                const uint32_t aa = tc::smem_u32(sA + s * A_BYTES), ab = tc::smem_u32(sB + s * B_BYTES);
+                const uint64_t da = p.a_mn ? tc::umma_desc_mn_sw128(aa, A_BYTES / 2) : tc::umma_desc_k_sw128(aa);
+                const uint64_t db = p.b_mn ? tc::umma_desc_mn_sw128(ab, B_BYTES / 2) : tc::umma_desc_k_sw128(ab);
+                // per K=16 step: K-major advances 32 B inside the swizzled row; MN-major advances 16 K-rows = 2048 B
+                const uint64_t sa = p.a_mn ? 128 : 2, sb = p.b_mn ? 128 : 2;
 #pragma unroll
-                for (int kk = 0; kk < BK / 16; ++kk)      // advance 16 bf16 = 32 B = 2 descriptor units
-                    tc::umma_bf16(tmem, da + 2 * kk, db + 2 * kk, idesc, (i | kk) ? 1u : 0u);
+                for (int kk = 0; kk < BK / 16; ++kk)
+                    tc::umma_bf16(tmem, da + sa * kk, db + sb * kk, idesc, (i | kk) ? 1u : 0u);
                 tc::umma_commit(&empty[s]);               // frees the smem slot when these MMAs retire
             }
             tc::umma_commit(accum);
@@ -281,6 +291,14 @@ static inline int make_output_map(CUtensorMap* m, void* base, int mode, uint64_t
     const uint64_t strides[1] = {ldc * (bf ? 2u : 4u)};
     const uint32_t box[2] = {bf ? 64u : 32u, 128u};
     return make_tmap_typed(m, bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, 2, dims, strides, box);
+}
+
+// MN-major bf16 operand stored [K rows][MN] with row stride ld (elements) -> 2-D map, box 64(MN) x 64(K rows)
+static inline int make_operand_map_mn(CUtensorMap* m, const void* base, uint64_t Krows, uint64_t MN, uint64_t ld) {
+    const uint64_t dims[2] = {MN, Krows};
+    const uint64_t strides[1] = {ld * 2};
+    const uint32_t box[2] = {64u, (uint32_t)BK};
+    return make_tmap_bf16(m, base, 2, dims, strides, box);
 }
 
 static inline cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p_in, cudaStream_t st) {

@@ -22,7 +22,6 @@
 //   G    bf16 [block][4][256][8]   r, z, n, hn = W_hn h + b_hn  (stash for backward)              (written)
 //   YB   bf16 [block][256][8]      h_t (h_{t-1} of the backward scan)                            (written)
 //   Yrow bf16 [R][D*H]    layer output                                        (written)
-//   YT   bf16 [D*H][R]    layer output transposed (wgrad operand, h_{t-1} of the backward scan)   (written)
 //   Wimg bf16 [D][H units][3][H]  per-unit rows of W_hh (r|z|n), copied to TMEM   (read once)
 #pragma once
 #include "tc_common.cuh"
@@ -116,7 +115,6 @@ struct FwdParams {
     const __nv_bfloat16* giB;
     const float* b_hn;            // [D][H]
     __nv_bfloat16* Yrow;
-    __nv_bfloat16* YT;
     __nv_bfloat16* G;
     __nv_bfloat16* YB;
     float* hn_out;                // [D][B][H] fp32, nullable
@@ -289,7 +287,6 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
                 gs[0] = *reinterpret_cast<uint4*>(sr); gs[256] = *reinterpret_cast<uint4*>(sz);
                 gs[512] = *reinterpret_cast<uint4*>(sn); gs[768] = *reinterpret_cast<uint4*>(shn);
             }
-            *reinterpret_cast<uint4*>(p.YT + (int64_t)(d * H + unit) * R + row0) = *reinterpret_cast<uint4*>(hv);
             reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.YB) + blk * YB_BLOCK)[tid] = *reinterpret_cast<uint4*>(hv);
             if (s == T - 1 && p.hn_out) {
 #pragma unroll
@@ -341,12 +338,12 @@ __global__ void pack_whh_image_kernel(const float* __restrict__ w_hh, __nv_bfloa
 //     D'[k, b] = sum_q W_hh[q, k] * dgh_{s-1}[b, q]                    (tcgen05.mma M=128 N=16, K = 3H)
 // i.e. the recurrent part of dh.  The epilogue thread of hidden unit k adds dY_t and the z-carry, forms the
 // gate derivatives from the stash, writes its three dgh values (bf16) into the [16 x 3H] operand tile of
-// the next step (locally + DSMEM bulk copy to the peers) and streams out dgi / dgh in row-major and
-// transposed form for the weight-gradient GEMMs; bias gradients accumulate in registers over all steps.
+// the next step (locally + DSMEM bulk copy to the peers) and streams out dgi / dgh row-major for the
+// weight-gradient GEMMs; bias gradients accumulate in registers over all steps.
 // The [16 x 3H] operand tile is double-buffered (2 x 24 KB); the control thread publishes it exactly as in the
 // forward kernel.
 // Per-step inputs (stash G, blocked h_{t-1} YB, blocked fp32 dY) come through a 3-stage bulk-copy ring.
-//   dgi_row bf16 [R][D*3H], dgiT / dghT bf16 [D*3H][R]                          (written)
+//   dgi_row bf16 [R][D*3H], dghn_row bf16 [R][D*H]: row-major, consumed as MN-major GEMM operands   (written)
 // =================================================================================================
 static inline size_t bwd_smem_bytes(int H) {
     const int KC3 = 3 * H / 64;
@@ -362,9 +359,8 @@ struct BwdParams {
     const __nv_bfloat16* YB;        // blocked h (see forward)
     const float* dYB;               // blocked fp32 dY: [block][256][8]
     const float* dh_init;           // [D][B][H] nullable: d(last hidden) of the top layer
-    __nv_bfloat16* dgi_row;
-    __nv_bfloat16* dgiT;
-    __nv_bfloat16* dghT;
+    __nv_bfloat16* dgi_row;         // [R][D*3H]  (da_r, da_z, da_n)
+    __nv_bfloat16* dghn_row;        // [R][D*H]   da_n * r  (the n-gate column block of dgh)
     float* db_ih;                   // grads of b_ih for direction 0; direction d at + d*dir_stride
     float* db_hh;
     int64_t dir_stride;
@@ -551,16 +547,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
             for (int i = 0; i < 8; ++i) {
                 __nv_bfloat16* gi_o = p.dgi_row + (row0 + i) * ldi + d * 3 * H + unit;
                 gi_o[0] = tr[i]; gi_o[H] = tz[i]; gi_o[2 * H] = tn[i];
-            }
-            {
-                __nv_bfloat16* o = p.dgiT + (int64_t)(d * 3 * H + unit) * R + row0;
-                *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(tr);
-                *reinterpret_cast<uint4*>(o + (int64_t)H * R) = *reinterpret_cast<uint4*>(tz);
-                *reinterpret_cast<uint4*>(o + (int64_t)2 * H * R) = *reinterpret_cast<uint4*>(tn);
-                __nv_bfloat16* o2 = p.dghT + (int64_t)(d * 3 * H + unit) * R + row0;
-                *reinterpret_cast<uint4*>(o2) = *reinterpret_cast<uint4*>(tr);
-                *reinterpret_cast<uint4*>(o2 + (int64_t)H * R) = *reinterpret_cast<uint4*>(tz);
-                *reinterpret_cast<uint4*>(o2 + (int64_t)2 * H * R) = *reinterpret_cast<uint4*>(tnr);
+                p.dghn_row[(row0 + i) * (D * H) + d * H + unit] = tnr[i];
             }
         }
         // bias gradients: sum the 8 columns of this thread; the two column halves and all tiles add atomically

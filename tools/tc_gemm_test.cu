@@ -9,7 +9,7 @@
 
 static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
-static int run_case(int M, int N, int K, int mode, int splitk, int kshift, bool use_bias, int a_off, int b_off) {
+static int run_case(int M, int N, int K, int mode, int splitk, int kshift, bool use_bias, int a_off, int b_off, int a_mn = 0, int b_mn = 0) {
     const int Arows = M + a_off, Brows = N + b_off;
     std::vector<float> A((size_t)Arows * K), B((size_t)Brows * K), bias(N);
     srand(M * 31 + N * 7 + K);
@@ -17,8 +17,11 @@ static int run_case(int M, int N, int K, int mode, int splitk, int kshift, bool 
     for (auto& v : B) v = bf((rand() % 2001 - 1000) / 1000.f);
     for (auto& v : bias) v = (rand() % 2001 - 1000) / 500.f;
     std::vector<__nv_bfloat16> Ah(A.size()), Bh(B.size());
-    for (size_t i = 0; i < A.size(); ++i) Ah[i] = __float2bfloat16(A[i]);
-    for (size_t i = 0; i < B.size(); ++i) Bh[i] = __float2bfloat16(B[i]);
+    // device copies: K-major [rows][K], or MN-major (transposed) [K][rows]
+    for (int r = 0; r < Arows; ++r) for (int k = 0; k < K; ++k)
+        Ah[a_mn ? (size_t)k * Arows + r : (size_t)r * K + k] = __float2bfloat16(A[(size_t)r * K + k]);
+    for (int r = 0; r < Brows; ++r) for (int k = 0; k < K; ++k)
+        Bh[b_mn ? (size_t)k * Brows + r : (size_t)r * K + k] = __float2bfloat16(B[(size_t)r * K + k]);
     __nv_bfloat16 *dA, *dB; float* dbias; void* dC; unsigned int* dbg;
     CK(cudaMalloc(&dA, Ah.size() * 2)); CK(cudaMalloc(&dB, Bh.size() * 2)); CK(cudaMalloc(&dbias, N * 4));
     CK(cudaMalloc(&dC, (size_t)M * N * 4)); CK(cudaMalloc(&dbg, 64));
@@ -27,10 +30,12 @@ static int run_case(int M, int N, int K, int mode, int splitk, int kshift, bool 
     CK(cudaMemcpy(dbias, bias.data(), N * 4, cudaMemcpyHostToDevice));
     CK(cudaMemset(dC, 0, (size_t)M * N * 4)); CK(cudaMemset(dbg, 0, 64));
     CUtensorMap tA, tB;
-    if (tcg::make_operand_map(&tA, dA, Arows, K, K) || tcg::make_operand_map(&tB, dB, Brows, K, K)) { printf("tensor map failed\n"); return 1; }
+    int me1 = a_mn ? tcg::make_operand_map_mn(&tA, dA, K, Arows, Arows) : tcg::make_operand_map(&tA, dA, Arows, K, K);
+    int me2 = b_mn ? tcg::make_operand_map_mn(&tB, dB, K, Brows, Brows) : tcg::make_operand_map(&tB, dB, Brows, K, K);
+    if (me1 || me2) { printf("tensor map failed\n"); return 1; }
     tcg::Params p{};
     p.M = M; p.N = N; p.K = K; p.batch = 1; p.splitk = splitk; p.mode = mode; p.C = dC; p.ldc = N; p.zC = 0;
-    p.a_row_off[0] = a_off; p.b_row_off[0] = b_off; p.b_k_off[0] = kshift; p.bias = use_bias ? dbias : nullptr; p.zBias = 0; p.dbg = dbg;
+    p.a_row_off[0] = a_off; p.b_row_off[0] = b_off; p.b_k_off[0] = kshift; p.a_mn = a_mn; p.b_mn = b_mn; p.bias = use_bias ? dbias : nullptr; p.zBias = 0; p.dbg = dbg;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     CK(tcg::launch(tA, tB, p, 0));
     CK(cudaDeviceSynchronize());
@@ -68,8 +73,8 @@ static int run_case(int M, int N, int K, int mode, int splitk, int kshift, bool 
     }
     const double tol = mode == tcg::OUT_BF16 ? 1e-2 * (maxref + 1) : 2e-4 * (maxref + 1);
     const bool pass = h[0] == 0 && maxerr < tol;
-    printf("%s M=%d N=%d K=%d mode=%d splitk=%d kshift=%d bias=%d off=(%d,%d): maxerr=%.3e (ref max %.2f, %ld checked) dbg=%x/%u/%u  %.3f ms %.1f TFLOP/s\n",
-           pass ? "PASS" : "FAIL", M, N, K, mode, splitk, kshift, (int)use_bias, a_off, b_off, maxerr, maxref, checked, h[0], h[1], h[2], ms,
+    printf("%s mn=%d%d M=%d N=%d K=%d mode=%d splitk=%d kshift=%d bias=%d off=(%d,%d): maxerr=%.3e (ref max %.2f, %ld checked) dbg=%x/%u/%u  %.3f ms %.1f TFLOP/s\n",
+           pass ? "PASS" : "FAIL", a_mn, b_mn, M, N, K, mode, splitk, kshift, (int)use_bias, a_off, b_off, maxerr, maxref, checked, h[0], h[1], h[2], ms,
            ms > 0 ? 2.0 * M * N * K / ms / 1e9 : 0.0);
     cudaFree(dA); cudaFree(dB); cudaFree(dbias); cudaFree(dC); cudaFree(dbg);
     return pass ? 0 : 2;
@@ -86,6 +91,12 @@ int main() {
     bad += run_case(768, 256, 8192, tcg::OUT_ATOMIC_F32, 8, 0, false, 0, 0);
     bad += run_case(768, 256, 8192, tcg::OUT_ATOMIC_F32, 16, -512, false, 768, 256);
     bad += run_case(768, 256, 8192, tcg::OUT_ATOMIC_F32, 16, 512, false, 0, 0);
+    bad += run_case(128, 128, 64, tcg::OUT_F32, 1, 0, false, 0, 0, 1, 0);
+    bad += run_case(128, 128, 64, tcg::OUT_F32, 1, 0, false, 0, 0, 0, 1);
+    bad += run_case(256, 384, 320, tcg::OUT_F32, 1, 0, true, 0, 0, 1, 1);
+    bad += run_case(768, 512, 8192, tcg::OUT_ATOMIC_F32, 16, 0, false, 768, 0, 1, 1);
+    bad += run_case(768, 256, 8192, tcg::OUT_ATOMIC_F32, 16, -512, false, 0, 256, 1, 1);
+    bad += run_case(768, 256, 65536, tcg::OUT_ATOMIC_F32, 37, 512, false, 0, 0, 1, 1);
     bad += run_case(65536, 1536, 64, tcg::OUT_BF16, 1, 0, true, 0, 0);
     bad += run_case(65536, 1536, 512, tcg::OUT_BF16, 1, 0, true, 0, 0);
     bad += run_case(65536, 512, 1536, tcg::OUT_F32, 1, 0, false, 0, 0);
