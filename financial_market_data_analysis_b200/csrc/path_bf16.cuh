@@ -143,60 +143,92 @@ __global__ void pack_bias_kernel(const float* __restrict__ b_ih, const float* __
     if (q >= 2 * H) bhn[d * H + q - 2 * H] = b_hh[q];
 }
 
-// pooling head on the time-major bf16 output (biGRU_model.py:111-133)
-__global__ void head_pool_tm_kernel(const bf16_t* __restrict__ Y, float* __restrict__ cat, int* __restrict__ arg,
-                                    int B, int T, int H, int D) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)B * H) return;
-    const int j = idx % H, b = idx / H;
+// All weight packing of a forward call in ONE launch: blockIdx.y enumerates (layer, direction).
+struct PackJob { const float* w_ih; const float* w_hh; const float* b_ih; const float* b_hh;
+                 bf16_t* Wih; bf16_t* WihT; bf16_t* Wimg; bf16_t* WTimg; float* bfold; float* bhn; int I; int d; };
+struct PackJobs { PackJob j[32]; };
+__global__ void pack_all_kernel(const PackJobs jobs, int H, int D) {
+    const PackJob& J = jobs.j[blockIdx.y];
+    const int H3 = 3 * H, I = J.I, d = J.d;
+    const int64_t n_ih = (int64_t)H3 * I, n_hh = (int64_t)H3 * H;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = i0; i < n_ih; i += stride) {          // W_ih [3H][I] -> rows d*3H.. of Wih, columns of WihT
+        const int k = i % I, q = i / I;
+        const bf16_t v = __float2bfloat16(J.w_ih[i]);
+        J.Wih[((int64_t)d * H3 + q) * I + k] = v;
+        J.WihT[(int64_t)k * D * H3 + (int64_t)d * H3 + q] = v;
+    }
+    for (int64_t i = i0; i < n_hh; i += stride) {          // W_hh [3H][H] -> per-unit rows (fwd) and rows of W_hh^T (bwd)
+        const int k = i % H, row = i / H, g = row / H, unit = row % H;
+        const bf16_t v = __float2bfloat16(J.w_hh[i]);
+        J.Wimg[((int64_t)unit * 3 + g) * H + k] = v;
+        J.WTimg[(int64_t)k * H3 + row] = v;
+    }
+    for (int64_t q = i0; q < H3; q += stride) {
+        J.bfold[d * H3 + q] = J.b_ih[q] + (q < 2 * H ? J.b_hh[q] : 0.f);
+        if (q >= 2 * H) J.bhn[d * H + q - 2 * H] = J.b_hh[q];
+    }
+}
+
+// Head forward (biGRU_model.py:111-137) fused: direction sum, last hidden, max / mean pooling over T and the
+// Linear(3H -> C), one block per batch row (threads = hidden units; each time step is one contiguous 2*D*H-byte row).
+__global__ void head_fwd_kernel(const bf16_t* __restrict__ Y, const float* __restrict__ lin_w, const float* __restrict__ lin_b,
+                                float* __restrict__ cat, int* __restrict__ arg, float* __restrict__ logits,
+                                int B, int T, int H, int D, int C) {
+    extern __shared__ float red[];                     // [C][blockDim/32]
+    const int b = blockIdx.x, j = threadIdx.x;
     const int ld = D * H;
-    float last = __bfloat162float(Y[((int64_t)(T - 1) * B + b) * ld + j]);
-    if (D == 2) last += __bfloat162float(Y[(int64_t)b * ld + H + j]);
-    float mx = -INFINITY, sum = 0.f;
+    float last = 0.f, mx = -INFINITY, sum = 0.f;
     int am = 0;
-    for (int t = 0; t < T; ++t) {
-        const bf16_t* y = Y + ((int64_t)t * B + b) * ld;
-        float s = __bfloat162float(y[j]);
-        if (D == 2) s += __bfloat162float(y[H + j]);
-        if (s > mx) { mx = s; am = t; }
-        sum += s;
-    }
-    float* c = cat + (int64_t)b * 3 * H;
-    c[j] = last; c[H + j] = mx; c[2 * H + j] = sum / (float)T;
-    arg[idx] = am;
-}
-// blocked dY (fp32, layout of tc_gemm OUT_SCAN_F32 with G = 1) of the top layer and the initial dh carry [D][B][H]
-__global__ void head_bwd_dy_tm_kernel(const float* __restrict__ dcat, const int* __restrict__ arg, float* __restrict__ dYB,
-                                      float* __restrict__ dhinit, int B, int T, int H, int D) {
-    // one thread per (tile, t, cta, tid): writes its 8 values for both directions
-    const int CS = H / 128, ntl = B / 16;
-    const int64_t nthreads = (int64_t)ntl * T * CS * 256;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nthreads) return;
-    int64_t e = idx;
-    const int tid = e % 256; e /= 256;
-    const int c = e % CS; e /= CS;
-    const int t = e % T;
-    const int tile = e / T;
-    const int unit = c * 128 + ((tid >> 5) & 3) * 32 + (tid & 31);
-    const int b0 = tile * 16 + (tid >> 7) * 8;
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int b = b0 + i;
-        const float* dc = dcat + (int64_t)b * 3 * H;
-        v[i] = dc[2 * H + unit] / (float)T + (arg[(int64_t)b * H + unit] == t ? dc[H + unit] : 0.f);
-        if (t == 0) {
-            dhinit[(int64_t)b * H + unit] = dc[unit];
-            if (D == 2) dhinit[((int64_t)B + b) * H + unit] = dc[unit];
+    if (j < H) {
+        last = __bfloat162float(Y[((int64_t)(T - 1) * B + b) * ld + j]);
+        if (D == 2) last += __bfloat162float(Y[(int64_t)b * ld + H + j]);
+#pragma unroll 16
+        for (int t = 0; t < T; ++t) {
+            const bf16_t* y = Y + ((int64_t)t * B + b) * ld;
+            float s = __bfloat162float(y[j]);
+            if (D == 2) s += __bfloat162float(y[H + j]);
+            if (s > mx) { mx = s; am = t; }
+            sum += s;
         }
+        float* c = cat + (int64_t)b * 3 * H;
+        c[j] = last; c[H + j] = mx; c[2 * H + j] = sum / (float)T;
+        arg[(int64_t)b * H + j] = am;
     }
-    for (int d = 0; d < D; ++d) {
-        float4* o = reinterpret_cast<float4*>(dYB + ((((int64_t)d * ntl + tile) * T + t) * CS + c) * 256 * 8 + (int64_t)tid * 8);
-        o[0] = make_float4(v[0], v[1], v[2], v[3]);
-        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    const float avg = sum / (float)T;
+    const int nw = blockDim.x >> 5;
+    for (int cc = 0; cc < C; ++cc) {
+        float v = 0.f;
+        if (j < H) {
+            const float* w = lin_w + (int64_t)cc * 3 * H;
+            v = last * w[j] + mx * w[H + j] + avg * w[2 * H + j];
+        }
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((j & 31) == 0) red[cc * nw + (j >> 5)] = v;
+    }
+    __syncthreads();
+    if (j < C) {
+        float v = lin_b[j];
+        for (int w = 0; w < nw; ++w) v += red[j * nw + w];
+        logits[(int64_t)b * C + j] = v;
     }
 }
+// d(lin_w)[c][k] = sum_b dlogits[b][c] cat[b][k];  d(lin_b)[c] = sum_b dlogits[b][c]
+__global__ void head_bwd_w_kernel(const float* __restrict__ dlogits, const float* __restrict__ cat, float* __restrict__ dlin_w,
+                                  float* __restrict__ dlin_b, int B, int H3, int C) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cc = blockIdx.y;
+    if (k >= H3) return;
+    float acc = 0.f, accb = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const float g = dlogits[(int64_t)b * C + cc];
+        acc = fmaf(g, cat[(int64_t)b * H3 + k], acc);
+        accb += g;
+    }
+    dlin_w[(int64_t)cc * H3 + k] = acc;
+    if (k == 0) dlin_b[cc] = accb;
+}
+
 // dX^T of layer 0 (fp32 [F][R]) back to the caller's [B][T][F] (+ input-dropout mask); 32x32 smem transpose
 __global__ void dx_to_batch_major_kernel(const float* __restrict__ dXT, float* __restrict__ dx, int B, int T, int F,
                                          float pdrop, int spatial, uint64_t seed) {
@@ -227,7 +259,7 @@ __global__ void dx_to_batch_major_kernel(const float* __restrict__ dXT, float* _
 // ---------------------------------------------------------------------------------------------------
 // A / B operand descriptions: K-major [rows][K] (ld = row stride) or MN-major [K rows][MN] (p.a_mn / p.b_mn set)
 static int tc_gemm(const void* A, int64_t a_rows, int64_t lda, const void* Bm, int64_t b_rows, int64_t ldb,
-                   tcg::Params& p, cudaStream_t st) {
+                   tcg::Params& p, cudaStream_t st, int kclass = KC_TC_GEMM) {
     CUtensorMap tA, tB;
     const int ea = p.a_mn ? tcg::make_operand_map_mn(&tA, A, (uint64_t)p.K, (uint64_t)a_rows, (uint64_t)lda)
                           : tcg::make_operand_map(&tA, A, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda);
@@ -238,7 +270,7 @@ static int tc_gemm(const void* A, int64_t a_rows, int64_t lda, const void* Bm, i
                         (long long)b_rows, p.K, (long long)lda, (long long)ldb);
         return BIGRU_ERR_CUDA;
     }
-    ProfScope ps(KC_TC_GEMM, 2.0 * p.M * p.N * (double)p.K * p.batch, 0.0, st);
+    ProfScope ps(kclass, 2.0 * p.M * p.N * (double)p.K * p.batch, 0.0, st);
     CUDA_TRY(tcg::launch(tA, tB, p, st));
     return BIGRU_OK;
 }
@@ -261,20 +293,20 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
     unsigned int* dbg = (unsigned int*)(S + L.dbg);
     CUDA_TRY(cudaMemsetAsync(dbg, 0, 64, st));
 
-    // 1. pack weights to bf16 operand images
-    for (int l = 0; l < p.L; ++l) {
-        const int I = (int)p.in_size(l);
-        for (int d = 0; d < D; ++d) {
-            KLAUNCH(KC_PACK, 0.0, 0.0, st, pack_wih_kernel<<<148, 256, 0, st>>>(params + p.off_wih(l, d), (bf16_t*)(S + L.Wih[l]),
-                                                                               (bf16_t*)(S + L.WihT[l]), 3 * H, I, d, D));
-            KLAUNCH(KC_PACK, 0.0, 0.0, st, tcs::pack_whh_image_kernel<<<148, 256, 0, st>>>(
-                                               params + p.off_whh(l, d), (bf16_t*)(S + L.Wimg[l]) + (size_t)d * 3 * H * H, H));
-            KLAUNCH(KC_PACK, 0.0, 0.0, st, tcs::pack_whhT_image_kernel<<<148, 256, 0, st>>>(
-                                               params + p.off_whh(l, d), (bf16_t*)(S + L.WTimg[l]) + (size_t)d * 3 * H * H, H));
-            KLAUNCH(KC_PACK, 0.0, 0.0, st, pack_bias_kernel<<<nblk2(3 * H, 128), 128, 0, st>>>(
-                                               params + p.off_bih(l, d), params + p.off_bhh(l, d), (float*)(S + L.bfold[l]),
-                                               (float*)(S + L.bhn[l]), H, d));
-        }
+    // 1. pack weights to bf16 operand images (one launch for all layers and directions)
+    {
+        PackJobs jobs{};
+        int nj = 0;
+        for (int l = 0; l < p.L; ++l)
+            for (int d = 0; d < D; ++d) {
+                PackJob& J = jobs.j[nj++];
+                J.w_ih = params + p.off_wih(l, d); J.w_hh = params + p.off_whh(l, d);
+                J.b_ih = params + p.off_bih(l, d); J.b_hh = params + p.off_bhh(l, d);
+                J.Wih = (bf16_t*)(S + L.Wih[l]); J.WihT = (bf16_t*)(S + L.WihT[l]);
+                J.Wimg = (bf16_t*)(S + L.Wimg[l]) + (size_t)d * 3 * H * H; J.WTimg = (bf16_t*)(S + L.WTimg[l]) + (size_t)d * 3 * H * H;
+                J.bfold = (float*)(S + L.bfold[l]); J.bhn = (float*)(S + L.bhn[l]); J.I = (int)p.in_size(l); J.d = d;
+            }
+        KLAUNCH(KC_PACK, 0.0, 0.0, st, pack_all_kernel<<<dim3(64, nj), 256, 0, st>>>(jobs, H, D));
     }
     // 2. layer-0 input: cast to bf16, time-major rows (+ input dropout)
     KLAUNCH(KC_PACK, 0.0, 6.0 * R * F, st, cast_x_kernel<<<148 * 8, 256, 0, st>>>(x, (bf16_t*)(S + L.Xrow[0]), B, T, F,
@@ -308,12 +340,13 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
             CUDA_TRY(tcs::launch_fwd(f, st));
         }
     }
-    // 5. head
-    KLAUNCH(KC_HEAD, 0.0, 0.0, st, head_pool_tm_kernel<<<nblk2((int64_t)B * H, 128), 128, 0, st>>>(
-                                       (const bf16_t*)(S + L.Yrow[p.L - 1]), (float*)(S + L.cat), (int*)(S + L.arg), B, T, H, D));
-    GemmArgs lin = gemm_args((const float*)(S + L.cat), params + p.off_linw(), logits, B, p.C, 3 * H, 3 * H, 1, 3 * H, 1, p.C);
-    lin.bias = params + p.off_linb();
-    TRY(sgemm_launch(lin, st));
+    // 5. head: pooling + Linear fused
+    {
+        const int threads = ((H + 31) / 32) * 32;
+        KLAUNCH(KC_HEAD, 0.0, 2.0 * R * D * H, st, head_fwd_kernel<<<B, threads, sizeof(float) * p.C * (threads / 32), st>>>(
+                    (const bf16_t*)(S + L.Yrow[p.L - 1]), params + p.off_linw(), params + p.off_linb(), (float*)(S + L.cat),
+                    (int*)(S + L.arg), logits, B, T, H, D, p.C));
+    }
     return BIGRU_OK;
 }
 
@@ -333,25 +366,19 @@ static int backward_bf16(const bigru_plan& p, const float* params, const float* 
     const bool do_drop = training && drop > 0.f;
     unsigned int* dbg = (unsigned int*)(const_cast<uint8_t*>(S) + L.dbg);
     CUDA_TRY(cudaMemsetAsync(grads, 0, sizeof(float) * p.nparams, st));
-    float* dcat = (float*)(W + L.dcat);
     const float* cat = (const float*)(S + L.cat);
-    GemmArgs a = gemm_args(dlogits, params + p.off_linw(), dcat, B, 3 * H, C, C, 1, 1, 3 * H, 3 * H);
-    TRY(sgemm_launch(a, st));
-    GemmArgs w = gemm_args(dlogits, cat, grads + p.off_linw(), C, 3 * H, B, 1, C, 1, 3 * H, 3 * H);
-    TRY(sgemm_launch(w, st));
-    TRY(colsum_launch(dlogits, grads + p.off_linb(), B, C, C, 1, 0, 0, st));
+    KLAUNCH(KC_HEAD, 0.0, 0.0, st, head_bwd_w_kernel<<<dim3(nblk2(3 * H, 128), C), 128, 0, st>>>(
+                dlogits, cat, grads + p.off_linw(), grads + p.off_linb(), B, 3 * H, C));
     float* dY = (float*)(W + L.dYa);
     float* dYnext = (float*)(W + L.dYb);
-    float* dhinit = (float*)(W + L.dhinit);
-    KLAUNCH(KC_HEAD, 0.0, 0.0, st, head_bwd_dy_tm_kernel<<<nblk2(R * H / 8, 256), 256, 0, st>>>(dcat, (const int*)(S + L.arg), dY,
-                                                                                           dhinit, B, T, H, D));
     for (int l = p.L - 1; l >= 0; --l) {
         const int I = (int)p.in_size(l);
         // 1. BPTT scan
         tcs::BwdParams b{};
         b.B = B; b.T = T; b.H = H; b.D = D;
         b.WTimg = (const bf16_t*)(S + L.WTimg[l]); b.G = (const bf16_t*)(S + L.G[l]); b.YB = (const bf16_t*)(S + L.YB[l]);
-        b.dYB = dY; b.dh_init = l == p.L - 1 ? dhinit : nullptr;
+        b.dYB = dY;
+        if (l == p.L - 1) { b.dlogits = dlogits; b.lin_w = params + p.off_linw(); b.arg = (const int*)(S + L.arg); b.C = C; }
         b.dgi_row = (bf16_t*)(W + L.gi); b.dghn_row = (bf16_t*)(W + L.dghn);
         b.db_ih = grads + p.off_bih(l, 0); b.db_hh = grads + p.off_bhh(l, 0); b.dir_stride = p.ld_block(l); b.dbg = dbg;
         {
@@ -371,7 +398,7 @@ static int backward_bf16(const bigru_plan& p, const float* params, const float* 
             g.C = grads + p.off_wih(l, 0); g.ldc = I; g.zC = p.ld_block(l);
             for (int d = 0; d < D; ++d) { g.a_row_off[d] = d * 3 * H; g.b_row_off[d] = 0; g.b_k_off[d] = 0; }
             g.dbg = dbg;
-            TRY(tc_gemm(W + L.gi, (int64_t)D * 3 * H, (int64_t)D * 3 * H, Xin, I, I, g, st));
+            TRY(tc_gemm(W + L.gi, (int64_t)D * 3 * H, (int64_t)D * 3 * H, Xin, I, I, g, st, KC_TC_GEMM_DWIH));
         }
         // 3. dW_hh[d] = dgh[d]^T H_prev  with H_prev(t) = Y(t-1) (dir 0) / Y(t+1) (dir 1): a shift of -+B ROWS of the
         //    time-major output; rows outside [0, R) read as zero through TMA (h_prev = 0 at the first step).
@@ -387,8 +414,8 @@ static int backward_bf16(const bigru_plan& p, const float* params, const float* 
                 g.b_row_off[d] = d * H; g.b_k_off[d] = d == 0 ? -B : B;
             }
             g.dbg = dbg;
-            if (part == 0) TRY(tc_gemm(W + L.gi, (int64_t)D * 3 * H, (int64_t)D * 3 * H, S + L.Yrow[l], (int64_t)D * H, (int64_t)D * H, g, st));
-            else TRY(tc_gemm(W + L.dghn, (int64_t)D * H, (int64_t)D * H, S + L.Yrow[l], (int64_t)D * H, (int64_t)D * H, g, st));
+            if (part == 0) TRY(tc_gemm(W + L.gi, (int64_t)D * 3 * H, (int64_t)D * 3 * H, S + L.Yrow[l], (int64_t)D * H, (int64_t)D * H, g, st, KC_TC_GEMM_DWHH));
+            else TRY(tc_gemm(W + L.dghn, (int64_t)D * H, (int64_t)D * H, S + L.Yrow[l], (int64_t)D * H, (int64_t)D * H, g, st, KC_TC_GEMM_DWHH));
         }
         // 4. dX^T = W_ih^T (both directions concatenated along K = D*3H) x dgi_row^T.  For l > 0 it is written directly in
         //    the blocked layout the next backward scan reads; for layer 0 (caller wants dx) as [F][R] and then re-laid.
@@ -399,7 +426,7 @@ static int backward_bf16(const bigru_plan& p, const float* params, const float* 
             g.mode = l > 0 ? tcg::OUT_SCAN_F32 : tcg::OUT_F32;
             g.blk = tcg::ScanBlk{T, B, H, 1};
             g.C = dYnext; g.ldc = R; g.dbg = dbg;
-            TRY(tc_gemm(S + L.WihT[l], I, (int64_t)D * 3 * H, W + L.gi, R, (int64_t)D * 3 * H, g, st));
+            TRY(tc_gemm(S + L.WihT[l], I, (int64_t)D * 3 * H, W + L.gi, R, (int64_t)D * 3 * H, g, st, KC_TC_GEMM_DX));
             if (l > 0 && dropped)
                 KLAUNCH(KC_MISC, 0.0, 0.0, st, dropout_grad_rows_kernel<<<148 * 8, 256, 0, st>>>(dYnext, R, I, B, T, H, drop, seed, (uint32_t)l));
             if (l == 0) {

@@ -101,6 +101,7 @@ constexpr int DY_BLOCK = 256 * 32;        // bytes of one blocked fp32 dY block
 constexpr int NSF = 4;                    // forward input ring depth
 constexpr int NSB = 3;                    // backward input ring depth
 constexpr int BWD_STAGE = G_BLOCK + YB_BLOCK + DY_BLOCK;
+constexpr int HEAD_CONST = 3 * 256 * 32;   // top layer: per-thread davg/T, dmax, argmax (8 values each)
 
 static inline size_t fwd_smem_bytes(int H) {
     const int KC = H / 64;
@@ -347,7 +348,7 @@ __global__ void pack_whh_image_kernel(const float* __restrict__ w_hh, __nv_bfloa
 // =================================================================================================
 static inline size_t bwd_smem_bytes(int H) {
     const int KC3 = 3 * H / 64;
-    return (size_t)2 * KC3 * H_CHUNK + (size_t)NSB * BWD_STAGE + 1024 + 256;
+    return (size_t)2 * KC3 * H_CHUNK + (size_t)NSB * BWD_STAGE + (size_t)HEAD_CONST + 1024 + 256;
 }
 constexpr uint32_t BWD_A_COL = 32;        // accumulator in columns [0, 16), W_hh^T from column 32
 __host__ __device__ static inline uint32_t bwd_tmem_cols(int H) { return 32 + 3 * H / 2 <= 256 ? 256u : 512u; }
@@ -357,8 +358,13 @@ struct BwdParams {
     const __nv_bfloat16* WTimg;     // [D][H units][3H]  rows of W_hh^T, copied to TMEM
     const __nv_bfloat16* G;
     const __nv_bfloat16* YB;        // blocked h (see forward)
-    const float* dYB;               // blocked fp32 dY: [block][256][8]
-    const float* dh_init;           // [D][B][H] nullable: d(last hidden) of the top layer
+    const float* dYB;               // blocked fp32 dY: [block][256][8]   (lower layers)
+    // top layer: dY is formed on the fly from the head (biGRU_model.py:111-137): d(concat) = dlogits x lin_w,
+    // dY_t[b,u] = davg/T + (argmax_t == t ? dmax : 0), initial carry = d(last hidden); dYB is not read then
+    const float* dlogits;           // [B][C] nullable (non-null selects top-layer mode)
+    const float* lin_w;             // [C][3H]
+    const int* arg;                 // [B][H] argmax_t of the pooled output
+    int C;
     __nv_bfloat16* dgi_row;         // [R][D*3H]  (da_r, da_z, da_n)
     __nv_bfloat16* dghn_row;        // [R][D*H]   da_n * r  (the n-gate column block of dgh)
     float* db_ih;                   // grads of b_ih for direction 0; direction d at + d*dir_stride
@@ -373,7 +379,8 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
     const int H = p.H, KC = H / 64, KC3 = 3 * KC, CS = H / UNITS, B = p.B, T = p.T, D = p.D;
     uint8_t* sD = smem;                                    // [2][KC3][H_CHUNK]  dgh operand tiles
     uint8_t* sIn = sD + (size_t)2 * KC3 * H_CHUNK;         // [NSB][G | YB | dY]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + (size_t)NSB * BWD_STAGE);
+    float* sHead = reinterpret_cast<float*>(sIn + (size_t)NSB * BWD_STAGE);    // [3][256][8]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + (size_t)NSB * BWD_STAGE + HEAD_CONST);
     uint64_t* d_full = bars;           // [2]  peers' dgh chunks landed
     uint64_t* mma_done = bars + 2;
     uint64_t* epi_done = bars + 3;
@@ -387,6 +394,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
     const int ntiles = B / NB;
     const int d = cluster_id / ntiles, tile = cluster_id % ntiles;
     const int64_t R = (int64_t)T * B;
+    const bool top = p.dlogits != nullptr;
 
     if (threadIdx.x == 0) {
         tc::mbar_init(&d_full[0], 1);
@@ -419,10 +427,10 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
                 const int t = d == 0 ? T - 1 - s : s;
                 const bool first = d == 0 ? t == 0 : t == T - 1;         // first step of the FORWARD recurrence: h_prev = 0
                 uint8_t* dst = sIn + (size_t)st * BWD_STAGE;
-                tc::mbar_arrive_expect_tx(&in_full[st], (uint32_t)(G_BLOCK + DY_BLOCK + (first ? 0 : YB_BLOCK)));
+                tc::mbar_arrive_expect_tx(&in_full[st], (uint32_t)(G_BLOCK + (top ? 0 : DY_BLOCK) + (first ? 0 : YB_BLOCK)));
                 const size_t blk = blk_index(d, tile, t, (int)c, ntiles, T, CS);
                 tc::bulk_g2s(dst, reinterpret_cast<const uint8_t*>(p.G) + blk * G_BLOCK, G_BLOCK, &in_full[st]);
-                tc::bulk_g2s(dst + G_BLOCK + YB_BLOCK, reinterpret_cast<const uint8_t*>(p.dYB) + blk * DY_BLOCK, DY_BLOCK, &in_full[st]);
+                if (!top) tc::bulk_g2s(dst + G_BLOCK + YB_BLOCK, reinterpret_cast<const uint8_t*>(p.dYB) + blk * DY_BLOCK, DY_BLOCK, &in_full[st]);
                 if (!first) {
                     const size_t pblk = blk_index(d, tile, d == 0 ? t - 1 : t + 1, (int)c, ntiles, T, CS);
                     tc::bulk_g2s(dst + G_BLOCK, reinterpret_cast<const uint8_t*>(p.YB) + pblk * YB_BLOCK, YB_BLOCK, &in_full[st]);
@@ -471,8 +479,25 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
         const int ldi = D * 3 * H;
         float dhz[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-            dhz[i] = p.dh_init ? p.dh_init[((int64_t)d * B + tile * NB + col0 + i) * H + unit] : 0.f;
+        for (int i = 0; i < 8; ++i) dhz[i] = 0.f;
+        if (top) {
+            // d(concat) rows of this thread's 8 batch columns: [last | max | avg] x lin_w^T
+            float* c_avg = sHead + (size_t)tid * 8;
+            float* c_max = sHead + 256 * 8 + (size_t)tid * 8;
+            int* c_arg = reinterpret_cast<int*>(sHead + 2 * 256 * 8) + (size_t)tid * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int b = tile * NB + col0 + i;
+                float dl = 0.f, dm = 0.f, da = 0.f;
+                for (int cc = 0; cc < p.C; ++cc) {
+                    const float g = p.dlogits[(int64_t)b * p.C + cc];
+                    const float* w = p.lin_w + (int64_t)cc * 3 * H;
+                    dl = fmaf(g, w[unit], dl); dm = fmaf(g, w[H + unit], dm); da = fmaf(g, w[2 * H + unit], da);
+                }
+                dhz[i] = dl;                                   // d(last hidden) enters the carry of both directions
+                c_avg[i] = da / (float)T; c_max[i] = dm; c_arg[i] = p.arg[(int64_t)b * H + unit];
+            }
+        }
         float sb_r = 0.f, sb_z = 0.f, sb_n = 0.f, sb_nr = 0.f;
         bool ok = true;
         for (int s = 0; s < T; ++s) {
@@ -487,8 +512,21 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
                 const uint4* gp = reinterpret_cast<const uint4*>(base) + tid;
                 const uint4 u0 = gp[0], u1 = gp[256], u2 = gp[512], u3 = gp[768];
                 const uint4 uh = first ? make_uint4(0u, 0u, 0u, 0u) : reinterpret_cast<const uint4*>(base + G_BLOCK)[tid];
-                const float4* dyp = reinterpret_cast<const float4*>(base + G_BLOCK + YB_BLOCK) + 2 * tid;
-                const float4 a = dyp[0], b = dyp[1];
+                float4 a, b;
+                if (top) {
+                    const float4* ca = reinterpret_cast<const float4*>(sHead + (size_t)tid * 8);
+                    const float4* cm = reinterpret_cast<const float4*>(sHead + 256 * 8 + (size_t)tid * 8);
+                    const int4* cg = reinterpret_cast<const int4*>(sHead + 2 * 256 * 8 + (size_t)tid * 8);
+                    const float4 a0 = ca[0], a1 = ca[1], m0 = cm[0], m1 = cm[1];
+                    const int4 g0 = cg[0], g1 = cg[1];
+                    a = make_float4(a0.x + (g0.x == t ? m0.x : 0.f), a0.y + (g0.y == t ? m0.y : 0.f),
+                                    a0.z + (g0.z == t ? m0.z : 0.f), a0.w + (g0.w == t ? m0.w : 0.f));
+                    b = make_float4(a1.x + (g1.x == t ? m1.x : 0.f), a1.y + (g1.y == t ? m1.y : 0.f),
+                                    a1.z + (g1.z == t ? m1.z : 0.f), a1.w + (g1.w == t ? m1.w : 0.f));
+                } else {
+                    const float4* dyp = reinterpret_cast<const float4*>(base + G_BLOCK + YB_BLOCK) + 2 * tid;
+                    a = dyp[0]; b = dyp[1];
+                }
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&in_empty[st]);
                 const __nv_bfloat16* t8 = reinterpret_cast<const __nv_bfloat16*>(&u0);
