@@ -183,7 +183,7 @@ __global__ void head_fwd_kernel(const bf16_t* __restrict__ Y, const float* __res
     if (j < H) {
         last = __bfloat162float(Y[((int64_t)(T - 1) * B + b) * ld + j]);
         if (D == 2) last += __bfloat162float(Y[(int64_t)b * ld + H + j]);
-#pragma unroll 16
+#pragma unroll 4
         for (int t = 0; t < T; ++t) {
             const bf16_t* y = Y + ((int64_t)t * B + b) * ld;
             float s = __bfloat162float(y[j]);

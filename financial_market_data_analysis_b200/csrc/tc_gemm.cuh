@@ -16,10 +16,13 @@
 
 namespace tcg {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;   // 3 x 32 KB: two CTAs per SM, so one tile's
+constexpr int BM = 128, BN = 128, BK = 64, MAX_STAGES = 4;   // 3 x 32 KB: two CTAs per SM, so one tile's
                                                               // epilogue overlaps the other's main loop
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
-constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+static inline int smem_bytes_for(int stages, int stage_out = 65536) {
+    const int ring = stages * (A_BYTES + B_BYTES);
+    return (ring < stage_out ? stage_out : ring) + 1024 /*align slack*/ + 256 /*barriers*/;
+}
 constexpr int THREADS = 192;
 
 enum { OUT_F32 = 0, OUT_BF16 = 1, OUT_ATOMIC_F32 = 2, OUT_SCAN_BF16 = 3, OUT_SCAN_F32 = 4 };
@@ -44,22 +47,28 @@ struct Params {
     int64_t zBias;
     int bias_per_row;
     ScanBlk blk;              // OUT_SCAN_* geometry
+    int stages;               // smem ring depth (1..4), chosen per problem: shallow rings let 3-4 CTAs share an SM
     int tma_store;            // 1: epilogue stages the tile in smem and writes it with TMA (store / reduce-add)
     unsigned int* dbg;        // watchdog record (nullable)
 };
 
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, 4)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC0, const __grid_constant__ CUtensorMap tmC1, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int STAGES = p.stages;
+    // the TMA-store epilogue needs up to 64 KB of staging (fp32 tile); with shallow rings it gets its own space
+    const int ring_bytes = STAGES * (A_BYTES + B_BYTES);
+    const int stage_out = p.tma_store ? (p.mode == OUT_BF16 ? 32768 : 65536) : 0;
+    const int data_bytes = ring_bytes < stage_out ? stage_out : ring_bytes;
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + data_bytes);
     uint64_t* full = bars;                 // [STAGES] TMA -> MMA
-    uint64_t* empty = bars + STAGES;       // [STAGES] MMA -> TMA
-    uint64_t* accum = bars + 2 * STAGES;   // MMA -> epilogue
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    uint64_t* empty = bars + 4;            // [STAGES] MMA -> TMA
+    uint64_t* accum = bars + 8;            // MMA -> epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int z = blockIdx.z / p.splitk, ks = blockIdx.z % p.splitk;
@@ -304,11 +313,17 @@ static inline int make_operand_map_mn(CUtensorMap* m, const void* base, uint64_t
 static inline cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p_in, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(MAX_STAGES));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     Params p = p_in;
+    {   // ring depth from the k-blocks one CTA walks: short reductions are latency-bound per tile, so trade ring depth
+        // for more co-resident CTAs (2 stages -> 3 CTAs/SM); long ones keep 3 stages (2 CTAs/SM)
+        const int kblocks = ((p.K + BK - 1) / BK + p.splitk - 1) / p.splitk;
+        p.stages = kblocks <= 2 ? kblocks : (kblocks <= 12 ? 2 : 3);
+        if (p.stages < 1) p.stages = 1;
+    }
     CUtensorMap tmC[2];
     memset(tmC, 0, sizeof(tmC));
     // TMA epilogue needs 16-byte aligned rows and base; otherwise the direct-store epilogue is used
@@ -321,7 +336,8 @@ static inline cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB,
     }
     p.tma_store = tma_ok ? 1 : 0;
     dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.batch * p.splitk);
-    gemm_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmB, tmC[0], tmC[1], p);
+    const int stage_out = p.tma_store ? (p.mode == OUT_BF16 ? 32768 : 65536) : 0;
+    gemm_kernel<<<grid, THREADS, smem_bytes_for(p.stages, stage_out), st>>>(tmA, tmB, tmC[0], tmC[1], p);
     return cudaGetLastError();
 }
 
