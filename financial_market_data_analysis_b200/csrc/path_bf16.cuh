@@ -326,7 +326,7 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
         // 3. input projection for all t, both directions, written in the scan kernel's blocked layout:  W_ih X^T + bias(row)
         tcg::Params g{};
         g.M = D * 3 * H; g.N = (int)R; g.K = I; g.batch = 1; g.splitk = 1; g.mode = tcg::OUT_SCAN_BF16;
-        g.blk = tcg::ScanBlk{T, B, H, 3};
+        g.blk = tcg::ScanBlk{T, B, H, 3}; g.m_fast = 1;      // the few weight m-tiles share each activation tile via L2
         g.C = W + L.gi; g.ldc = R; g.bias = (const float*)(S + L.bfold[l]); g.bias_per_row = 1; g.dbg = dbg;
         TRY(tc_gemm(S + L.Wih[l], D * 3 * H, I, Xrow, R, I, g, st));
         // 4. recurrence
@@ -424,7 +424,7 @@ static int backward_bf16(const bigru_plan& p, const float* params, const float* 
             tcg::Params g{};
             g.M = I; g.N = (int)R; g.K = D * 3 * H; g.batch = 1; g.splitk = 1;
             g.mode = l > 0 ? tcg::OUT_SCAN_F32 : tcg::OUT_F32;
-            g.blk = tcg::ScanBlk{T, B, H, 1};
+            g.blk = tcg::ScanBlk{T, B, H, 1}; g.m_fast = 1;
             g.C = dYnext; g.ldc = R; g.dbg = dbg;
             TRY(tc_gemm(S + L.WihT[l], I, (int64_t)D * 3 * H, W + L.gi, R, (int64_t)D * 3 * H, g, st, KC_TC_GEMM_DX));
             if (l > 0 && dropped)

@@ -47,6 +47,7 @@ struct Params {
     int64_t zBias;
     int bias_per_row;
     ScanBlk blk;              // OUT_SCAN_* geometry
+    int m_fast;               // rasterisation: 1 = consecutive CTAs walk m-tiles first (B tile shared through L2)
     int stages;               // smem ring depth (1..4), chosen per problem: shallow rings let 3-4 CTAs share an SM
     int tma_store;            // 1: epilogue stages the tile in smem and writes it with TMA (store / reduce-add)
     unsigned int* dbg;        // watchdog record (nullable)
@@ -60,7 +61,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int STAGES = p.stages;
     // the TMA-store epilogue needs up to 64 KB of staging (fp32 tile); with shallow rings it gets its own space
     const int ring_bytes = STAGES * (A_BYTES + B_BYTES);
-    const int stage_out = p.tma_store ? (p.mode == OUT_BF16 ? 32768 : 65536) : 0;
+    const int stage_out = p.tma_store ? ((p.mode == OUT_BF16 || p.mode == OUT_SCAN_BF16) ? 32768 : 65536) : 0;
     const int data_bytes = ring_bytes < stage_out ? stage_out : ring_bytes;
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
@@ -72,7 +73,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int z = blockIdx.z / p.splitk, ks = blockIdx.z % p.splitk;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int m0 = (p.m_fast ? blockIdx.x : blockIdx.y) * BM, n0 = (p.m_fast ? blockIdx.y : blockIdx.x) * BN;
     const int kblocks_total = (p.K + BK - 1) / BK;
     const int kb_per = (kblocks_total + p.splitk - 1) / p.splitk;
     const int kb0 = ks * kb_per;
@@ -137,7 +138,62 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc::tcgen05_fence_after();
         const float* bias = p.bias ? p.bias + z * p.zBias : nullptr;
         const float brow = (bias && p.bias_per_row && m < p.M) ? bias[m] : 0.f;
-        if (ok && p.tma_store) {
+        if (ok && p.mode >= OUT_SCAN_BF16 && p.tma_store) {
+            // ---- blocked ("scan-private") output through smem + 1-D bulk stores: for every 8-column run the 128 rows of
+            // this tile form one contiguous block [128 units][8] in the destination (see ScanBlk), staged at the same
+            // shape in smem (16-byte / 32-byte per thread: conflict-free) and written by cp.async.bulk.
+            const int ml = q * 32 + lane;
+            const bool bf = p.mode == OUT_SCAN_BF16;
+            const int run_bytes = bf ? 2048 : 4096;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                if (nkb > 0) { tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c * 32, v); tc::tmem_ld_wait(); }
+                else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0u;
+                }
+                const int nb = n0 + c * 32;
+#pragma unroll
+                for (int i8 = 0; i8 < 32; i8 += 8) {
+                    float f[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        f[j] = __uint_as_float(v[i8 + j]) + (bias ? (p.bias_per_row ? brow : ((nb + i8 + j < p.N) ? bias[nb + i8 + j] : 0.f)) : 0.f);
+                    uint8_t* dst = smem + (size_t)(c * 4 + (i8 >> 3)) * run_bytes;
+                    if (bf) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                            w[j] = *reinterpret_cast<uint32_t*>(&h2);
+                        }
+                        *reinterpret_cast<uint4*>(dst + ml * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                    } else {
+                        *reinterpret_cast<float4*>(dst + ml * 32) = make_float4(f[0], f[1], f[2], f[3]);
+                        *reinterpret_cast<float4*>(dst + ml * 32 + 16) = make_float4(f[4], f[5], f[6], f[7]);
+                    }
+                }
+            }
+            tc::fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp == 2 && tc::elect_one()) {
+                const int H = p.blk.H, G = p.blk.G, Bb = p.blk.B, Tt = p.blk.T;
+                const int dd = m0 / (G * H), gg = (m0 / H) % G, cc = (m0 % H) / 128;
+                const int CSs = H / 128, ntl = Bb / 16;
+                const size_t es = bf ? 2 : 4;
+                for (int r = 0; r < BN / 8; ++r) {
+                    const int n = n0 + r * 8;
+                    if (n >= p.N) break;
+                    const int t_ = n / Bb, b = n % Bb;
+                    const int tile_ = b >> 4, half = (b >> 3) & 1;
+                    const size_t e = ((((((size_t)dd * ntl + tile_) * Tt + t_) * CSs + cc) * G + gg) * 256 + (size_t)half * 128) * 8;
+                    tc::bulk_s2g(reinterpret_cast<uint8_t*>(p.C) + e * es, smem + (size_t)r * run_bytes, (uint32_t)run_bytes);
+                }
+                tc::tma_store_commit();
+                tc::tma_store_wait_all();
+            }
+        } else if (ok && p.tma_store) {
             // ---- staged epilogue: TMEM -> registers -> 128B-swizzled smem boxes -> TMA store / reduce-add.
             // The pipeline stages are free (every MMA has retired), so they serve as the staging buffer:
             // bf16: 2 boxes of [128 rows x 64 cols], fp32: 4 boxes of [128 rows x 32 cols], 16 KB each.
@@ -328,15 +384,18 @@ static inline cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB,
     memset(tmC, 0, sizeof(tmC));
     // TMA epilogue needs 16-byte aligned rows and base; otherwise the direct-store epilogue is used
     const size_t es = p.mode == OUT_BF16 ? 2 : 4;
-    bool tma_ok = p.mode < OUT_SCAN_BF16 && p.batch <= 2 && ((p.ldc * es) % 16 == 0) && ((p.zC * es) % 16 == 0) && ((uintptr_t)p.C % 16 == 0);
+    const bool scan_mode = p.mode >= OUT_SCAN_BF16;
+    bool tma_ok = !scan_mode && p.batch <= 2 && ((p.ldc * es) % 16 == 0) && ((p.zC * es) % 16 == 0) && ((uintptr_t)p.C % 16 == 0);
     if (tma_ok) {
         for (int z = 0; z < p.batch; ++z)
             if (make_output_map(&tmC[z], (uint8_t*)p.C + (size_t)z * p.zC * es, p.mode, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldc) != 0) tma_ok = false;
         if (p.batch == 1) tmC[1] = tmC[0];
     }
     p.tma_store = tma_ok ? 1 : 0;
+    if (scan_mode && p.M % BM == 0 && p.blk.B % 16 == 0 && ((uintptr_t)p.C % 16 == 0)) p.tma_store = 1;   // bulk-store epilogue
     dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.batch * p.splitk);
-    const int stage_out = p.tma_store ? (p.mode == OUT_BF16 ? 32768 : 65536) : 0;
+    if (p.m_fast) { const unsigned t = grid.x; grid.x = grid.y; grid.y = t; }
+    const int stage_out = p.tma_store ? ((p.mode == OUT_BF16 || p.mode == OUT_SCAN_BF16) ? 32768 : 65536) : 0;
     gemm_kernel<<<grid, THREADS, smem_bytes_for(p.stages, stage_out), st>>>(tmA, tmB, tmC[0], tmC[1], p);
     return cudaGetLastError();
 }
