@@ -190,25 +190,37 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
             for (int s = 1; s < T; ++s) {                  // after a watchdog hit: keep signalling, stop waiting
                 const int pb = (s - 1) & 1;
                 if (ok) ok = tc::mbar_wait(epi_done, (s - 1) & 1, p.dbg, 0x400 + (s & 0xff));
+                const uint32_t hb = tc::smem_u32(sH + (size_t)pb * KC * H_CHUNK);
+                // K chunks [2c, 2c+1] of h_{s-1} were produced by this CTA: their MMAs are issued right away and run
+                // while the peers' chunks are still in flight over DSMEM; the remaining chunks follow after h_full.
+                auto issue = [&](int kc_lo, int kc_hi, bool first_pass) {
+#pragma unroll 1
+                    for (int g = 0; g < 3; ++g) {
+                        const uint32_t ta = tmem + FWD_A_COL + (uint32_t)(g * (H / 2));     // gate g: H/2 columns per row
+#pragma unroll 1
+                        for (int kc = kc_lo; kc < kc_hi; ++kc) {
+                            const uint64_t db = tc::umma_desc_k_sw128(hb + (uint32_t)kc * H_CHUNK);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)       // K = 16 bf16 = 8 TMEM columns of A, 32 B of B
+                                umma_bf16_ts(tmem + g * NB, ta + (uint32_t)((kc * 4 + kk) * 8), db + 2 * kk, idesc,
+                                             (!first_pass || kc > kc_lo || kk) ? 1u : 0u);
+                        }
+                    }
+                };
+                const int my_lo = (int)c * (UNITS / 64), my_hi = my_lo + UNITS / 64;
+                tc::tcgen05_fence_after();
                 if (CS > 1) {
                     uint8_t* mine = sH + (size_t)pb * KC * H_CHUNK + (size_t)c * chunk_bytes_mine;
                     for (uint32_t peer = 0; peer < (uint32_t)CS; ++peer)
                         if (peer != c) tc::bulk_s2cluster(mine, mine, chunk_bytes_mine, &h_full[pb], peer);
+                    issue(my_lo, my_hi, true);
                     if (ok) ok = tc::mbar_wait(&h_full[pb], ((s - 1) >> 1) & 1, p.dbg, 0x500 + (s & 0xff));
                     if (s + 1 < T) tc::mbar_arrive_expect_tx(&h_full[s & 1], (uint32_t)(CS - 1) * chunk_bytes_mine);
-                }
-                tc::tcgen05_fence_after();
-                const uint32_t hb = tc::smem_u32(sH + (size_t)pb * KC * H_CHUNK);
-#pragma unroll 1
-                for (int g = 0; g < 3; ++g) {
-                    const uint32_t ta = tmem + FWD_A_COL + (uint32_t)(g * (H / 2));     // gate g: H/2 columns per row
-#pragma unroll 1
-                    for (int kc = 0; kc < KC; ++kc) {
-                        const uint64_t db = tc::umma_desc_k_sw128(hb + (uint32_t)kc * H_CHUNK);
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)       // K = 16 bf16 = 8 TMEM columns of A, 32 B of B
-                            umma_bf16_ts(tmem + g * NB, ta + (uint32_t)((kc * 4 + kk) * 8), db + 2 * kk, idesc, (kc | kk) ? 1u : 0u);
-                    }
+                    tc::tcgen05_fence_after();
+                    if (my_lo > 0) issue(0, my_lo, false);
+                    if (my_hi < KC) issue(my_hi, KC, false);
+                } else {
+                    issue(0, KC, true);
                 }
                 tc::umma_commit(mma_done);
             }
@@ -447,6 +459,24 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
                 const int pb = (s - 1) & 1;
                 uint8_t* tileb = sD + (size_t)pb * KC3 * H_CHUNK;
                 if (ok) ok = tc::mbar_wait(epi_done, (s - 1) & 1, p.dbg, 0x700 + (s & 0xff));
+                const uint32_t db0 = tc::smem_u32(tileb);
+                // K chunks of the three gates that this CTA produced itself go first (see forward kernel)
+                auto issue = [&](int u_lo, int u_hi, bool first_pass) {      // u = chunk index inside a gate, [0, KC)
+#pragma unroll 1
+                    for (int g = 0; g < 3; ++g) {
+#pragma unroll 1
+                        for (int u = u_lo; u < u_hi; ++u) {
+                            const int kc = g * KC + u;
+                            const uint64_t db = tc::umma_desc_k_sw128(db0 + (uint32_t)kc * H_CHUNK);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                umma_bf16_ts(tmem, tmem + BWD_A_COL + (uint32_t)((kc * 4 + kk) * 8), db + 2 * kk, idesc,
+                                             (!first_pass || g > 0 || u > u_lo || kk) ? 1u : 0u);
+                        }
+                    }
+                };
+                const int my_lo = (int)c * (UNITS / 64), my_hi = my_lo + UNITS / 64;
+                tc::tcgen05_fence_after();
                 if (CS > 1) {
                     for (uint32_t peer = 0; peer < (uint32_t)CS; ++peer) {
                         if (peer == c) continue;
@@ -455,17 +485,14 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
                             tc::bulk_s2cluster(mine, mine, gate_bytes_mine, &d_full[pb], peer);
                         }
                     }
+                    issue(my_lo, my_hi, true);
                     if (ok) ok = tc::mbar_wait(&d_full[pb], ((s - 1) >> 1) & 1, p.dbg, 0x800 + (s & 0xff));
                     if (s + 1 < T) tc::mbar_arrive_expect_tx(&d_full[s & 1], (uint32_t)(CS - 1) * 3 * gate_bytes_mine);
-                }
-                tc::tcgen05_fence_after();
-                const uint32_t db0 = tc::smem_u32(tileb);
-#pragma unroll 1
-                for (int kc = 0; kc < KC3; ++kc) {
-                    const uint64_t db = tc::umma_desc_k_sw128(db0 + (uint32_t)kc * H_CHUNK);
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        umma_bf16_ts(tmem, tmem + BWD_A_COL + (uint32_t)((kc * 4 + kk) * 8), db + 2 * kk, idesc, (kc | kk) ? 1u : 0u);
+                    tc::tcgen05_fence_after();
+                    if (my_lo > 0) issue(0, my_lo, false);
+                    if (my_hi < KC) issue(my_hi, KC, false);
+                } else {
+                    issue(0, KC, true);
                 }
                 tc::umma_commit(mma_done);
             }
