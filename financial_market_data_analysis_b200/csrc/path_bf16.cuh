@@ -183,7 +183,7 @@ __global__ void head_fwd_kernel(const bf16_t* __restrict__ Y, const float* __res
     if (j < H) {
         last = __bfloat162float(Y[((int64_t)(T - 1) * B + b) * ld + j]);
         if (D == 2) last += __bfloat162float(Y[(int64_t)b * ld + H + j]);
-#pragma unroll 4
+#pragma unroll 8
         for (int t = 0; t < T; ++t) {
             const bf16_t* y = Y + ((int64_t)t * B + b) * ld;
             float s = __bfloat162float(y[j]);
@@ -213,20 +213,23 @@ __global__ void head_fwd_kernel(const bf16_t* __restrict__ Y, const float* __res
         logits[(int64_t)b * C + j] = v;
     }
 }
-// d(lin_w)[c][k] = sum_b dlogits[b][c] cat[b][k];  d(lin_b)[c] = sum_b dlogits[b][c]
+// d(lin_w)[c][k] = sum_b dlogits[b][c] cat[b][k];  d(lin_b)[c] = sum_b dlogits[b][c]   (outputs pre-zeroed; the batch
+// is split over blockIdx.z and combined with atomics so that the tiny reduction is not one long serial loop)
 __global__ void head_bwd_w_kernel(const float* __restrict__ dlogits, const float* __restrict__ cat, float* __restrict__ dlin_w,
-                                  float* __restrict__ dlin_b, int B, int H3, int C) {
+                                  float* __restrict__ dlin_b, int B, int H3, int C, int bchunk) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int cc = blockIdx.y;
     if (k >= H3) return;
+    const int b0 = blockIdx.z * bchunk, b1 = min(B, b0 + bchunk);
     float acc = 0.f, accb = 0.f;
-    for (int b = 0; b < B; ++b) {
+#pragma unroll 4
+    for (int b = b0; b < b1; ++b) {
         const float g = dlogits[(int64_t)b * C + cc];
         acc = fmaf(g, cat[(int64_t)b * H3 + k], acc);
         accb += g;
     }
-    dlin_w[(int64_t)cc * H3 + k] = acc;
-    if (k == 0) dlin_b[cc] = accb;
+    atomicAdd(dlin_w + (int64_t)cc * H3 + k, acc);
+    if (k == 0) atomicAdd(dlin_b + cc, accb);
 }
 
 // dX^T of layer 0 (fp32 [F][R]) back to the caller's [B][T][F] (+ input-dropout mask); 32x32 smem transpose
@@ -367,8 +370,11 @@ static int backward_bf16(const bigru_plan& p, const float* params, const float* 
     unsigned int* dbg = (unsigned int*)(const_cast<uint8_t*>(S) + L.dbg);
     CUDA_TRY(cudaMemsetAsync(grads, 0, sizeof(float) * p.nparams, st));
     const float* cat = (const float*)(S + L.cat);
-    KLAUNCH(KC_HEAD, 0.0, 0.0, st, head_bwd_w_kernel<<<dim3(nblk2(3 * H, 128), C), 128, 0, st>>>(
-                dlogits, cat, grads + p.off_linw(), grads + p.off_linb(), B, 3 * H, C));
+    {
+        const int bchunk = 16;
+        KLAUNCH(KC_HEAD, 0.0, 0.0, st, head_bwd_w_kernel<<<dim3(nblk2(3 * H, 128), C, (B + bchunk - 1) / bchunk), 128, 0, st>>>(
+                    dlogits, cat, grads + p.off_linw(), grads + p.off_linb(), B, 3 * H, C, bchunk));
+    }
     float* dY = (float*)(W + L.dYa);
     float* dYnext = (float*)(W + L.dYb);
     for (int l = p.L - 1; l >= 0; --l) {

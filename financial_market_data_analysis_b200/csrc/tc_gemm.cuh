@@ -191,7 +191,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     tc::bulk_s2g(reinterpret_cast<uint8_t*>(p.C) + e * es, smem + (size_t)r * run_bytes, (uint32_t)run_bytes);
                 }
                 tc::tma_store_commit();
-                tc::tma_store_wait_all();
+                tc::tma_store_wait_read();     // smem may be released once it has been read; the writes complete on their own
             }
         } else if (ok && p.tma_store) {
             // ---- staged epilogue: TMEM -> registers -> 128B-swizzled smem boxes -> TMA store / reduce-add.
@@ -252,7 +252,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     else tc::tma_store_2d(tmC, smem + (size_t)b * 16384, n0 + b * bw, m0);
                 }
                 tc::tma_store_commit();
-                tc::tma_store_wait_all();
+                tc::tma_store_wait_read();     // smem may be released once it has been read; the writes complete on their own
             }
         } else if (ok) {
 #pragma unroll 1

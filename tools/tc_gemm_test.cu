@@ -40,7 +40,7 @@ static int run_case(int M, int N, int K, int mode, int splitk, int kshift, bool 
     CK(tcg::launch(tA, tB, p, 0));
     CK(cudaDeviceSynchronize());
     float ms = 0.f;
-    if (mode != tcg::OUT_ATOMIC_F32) {
+    if (mode != tcg::OUT_ATOMIC_F32 || M * (long)N * K > (1L << 34)) {
         cudaEventRecord(e0);
         for (int i = 0; i < 5; ++i) CK(tcg::launch(tA, tB, p, 0));
         cudaEventRecord(e1);
@@ -97,6 +97,10 @@ int main() {
     bad += run_case(768, 512, 8192, tcg::OUT_ATOMIC_F32, 16, 0, false, 768, 0, 1, 1);
     bad += run_case(768, 256, 8192, tcg::OUT_ATOMIC_F32, 16, -512, false, 0, 256, 1, 1);
     bad += run_case(768, 256, 65536, tcg::OUT_ATOMIC_F32, 37, 512, false, 0, 0, 1, 1);
+    bad += run_case(768, 512, 65536, tcg::OUT_ATOMIC_F32, 10, 0, false, 0, 0, 1, 1);
+    bad += run_case(768, 512, 65536, tcg::OUT_ATOMIC_F32, 10, 0, false, 0, 0, 0, 0);
+    bad += run_case(768, 512, 65536, tcg::OUT_ATOMIC_F32, 20, 0, false, 0, 0, 1, 1);
+    bad += run_case(512, 256, 65536, tcg::OUT_ATOMIC_F32, 37, 0, false, 0, 0, 1, 1);
     bad += run_case(65536, 1536, 64, tcg::OUT_BF16, 1, 0, true, 0, 0);
     bad += run_case(65536, 1536, 512, tcg::OUT_BF16, 1, 0, true, 0, 0);
     bad += run_case(65536, 512, 1536, tcg::OUT_F32, 1, 0, false, 0, 0);
