@@ -337,6 +337,13 @@ def main():
                 roofline = {"kernel": top["name"], "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                             "frac": ach / hbm_peak, "traffic": None, "peak_source": src,
                             "ms_per_step_in_kernel": top["ms"], "launches_per_step": top["launches"]}
+            try:        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch)
+                tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+                if tr.get("kernel") == top["name"]:
+                    roofline["traffic"] = tr["dram_bytes_per_launch"]
+                    roofline["traffic_source"] = tr["source"]
+            except Exception:
+                pass
             step_flops = flops_train_per_seq(T, F, H, L, C) * B
             roofline["step_model_tflops"] = step_flops / (ms_step * 1e-3) / 1e12
             roofline["step_frac_of_gemm_roofline"] = roofline["step_model_tflops"] / tf_peak
