@@ -115,14 +115,15 @@ struct FwdParams {
     const __nv_bfloat16* Wimg;
     const __nv_bfloat16* giB;
     const float* b_hn;            // [D][H]
-    __nv_bfloat16* Yrow;
+    __nv_bfloat16* Yrow;          // written by TMA tile stores straight from the h operand tile (tmY)
     __nv_bfloat16* G;
     __nv_bfloat16* YB;
     float* hn_out;                // [D][B][H] fp32, nullable
     unsigned int* dbg;
+    CUtensorMap tmY;              // Yrow as [R rows][D*H], box 64 x 16, 128B swizzle (filled by launch_fwd)
 };
 
-__global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int H = p.H, KC = H / 64, CS = H / UNITS, B = p.B, T = p.T, D = p.D;
@@ -187,6 +188,13 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
             constexpr uint32_t idesc = tc::umma_idesc_bf16(UNITS, NB);
             bool ok = true;
             if (CS > 1 && T > 1) tc::mbar_arrive_expect_tx(&h_full[0], (uint32_t)(CS - 1) * chunk_bytes_mine);
+            auto store_tile = [&](int step) {             // this CTA's 128 columns of Yrow for time step `step`
+                const int tt = d == 0 ? step : T - 1 - step;
+                const uint8_t* src = sH + (size_t)(step & 1) * KC * H_CHUNK + (size_t)c * chunk_bytes_mine;
+                for (int k = 0; k < UNITS / 64; ++k)
+                    tc::tma_store_2d(&p.tmY, src + (size_t)k * H_CHUNK, d * H + (int)c * UNITS + 64 * k, tt * B + tile * NB);
+                tc::tma_store_commit();
+            };
             for (int s = 1; s < T; ++s) {                  // after a watchdog hit: keep signalling, stop waiting
                 const int pb = (s - 1) & 1;
                 if (ok) ok = tc::mbar_wait(epi_done, (s - 1) & 1, p.dbg, 0x400 + (s & 0xff));
@@ -222,8 +230,14 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
                 } else {
                     issue(0, KC, true);
                 }
+                tc::tma_store_wait_read();                // the tile stored two steps ago is re-written after this commit
                 tc::umma_commit(mma_done);
+                // layer output rows of step s-1: TMA tile store straight from the operand tile (off the chain)
+                store_tile(s - 1);
             }
+            if (ok) ok = tc::mbar_wait(epi_done, (T - 1) & 1, p.dbg, 0x400);
+            store_tile(T - 1);
+            tc::tma_store_wait_all();
         }
     } else if (warp < EPI_WARPS) {
         // ---- epilogue: thread = hidden unit (TMEM lane), 8 of the 16 batch columns
@@ -233,14 +247,12 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
         const int col0 = half * 8;
         const int tid = threadIdx.x;
         const float bhn = p.b_hn[d * H + unit];
-        const int ldy = D * H;
         float hprev[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) hprev[i] = 0.f;
         bool ok = true;
         for (int s = 0; s < T; ++s) {
             const int t = d == 0 ? s : T - 1 - s;
-            const int64_t row0 = (int64_t)t * B + tile * NB + col0;
             const size_t blk = blk_index(d, tile, t, (int)c, ntiles, T, CS);
             // this step's gi from the prefetch ring
             float gr[8], gz[8], gn[8];
@@ -293,8 +305,6 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(epi_done);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) p.Yrow[(row0 + i) * ldy + d * H + unit] = hv[i];
             {
                 uint4* gs = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.G) + blk * G_BLOCK) + tid;
                 gs[0] = *reinterpret_cast<uint4*>(sr); gs[256] = *reinterpret_cast<uint4*>(sz);
@@ -313,7 +323,14 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const FwdParam
     if (warp == EPI_WARPS) tc::tmem_dealloc(tmem, fwd_tmem_cols(H));
 }
 
-static inline cudaError_t launch_fwd(const FwdParams& p, cudaStream_t st) {
+static inline cudaError_t launch_fwd(const FwdParams& p_in, cudaStream_t st) {
+    FwdParams p = p_in;
+    {
+        const uint64_t dims[2] = {(uint64_t)p.D * p.H, (uint64_t)p.T * p.B};
+        const uint64_t strides[1] = {(uint64_t)p.D * p.H * 2};
+        const uint32_t box[2] = {64u, (uint32_t)NB};
+        if (make_tmap_bf16(&p.tmY, p.Yrow, 2, dims, strides, box) != 0) return cudaErrorInvalidValue;
+    }
     const int CS = p.H / UNITS;
     const size_t smem = fwd_smem_bytes(p.H);
     static size_t attr = 0;
@@ -360,7 +377,7 @@ __global__ void pack_whh_image_kernel(const float* __restrict__ w_hh, __nv_bfloa
 // =================================================================================================
 static inline size_t bwd_smem_bytes(int H) {
     const int KC3 = 3 * H / 64;
-    return (size_t)2 * KC3 * H_CHUNK + (size_t)NSB * BWD_STAGE + (size_t)HEAD_CONST + 1024 + 256;
+    return (size_t)2 * KC3 * H_CHUNK + (size_t)2 * (UNITS / 64) * H_CHUNK + (size_t)NSB * BWD_STAGE + (size_t)HEAD_CONST + 1024 + 256;
 }
 constexpr uint32_t BWD_A_COL = 32;        // accumulator in columns [0, 16), W_hh^T from column 32
 __host__ __device__ static inline uint32_t bwd_tmem_cols(int H) { return 32 + 3 * H / 2 <= 256 ? 256u : 512u; }
@@ -377,20 +394,22 @@ struct BwdParams {
     const float* lin_w;             // [C][3H]
     const int* arg;                 // [B][H] argmax_t of the pooled output
     int C;
-    __nv_bfloat16* dgi_row;         // [R][D*3H]  (da_r, da_z, da_n)
-    __nv_bfloat16* dghn_row;        // [R][D*H]   da_n * r  (the n-gate column block of dgh)
+    __nv_bfloat16* dgi_row;         // [R][D*3H]  (da_r, da_z, da_n)      written by TMA tile stores (tmGI)
+    __nv_bfloat16* dghn_row;        // [R][D*H]   da_n * r  (the n-gate column block of dgh)   (tmGN)
+    CUtensorMap tmGI, tmGN;         // box 64 x 16, 128B swizzle (filled by launch_bwd)
     float* db_ih;                   // grads of b_ih for direction 0; direction d at + d*dir_stride
     float* db_hh;
     int64_t dir_stride;
     unsigned int* dbg;
 };
 
-__global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_constant__ BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int H = p.H, KC = H / 64, KC3 = 3 * KC, CS = H / UNITS, B = p.B, T = p.T, D = p.D;
     uint8_t* sD = smem;                                    // [2][KC3][H_CHUNK]  dgh operand tiles
-    uint8_t* sIn = sD + (size_t)2 * KC3 * H_CHUNK;         // [NSB][G | YB | dY]
+    uint8_t* sN = sD + (size_t)2 * KC3 * H_CHUNK;          // [2][UNITS/64][H_CHUNK]  da_n of this CTA's units (dgi n-gate, store only)
+    uint8_t* sIn = sN + (size_t)2 * (UNITS / 64) * H_CHUNK;   // [NSB][G | YB | dY]
     float* sHead = reinterpret_cast<float*>(sIn + (size_t)NSB * BWD_STAGE);    // [3][256][8]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + (size_t)NSB * BWD_STAGE + HEAD_CONST);
     uint64_t* d_full = bars;           // [2]  peers' dgh chunks landed
@@ -455,6 +474,21 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
             constexpr uint32_t idesc = tc::umma_idesc_bf16(UNITS, NB);
             bool ok = true;
             if (CS > 1 && T > 1) tc::mbar_arrive_expect_tx(&d_full[0], (uint32_t)(CS - 1) * 3 * gate_bytes_mine);
+            auto store_tile = [&](int step) {             // dgi / dgh_n rows of time step `step`, this CTA's 128 units
+                const int tt = d == 0 ? T - 1 - step : step;
+                const int row = tt * B + tile * NB;
+                const uint8_t* tb = sD + (size_t)(step & 1) * KC3 * H_CHUNK;
+                const uint8_t* nb = sN + (size_t)(step & 1) * (UNITS / 64) * H_CHUNK;
+                for (int k = 0; k < UNITS / 64; ++k) {
+                    const int cu = (int)c * UNITS + 64 * k;
+                    const size_t co = ((size_t)c * (UNITS / 64) + k) * H_CHUNK;
+                    tc::tma_store_2d(&p.tmGI, tb + (size_t)(0 * KC) * H_CHUNK + co, d * 3 * H + cu, row);            // da_r
+                    tc::tma_store_2d(&p.tmGI, tb + (size_t)(1 * KC) * H_CHUNK + co, d * 3 * H + H + cu, row);        // da_z
+                    tc::tma_store_2d(&p.tmGI, nb + (size_t)k * H_CHUNK, d * 3 * H + 2 * H + cu, row);                 // da_n
+                    tc::tma_store_2d(&p.tmGN, tb + (size_t)(2 * KC) * H_CHUNK + co, d * H + cu, row);                // da_n * r
+                }
+                tc::tma_store_commit();
+            };
             for (int s = 1; s < T; ++s) {
                 const int pb = (s - 1) & 1;
                 uint8_t* tileb = sD + (size_t)pb * KC3 * H_CHUNK;
@@ -494,8 +528,13 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
                 } else {
                     issue(0, KC, true);
                 }
+                tc::tma_store_wait_read();
                 tc::umma_commit(mma_done);
+                store_tile(s - 1);
             }
+            if (ok) ok = tc::mbar_wait(epi_done, (T - 1) & 1, p.dbg, 0x700);
+            store_tile(T - 1);
+            tc::tma_store_wait_all();
         }
     } else if (warp < EPI_WARPS) {
         const int q = warp & 3, half = warp >> 2;
@@ -503,7 +542,6 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
         const int unit = (int)c * UNITS + j;
         const int col0 = half * 8;
         const int tid = threadIdx.x;
-        const int ldi = D * 3 * H;
         float dhz[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) dhz[i] = 0.f;
@@ -602,18 +640,13 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
                 *reinterpret_cast<__nv_bfloat16*>(tileb + (size_t)(0 * KC + kc_u) * H_CHUNK + so) = tr[i];
                 *reinterpret_cast<__nv_bfloat16*>(tileb + (size_t)(1 * KC + kc_u) * H_CHUNK + so) = tz[i];
                 *reinterpret_cast<__nv_bfloat16*>(tileb + (size_t)(2 * KC + kc_u) * H_CHUNK + so) = tnr[i];
+                *reinterpret_cast<__nv_bfloat16*>(sN + (size_t)((s & 1) * (UNITS / 64) + ((unit & (UNITS - 1)) >> 6)) * H_CHUNK + so) = tn[i];
             }
             // hand dgh_s to the control thread (the step chain); HBM stores follow, off the chain
             tc::tcgen05_fence_before();
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(epi_done);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                __nv_bfloat16* gi_o = p.dgi_row + (row0 + i) * ldi + d * 3 * H + unit;
-                gi_o[0] = tr[i]; gi_o[H] = tz[i]; gi_o[2 * H] = tn[i];
-                p.dghn_row[(row0 + i) * (D * H) + d * H + unit] = tnr[i];
-            }
         }
         // bias gradients: sum the 8 columns of this thread; the two column halves and all tiles add atomically
         float* dbi = p.db_ih + (int64_t)d * p.dir_stride;
@@ -627,7 +660,17 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const BwdParam
     if (warp == EPI_WARPS) tc::tmem_dealloc(tmem, bwd_tmem_cols(H));
 }
 
-static inline cudaError_t launch_bwd(const BwdParams& p, cudaStream_t st) {
+static inline cudaError_t launch_bwd(const BwdParams& p_in, cudaStream_t st) {
+    BwdParams p = p_in;
+    {
+        const uint32_t box[2] = {64u, (uint32_t)NB};
+        const uint64_t d1[2] = {(uint64_t)p.D * 3 * p.H, (uint64_t)p.T * p.B};
+        const uint64_t s1[1] = {(uint64_t)p.D * 3 * p.H * 2};
+        const uint64_t d2[2] = {(uint64_t)p.D * p.H, (uint64_t)p.T * p.B};
+        const uint64_t s2[1] = {(uint64_t)p.D * p.H * 2};
+        if (make_tmap_bf16(&p.tmGI, p.dgi_row, 2, d1, s1, box) != 0 || make_tmap_bf16(&p.tmGN, p.dghn_row, 2, d2, s2, box) != 0)
+            return cudaErrorInvalidValue;
+    }
     const int CS = p.H / UNITS;
     const size_t smem = bwd_smem_bytes(p.H);
     static size_t attr = 0;
