@@ -350,6 +350,33 @@ def main():
             roofline["kernel_shares"] = [{"kernel": r["name"], "ms_per_step": round(r["ms"], 4), "launches": r["launches"]}
                                          for r in rows[:8]]
 
+    # ---- context only: the reference wrapper on torch's cuDNN GRU on this GPU (BASELINE config 2 comparator) ----
+    cudnn = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle.bigru_oracle import OracleBiGRU, train_step as oracle_step
+            torch.manual_seed(0)
+            ref = OracleBiGRU(H, F, C, L, 50, 0.0, False, True).cuda()
+            ropt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+            rloss = nn.CrossEntropyLoss()
+            xr, tr_ = resident[0]
+            for _ in range(3):
+                oracle_step(ref, ropt, rloss, xr, tr_)
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for i in range(5):
+                oracle_step(ref, ropt, rloss, *resident[i % NBUF])
+            c1.record()
+            torch.cuda.synchronize()
+            cms = c0.elapsed_time(c1) / 5
+            cudnn = {"value": B / (cms * 1e-3), "unit": "sequences/s", "ms_per_step": cms,
+                     "what": "reference wrapper restated on torch.nn.GRU CUDA (cuDNN, fp32/TF32 defaults), same step, same shapes; "
+                             "comparator only, not part of the product"}
+            del ref, ropt
+        except Exception as e:                              # the comparator must never break the bench line
+            cudnn = {"error": str(e)[:200]}
+
     # ---- reference CPU path on this box's host cores (rank 0, N=1) -----------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -361,7 +388,8 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
                 "config": workload_config(world, precision), "clocks": clocks, "e2e": e2e,
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "cudnn_comparator": cudnn}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

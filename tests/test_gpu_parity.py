@@ -429,3 +429,90 @@ def test_error_conventions():
         m(torch.zeros(2, 3, 4), torch.zeros(1, 2, 8))  # wrong hidden shape
     with pytest.raises(RuntimeError):
         pkg.BiGRU(8, 4, 2, 1)(torch.zeros(2, 3, 4))    # parameters on CPU: no CPU path
+
+
+def test_long_sequence_config_reduced():
+    """BASELINE config 4 (B256,T1024,F128,H512,L2) at reduced batch/length: H=512 runs on the fp32 path (the
+    tensor-core path covers H in {128, 256} and must refuse loudly); logits <= 1e-4 rel of the torch.nn.GRU CPU path."""
+    B, T, F, H, L, C = 16, 256, 128, 512, 2, 3
+    torch.manual_seed(0)
+    ref = bo.OracleBiGRU(H, F, C, L, 50, 0.0, False, True)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(B, T, F, generator=g)
+    ref.eval()
+    with torch.no_grad():
+        want = ref(x).numpy()
+    torch.manual_seed(0)
+    m = _pkg().BiGRU(H, F, C, L, 50, 0.0, False, True, precision="fp32").cuda()
+    m.eval()
+    with torch.no_grad():
+        got = m(x.cuda()).cpu().numpy()
+    assert rel(got, want) < 1e-4
+    if "bf16" in precisions():
+        mb = _pkg().BiGRU(H, F, C, L, 50, 0.0, False, True, precision="bf16").cuda()
+        with pytest.raises(ValueError, match="hidden_size 128 or 256"):
+            mb(x.cuda())
+
+
+def test_training_trajectories_agree():
+    """Ten fused optimisation steps: the tensor-core path follows the fp32 path's loss trajectory."""
+    if "bf16" not in precisions():
+        pytest.skip("tensor-core path not built")
+    B, T, F, H, L, C = 64, 24, 32, 128, 2, 3
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, T, F, generator=g).cuda()
+    t = torch.randint(0, C, (B,), generator=g).cuda()
+    traj = {}
+    for precision in ("fp32", "bf16"):
+        torch.manual_seed(1)
+        m = _pkg().BiGRU(H, F, C, L, 50, 0.0, False, True, precision=precision).cuda()
+        m.add_loss_fn(nn.CrossEntropyLoss())
+        m.add_optimizer(torch.optim.Adam(m.parameters(), lr=3e-3))
+        m.train()
+        traj[precision] = [float(m.train_step(x, t)[0]) for _ in range(10)]
+    a, b = np.array(traj["fp32"]), np.array(traj["bf16"])
+    assert a[-1] < a[0] * 0.8                       # it learns
+    assert np.abs(a - b).max() < 0.03 * a[0], (a, b)
+
+
+def test_two_gpu_data_parallel_step_matches_single_gpu(tmp_path):
+    """Batch data parallelism over NCCL: two ranks with half the batch each end up with the parameters of one
+    rank stepping on the whole batch (one all-reduce of the flat gradient, loss normalised by the global batch)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess, sys, textwrap
+    script = tmp_path / "dp.py"
+    script.write_text(textwrap.dedent('''
+        import os, sys, torch, torch.nn as nn, torch.distributed as dist
+        sys.path.insert(0, os.environ["REPO"])
+        import financial_market_data_analysis_b200 as pkg
+        from financial_market_data_analysis_b200.parallel import shard_batch
+        rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+        g = torch.Generator().manual_seed(3)
+        x = torch.randn(64, 12, 16, generator=g); t = torch.randint(0, 3, (64,), generator=g)
+        def run(dp):
+            torch.manual_seed(0)
+            m = pkg.BiGRU(128, 16, 3, 2, 1, 0.0, False, True, precision="fp32").cuda()
+            m.add_loss_fn(nn.CrossEntropyLoss()); m.add_optimizer(torch.optim.Adam(m.parameters(), lr=1e-2)); m.train()
+            if dp:
+                m.enable_data_parallel()
+                xs, ts = shard_batch(x, rank, world), shard_batch(t, rank, world)
+            else:
+                xs, ts = x, t
+            for _ in range(3):
+                loss, _ = m.train_step(xs.cuda(), ts.cuda())
+            return m.flat_parameters().clone(), float(loss)
+        pd, ld = run(True); ps, ls = run(False)
+        err = float((pd - ps).norm() / ps.norm())
+        if rank == 0: print("DPERR", err, ld, ls)
+        assert err < 1e-5 and abs(ld - ls) < 1e-5
+        dist.destroy_process_group()
+    '''))
+    env = dict(os.environ, REPO=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "DPERR" in out.stdout
