@@ -395,6 +395,85 @@ class BiGRU(nn.Module):
                    "bigru_clip_adam_step")
         return loss.clone(), logits
 
+    # ------------------------------------------------------------------ zero-copy windows
+    def _window_args(self, dataset, start, count):
+        if dataset.device != self._flat.device:
+            raise RuntimeError("dataset and model live on different devices")
+        if dataset.n_features != self.n_features:
+            raise ValueError(f"dataset has {dataset.n_features} features, the model expects {self.n_features}")
+        if count <= 0 or start < 0 or start + count + dataset.window - 1 > dataset.n_rows:
+            raise ValueError(f"windows [{start}, {start + count}) of width {dataset.window} exceed the {dataset.n_rows}-row chunk")
+
+    def forward_windows(self, dataset, start: int, count: int):
+        """Logits for windows start .. start+count-1 of a chunk-resident ``MySQLBatchLoader`` without materialising
+        x[count, window, F]: the first kernel of the path reads (and normalises) the rows of the chunk directly."""
+        if not self._is_flat():
+            self._flatten()
+        lib = _lib.load()
+        self._window_args(dataset, start, count)
+        plan = self._plan_for(torch.empty(count, dataset.window, 0, device=self._flat.device))     # keyed by (B, T)
+        logits = torch.empty(count, self.output_size, device=self._flat.device, dtype=torch.float32)
+        stash = plan.acquire_stash()
+        training = bool(self.training and self.dropout_p > 0)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
+        _lib.check(lib.bigru_forward_windows(plan.handle, _lib.ptr(self._flat), _lib.ptr(dataset.x_raw), _lib.ptr(dataset.x_min),
+                                             _lib.ptr(dataset.x_max), int(start), dataset.n_rows, float(self.dropout_p),
+                                             int(bool(self.spatial_dropout)), int(training), seed, _lib.ptr(stash),
+                                             _lib.ptr(plan.scratch), _lib.ptr(logits), None, _stream_ptr()),
+                   "bigru_forward_windows")
+        self._win_ctx = (plan, stash, training, seed)
+        return logits
+
+    def train_step_windows(self, dataset, start: int, count: int):
+        """``train_step`` on windows of a chunk-resident dataset (inputs and targets gathered on the device, the
+        fp32 batch never exists).  Returns (loss, logits)."""
+        spec, g = self._loss_spec(), self._adam_spec()
+        if spec is None or g is None:
+            raise RuntimeError("train_step_windows needs a fusable loss and torch.optim.Adam (see train_step)")
+        lib = _lib.load()
+        kind, w, pw = spec
+        logits = self.forward_windows(dataset, start, count)
+        plan, stash, training, seed = self._win_ctx
+        dev, B, C = logits.device, count, self.output_size
+        y = torch.empty(count, 1, dataset.n_targets, device=dev, dtype=torch.float32)
+        s = _stream_ptr()
+        _lib.check(lib.bigru_window_targets(_lib.ptr(dataset.y), int(start), dataset.n_rows, count, dataset.window,
+                                            dataset.n_targets, _lib.ptr(y), s), "bigru_window_targets")
+        if kind == _lib.LOSS_CE:
+            tgt = y.reshape(count, -1)[:, 0].to(torch.int64).contiguous()
+            denom = float(B * self._dp_world)
+        else:
+            tgt = y.reshape(count, C).contiguous()
+            denom = float(B * C * self._dp_world)
+        st = self._adam
+        if st is None:
+            st = self._adam = {"m": torch.zeros_like(self._flat), "v": torch.zeros_like(self._flat), "step": 0,
+                               "grad": torch.empty_like(self._flat),
+                               "scal": torch.zeros(2, device=dev, dtype=torch.float32)}
+        dlogits = torch.empty_like(logits)
+        loss, sq = st["scal"][0:1], st["scal"][1:2]
+        wv, pwv = self._loss_vec(w, C), self._loss_vec(pw, C)
+        _lib.check(lib.bigru_loss(kind, _lib.ptr(logits), _lib.ptr(tgt), _lib.ptr(wv), _lib.ptr(pwv), B, C, denom,
+                                  _lib.ptr(loss), _lib.ptr(dlogits), s), "bigru_loss")
+        _lib.check(lib.bigru_backward(plan.handle, _lib.ptr(self._flat), None, None, float(self.dropout_p),
+                                      int(bool(self.spatial_dropout)), int(training), seed, _lib.ptr(stash),
+                                      _lib.ptr(plan.scratch), _lib.ptr(dlogits), _lib.ptr(st["grad"]), None, None, s),
+                   "bigru_backward")
+        plan.release_stash(stash)
+        self._win_ctx = None
+        if self._dp_world > 1:
+            allreduce_flat_(st["grad"], self._dp_group)
+            allreduce_flat_(loss, self._dp_group)
+        sq.zero_()
+        _lib.check(lib.bigru_sqnorm(_lib.ptr(st["grad"]), st["grad"].numel(), _lib.ptr(sq), s), "bigru_sqnorm")
+        st["step"] += 1
+        b1, b2 = g["betas"]
+        _lib.check(lib.bigru_clip_adam_step(_lib.ptr(self._flat), _lib.ptr(st["grad"]), _lib.ptr(st["m"]),
+                                            _lib.ptr(st["v"]), self._flat.numel(), _lib.ptr(sq), float(self.clip),
+                                            float(g["lr"]), float(b1), float(b2), float(g["eps"]), st["step"], 1.0, s),
+                   "bigru_clip_adam_step")
+        return loss.clone(), logits
+
     def _generic_step(self, x, target):
         """Any loss / optimiser: autograd drives the same CUDA forward/backward kernels."""
         self.optimizer.zero_grad()

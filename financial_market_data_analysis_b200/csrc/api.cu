@@ -239,7 +239,7 @@ static int backward_f32(const bigru_plan& p, const float* params, const float* x
         if (dh0) CUDA_TRY(cudaMemcpyAsync(dh0 + (int64_t)l * D * B * H, dhc, sizeof(float) * D * B * H,
                                           cudaMemcpyDeviceToDevice, st));
         // layer input as seen by the projection (dropped copy when dropout was applied)
-        const float* inp = l == 0 ? x : stash + S.Y[l - 1];
+        const float* inp = l == 0 ? (x ? x : stash + S.X[0]) : stash + S.Y[l - 1];     // x == NULL: forward_windows left it in the stash
         if (do_drop && (l == 0 || p.L > 1)) inp = stash + S.X[l];
         const int splitk = (int)min((int64_t)64, max((int64_t)1, BT / 512));
         for (int d = 0; d < D; ++d) {
@@ -309,7 +309,7 @@ extern "C" int bigru_backward(const bigru_plan* plan, const float* d_params, con
                               float dropout_p, int spatial, int training, uint64_t seed, const void* d_stash,
                               void* d_scratch, const float* d_dlogits, float* d_grads, float* d_dx, float* d_dh0,
                               void* stream) {
-    if (!plan || !d_params || !d_x || !d_stash || !d_scratch || !d_dlogits || !d_grads) {
+    if (!plan || !d_params || !d_stash || !d_scratch || !d_dlogits || !d_grads) {
         bigru_set_error("backward: null argument");
         return BIGRU_ERR_ARG;
     }
@@ -319,6 +319,42 @@ extern "C" int bigru_backward(const bigru_plan* plan, const float* d_params, con
                              d_dlogits, d_grads, d_dx, d_dh0, st);
     return backward_f32(*plan, d_params, d_x, d_h0, dropout_p, spatial, training, seed, (const float*)d_stash,
                         (float*)d_scratch, d_dlogits, d_grads, d_dx, d_dh0, st);
+}
+
+extern "C" int bigru_forward_windows(const bigru_plan* plan, const float* d_params, const float* d_src, const float* d_xmin,
+                                     const float* d_xmax, int64_t start, int64_t N, float dropout_p, int spatial,
+                                     int training, uint64_t seed, void* d_stash, void* d_scratch, float* d_logits,
+                                     float* d_hn, void* stream) {
+    if (!plan || !d_params || !d_src || !d_stash || !d_scratch || !d_logits || ((d_xmin == nullptr) != (d_xmax == nullptr))) {
+        bigru_set_error("forward_windows: null argument");
+        return BIGRU_ERR_ARG;
+    }
+    if (start < 0 || start + plan->B + plan->T - 1 > N) {
+        bigru_set_error("forward_windows: windows [%lld, %lld) exceed the %lld-row chunk", (long long)start,
+                        (long long)(start + plan->B + plan->T - 1), (long long)N);
+        return BIGRU_ERR_ARG;
+    }
+    if (dropout_p < 0.f || dropout_p >= 1.f) { bigru_set_error("forward_windows: dropout_p must be in [0,1)"); return BIGRU_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plan->prec == BIGRU_PREC_BF16)
+        return forward_bf16(*plan, d_params, nullptr, nullptr, dropout_p, spatial, training, seed, d_stash, d_scratch,
+                            d_logits, d_hn, st, WindowSrc{d_src, d_xmin, d_xmax, start});
+    // fp32 path: collate into the stash slot of the layer-0 input, then the ordinary forward
+    float* xw = (float*)d_stash + stash_layout(*plan).X[0];
+    TRY(bigru_window_gather_norm(d_src, d_xmin, d_xmax, start, N, plan->B, plan->T, plan->F, xw, stream));
+    return forward_f32(*plan, d_params, xw, nullptr, dropout_p, spatial, training, seed, (float*)d_stash,
+                       (float*)d_scratch, d_logits, d_hn, st);
+}
+
+extern "C" int bigru_chunk_minmax(const float* d_table, int64_t N, int F, int64_t row_lo, int64_t row_hi, float* d_min,
+                                  float* d_max, void* stream) {
+    if (!d_table || !d_min || !d_max || F <= 0 || row_lo < 0 || row_hi > N || row_lo >= row_hi) {
+        bigru_set_error("chunk_minmax: bad argument");
+        return BIGRU_ERR_ARG;
+    }
+    KLAUNCH(KC_GATHER, 0.0, 4.0 * (row_hi - row_lo) * F, (cudaStream_t)stream,
+            chunk_minmax_kernel<<<(F + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(d_table, F, row_lo, row_hi, d_min, d_max));
+    return BIGRU_OK;
 }
 
 extern "C" int bigru_loss(int kind, const float* d_logits, const void* d_target, const float* d_weight,

@@ -421,6 +421,25 @@ __global__ void multilabel_counts_kernel(const float* __restrict__ logits, const
     if (mism) atomicAdd(counts + 1, (unsigned long long)mism);
 }
 
+// per-feature min / max over table rows [lo, hi); NaN (SQL NULL) ignored.  One block = 32 features x 8 row lanes.
+__global__ void chunk_minmax_kernel(const float* __restrict__ tab, int F, int64_t lo, int64_t hi, float* __restrict__ mn,
+                                    float* __restrict__ mx) {
+    __shared__ float smn[8][33], smx[8][33];
+    const int f = blockIdx.x * 32 + threadIdx.x;
+    float a = INFINITY, b = -INFINITY;
+    if (f < F)
+        for (int64_t r = lo + threadIdx.y; r < hi; r += 8) {
+            const float v = tab[r * F + f];
+            a = fminf(a, v); b = fmaxf(b, v);            // fminf/fmaxf return the non-NaN operand
+        }
+    smn[threadIdx.y][threadIdx.x] = a; smx[threadIdx.y][threadIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.y == 0 && f < F) {
+        for (int i = 1; i < 8; ++i) { a = fminf(a, smn[i][threadIdx.x]); b = fmaxf(b, smx[i][threadIdx.x]); }
+        mn[f] = a; mx[f] = b;
+    }
+}
+
 __global__ void fill_kernel(float* __restrict__ p, int64_t n, float v) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }

@@ -70,16 +70,22 @@ static void bf16_workspace(const bigru_plan& p, size_t* a, size_t* b) {
 // ---------------------------------------------------------------------------------------------------
 // small kernels of this path
 // ---------------------------------------------------------------------------------------------------
-// x fp32 [B][T][F] -> Xrow bf16 [(t*B+b)][F] (time-major rows), optional input dropout.
-__global__ void cast_x_kernel(const float* __restrict__ x, bf16_t* __restrict__ Xrow, int B, int T, int F, float pdrop,
-                              int spatial, uint64_t seed) {
+// x fp32 [B][T][F] -> Xrow bf16 [(t*B+b)][F] (time-major rows), optional input dropout.  With `src` set the batch is
+// read straight from the chunk table: x[b,t,f] = (src[start+b+t, f] - xmin[f]) / (xmax[f] - xmin[f])  (zero-copy windows).
+struct WindowSrc { const float* src; const float* xmin; const float* xmax; int64_t start; };
+__global__ void cast_x_kernel(const float* __restrict__ x, WindowSrc w, bf16_t* __restrict__ Xrow, int B, int T, int F,
+                              float pdrop, int spatial, uint64_t seed) {
     const float scale = pdrop > 0.f ? 1.f / (1.f - pdrop) : 1.f;
     const int64_t total = (int64_t)B * T * F;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int f = i % F;
         const int64_t r = i / F;                 // output row t*B + b
         const int64_t b = r % B, t = r / B;
-        float v = x[(b * T + t) * F + f];
+        float v;
+        if (w.src) {
+            v = w.src[(w.start + b + t) * F + f];
+            if (w.xmin) v = (v - w.xmin[f]) / (w.xmax[f] - w.xmin[f]);
+        } else v = x[(b * T + t) * F + f];
         if (pdrop > 0.f) {
             const uint64_t key = spatial ? (uint64_t)b * F + f : ((uint64_t)b * T + t) * F + f;
             v = bigru_uniform(seed, 0u, key) < pdrop ? 0.f : v * scale;
@@ -285,7 +291,7 @@ static inline unsigned nblk2(int64_t n, int bs) { return (unsigned)cdiv64(n, bs)
 // ---------------------------------------------------------------------------------------------------
 static int forward_bf16(const bigru_plan& p, const float* params, const float* x, const float* h0, float drop,
                         int spatial, int training, uint64_t seed, void* stash_v, void* scratch_v, float* logits,
-                        float* hn, cudaStream_t st) {
+                        float* hn, cudaStream_t st, WindowSrc win = WindowSrc{nullptr, nullptr, nullptr, 0}) {
     if (h0) { bigru_set_error("BIGRU_PREC_BF16: an initial hidden state is not supported; use BIGRU_PREC_FP32"); return BIGRU_ERR_UNSUPPORTED; }
     const Bf16Layout L = bf16_layout(p);
     uint8_t* S = (uint8_t*)stash_v;
@@ -312,7 +318,7 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
         KLAUNCH(KC_PACK, 0.0, 0.0, st, pack_all_kernel<<<dim3(64, nj), 256, 0, st>>>(jobs, H, D));
     }
     // 2. layer-0 input: cast to bf16, time-major rows (+ input dropout)
-    KLAUNCH(KC_PACK, 0.0, 6.0 * R * F, st, cast_x_kernel<<<148 * 8, 256, 0, st>>>(x, (bf16_t*)(S + L.Xrow[0]), B, T, F,
+    KLAUNCH(KC_PACK, 0.0, 6.0 * R * F, st, cast_x_kernel<<<148 * 8, 256, 0, st>>>(x, win, (bf16_t*)(S + L.Xrow[0]), B, T, F,
                                                                                    do_drop ? drop : 0.f, spatial, seed));
     for (int l = 0; l < p.L; ++l) {
         const int I = (int)p.in_size(l);

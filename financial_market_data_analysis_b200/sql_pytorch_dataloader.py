@@ -113,6 +113,39 @@ class MySQLChunkLoader(Dataset):
     def __len__(self):
         return self.num_chunks + 1
 
+    @classmethod
+    def from_table(cls, table: torch.Tensor, x_fields, chunk_size, window, norm_params_path="norm_params"):
+        """Same object, built from a bulk-loaded feature table resident in HBM instead of 2 SQL aggregates per chunk
+        (SURVEY.md 8(f) N3): ``table[i]`` is the row with database ID ``i + 1``, NaN = SQL NULL.  Per-chunk MIN/MAX come
+        from one reduction kernel (``bigru_chunk_minmax``); the min==max guard, order-book sharing and the
+        ``norm_params`` pickle are the reference's host rules, unchanged."""
+        if not table.is_cuda:
+            raise RuntimeError("from_table needs the table on a CUDA device (no CPU fallback)")
+        self = cls.__new__(cls)
+        table = table.to(torch.float32).contiguous()
+        db_length, F = table.shape
+        self.num_chunks = db_length // chunk_size
+        self.chunk_indices = chunk_id_ranges(db_length, chunk_size, window)
+        self.x_fields = list(x_fields)
+        self.norm_params = []
+        lib = _lib.load()
+        mn = torch.empty(F, device=table.device, dtype=torch.float32)
+        mx = torch.empty(F, device=table.device, dtype=torch.float32)
+        for ids in self.chunk_indices:
+            _lib.check(lib.bigru_chunk_minmax(_lib.ptr(table), db_length, F, ids[0] - 1, ids[-1], _lib.ptr(mn), _lib.ptr(mx),
+                                              torch.cuda.current_stream(table.device).cuda_stream), "bigru_chunk_minmax")
+            x_min, x_max = mn.cpu().reshape(1, F).clone(), mx.cpu().reshape(1, F).clone()
+            x_min[0], x_max[0] = widen_degenerate(x_min[0], x_max[0])
+            self.norm_params.append((x_min, x_max))
+        for x_min, x_max in self.norm_params:
+            share_book_levels(self.x_fields, x_min, x_max)
+        if norm_params_path:
+            last_min, last_max = self.norm_params[-1]
+            table_ = {name: {"MIN": last_min[0][i], "MAX": last_max[0][i]} for i, name in enumerate(self.x_fields)}
+            with open(norm_params_path, "wb") as fh:
+                pickle.dump(table_, fh)
+        return self
+
 
 def delivered_window_batches(n_rows: int, window: int, batch_size: int):
     """(start, count) of every batch a ``DataLoader(dataset, batch_size)`` over the reference dataset

@@ -72,7 +72,8 @@ int  bigru_forward(const bigru_plan* plan, const float* d_params, const float* d
                    void* d_stash, void* d_scratch, float* d_logits, float* d_hn, void* stream);
 
 /* --- loss.backward() through the model (biGRU_model.py:204): every parameter gradient into
- *  d_grads (flat, overwritten), optional d_dx[B,T,F] and d_dh0[L*D,B,H].  Must follow
+ *  d_grads (flat, overwritten), optional d_dx[B,T,F] and d_dh0[L*D,B,H].  d_x may be NULL after
+ *  bigru_forward_windows (the input is then taken from the stash).  Must follow
  *  bigru_forward on the same plan/stash with the same dropout arguments. */
 int  bigru_backward(const bigru_plan* plan, const float* d_params, const float* d_x, const float* d_h0,
                     float dropout_p, int spatial, int training, uint64_t seed,
@@ -103,6 +104,20 @@ int  bigru_window_gather_norm(const float* d_src, const float* d_xmin, const flo
                               int64_t start, int64_t N, int B, int T, int F, float* d_out, void* stream);
 int  bigru_window_targets(const float* d_y, int64_t start, int64_t N, int B, int T, int C,
                           float* d_out, void* stream);
+
+/* --- SURVEY.md 8(f) N1, zero-copy windows: forward straight from the HBM-resident chunk src[N,F] - the batch
+ *  x[b,t,:] = (src[start+b+t,:] - xmin) / (xmax - xmin) is formed inside the first kernel of the path and never
+ *  materialised as fp32 [B,T,F] by the caller (sql_pytorch_dataloader.py:239-245 + biGRU_model.py:63).  Pair it with
+ *  bigru_backward(..., d_x = NULL, ...): the backward then takes the layer-0 input from the stash. */
+int  bigru_forward_windows(const bigru_plan* plan, const float* d_params, const float* d_src, const float* d_xmin,
+                           const float* d_xmax, int64_t start, int64_t N, float dropout_p, int spatial, int training,
+                           uint64_t seed, void* d_stash, void* d_scratch, float* d_logits, float* d_hn, void* stream);
+
+/* --- SURVEY.md 8(f) N3, chunk statistics on the GPU: per-feature MIN / MAX over rows [row_lo, row_hi) of a
+ *  table[N,F] (NaN = SQL NULL, ignored), i.e. the two aggregate queries of MySQLChunkLoader
+ *  (sql_pytorch_dataloader.py:96-105).  The min==max guard and order-book sharing stay on the host. */
+int  bigru_chunk_minmax(const float* d_table, int64_t N, int F, int64_t row_lo, int64_t row_hi, float* d_min,
+                        float* d_max, void* stream);
 
 /* --- train_model/evaluate_model metrics (biGRU_model.py:213-221): pred = sigmoid(logit) > 0.5;
  *  d_counts[0] += #rows with all labels right; [1] += #label mismatches;

@@ -516,3 +516,60 @@ def test_two_gpu_data_parallel_step_matches_single_gpu(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "DPERR" in out.stdout
+
+
+def test_zero_copy_windows_match_collated_batches():
+    """forward / train step straight from the chunk equal collate-then-forward (same arithmetic,
+    so the fp32 path is bit-exact on the logits)."""
+    cols, targets, fields, query = fake_db.make_table(n_rows=200, with_nulls=False, n_plain=2, levels=2)
+    cur = fake_db.FakeCursor(cols, targets)
+    pkg = _pkg()
+    cl = pkg.MySQLChunkLoader(cur, "stock_data_joined", query, 200, 12, norm_params_path=None)
+    ids, norm = cl[0]
+    F = len(fields)
+    for precision in precisions():
+        H = 32 if precision == "fp32" else 128
+        if not supported(precision, 32, F, H):
+            continue
+        ds = pkg.MySQLBatchLoader(ids, norm, cur, "stock_data_joined", query, "t0, t1, t2, t3", 12)
+        torch.manual_seed(0)
+        m = pkg.BiGRU(H, F, 4, 2, 50, 0.0, False, True, precision=precision).cuda()
+        m.eval()
+        x, y = ds.collate(5, 32)
+        with torch.no_grad():
+            want = m(x)
+        got = m.forward_windows(ds, 5, 32)
+        if precision == "fp32":
+            assert torch.equal(got, want)
+        else:
+            assert rel(got.cpu().numpy(), want.cpu().numpy()) < 1e-6
+        # training step: same parameters afterwards
+        outs = []
+        for mode in ("collated", "windows"):
+            torch.manual_seed(0)
+            mm = pkg.BiGRU(H, F, 4, 2, 1, 0.0, False, True, precision=precision).cuda()
+            mm.add_loss_fn(nn.BCEWithLogitsLoss()); mm.add_optimizer(torch.optim.Adam(mm.parameters(), lr=1e-2)); mm.train()
+            if mode == "collated":
+                mm.train_step(x, y.squeeze(1))
+            else:
+                mm.train_step_windows(ds, 5, 32)
+            outs.append(mm.flat_parameters().clone())
+        assert rel_l2(outs[1].cpu().numpy(), outs[0].cpu().numpy()) < (1e-6 if precision == "fp32" else 1e-3)
+    with pytest.raises(ValueError):
+        m.forward_windows(ds, 170, 32)
+
+
+def test_chunk_statistics_on_gpu_match_sql_path(golden_dir, tmp_path):
+    """per-chunk MIN/MAX from the reduction kernel + host guard / order-book rules equal what the
+    unmodified reference computed through SQL aggregates (tests/golden/loader.npz)."""
+    z = np.load(os.path.join(golden_dir, "loader.npz"))
+    cols, targets, fields, query = fake_db.make_table(n_rows=250)
+    import financial_market_data_analysis_b200.sql_pytorch_dataloader as L
+    L.bid_levels, L.ask_levels = 2, 2
+    table = torch.tensor(np.stack([cols[f] for f in fields], 1), dtype=torch.float32).cuda()      # NaN = NULL
+    cl = L.MySQLChunkLoader.from_table(table, fields, 100, 30, norm_params_path=str(tmp_path / "norm_params"))
+    assert len(cl) == int(z["n_chunks"])
+    for i in range(len(cl)):
+        ids, (mn, mx) = cl[i]
+        assert np.array_equal(np.array(ids), z[f"chunk{i}_ids"])
+        assert np.array_equal(mn.numpy(), z[f"chunk{i}_min"]) and np.array_equal(mx.numpy(), z[f"chunk{i}_max"])
