@@ -76,21 +76,31 @@ struct WindowSrc { const float* src; const float* xmin; const float* xmax; int64
 __global__ void cast_x_kernel(const float* __restrict__ x, WindowSrc w, bf16_t* __restrict__ Xrow, int B, int T, int F,
                               float pdrop, int spatial, uint64_t seed) {
     const float scale = pdrop > 0.f ? 1.f / (1.f - pdrop) : 1.f;
-    const int64_t total = (int64_t)B * T * F;
+    const int F4 = F >> 2;                          // F % 8 == 0 on the tensor-core path
+    const int64_t total = (int64_t)B * T * F4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int f = i % F;
-        const int64_t r = i / F;                 // output row t*B + b
+        const int f = (int)(i % F4) * 4;
+        const int64_t r = i / F4;                // output row t*B + b
         const int64_t b = r % B, t = r / B;
-        float v;
+        float4 v;
         if (w.src) {
-            v = w.src[(w.start + b + t) * F + f];
-            if (w.xmin) v = (v - w.xmin[f]) / (w.xmax[f] - w.xmin[f]);
-        } else v = x[(b * T + t) * F + f];
+            v = *reinterpret_cast<const float4*>(w.src + (w.start + b + t) * F + f);
+            if (w.xmin) {
+                const float4 mn = *reinterpret_cast<const float4*>(w.xmin + f), mx = *reinterpret_cast<const float4*>(w.xmax + f);
+                v.x = (v.x - mn.x) / (mx.x - mn.x); v.y = (v.y - mn.y) / (mx.y - mn.y);
+                v.z = (v.z - mn.z) / (mx.z - mn.z); v.w = (v.w - mn.w) / (mx.w - mn.w);
+            }
+        } else v = *reinterpret_cast<const float4*>(x + (b * T + t) * F + f);
         if (pdrop > 0.f) {
-            const uint64_t key = spatial ? (uint64_t)b * F + f : ((uint64_t)b * T + t) * F + f;
-            v = bigru_uniform(seed, 0u, key) < pdrop ? 0.f : v * scale;
+            float* e = &v.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint64_t key = spatial ? (uint64_t)b * F + f + k : ((uint64_t)b * T + t) * F + f + k;
+                e[k] = bigru_uniform(seed, 0u, key) < pdrop ? 0.f : e[k] * scale;
+            }
         }
-        Xrow[i] = __float2bfloat16(v);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        *reinterpret_cast<uint2*>(Xrow + r * F + f) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
     }
 }
 
@@ -406,7 +416,7 @@ static int backward_bf16(const bigru_plan& p, const float* params, const float* 
             tcg::Params g{};
             g.M = 3 * H; g.N = I; g.K = (int)R; g.batch = D; g.mode = tcg::OUT_ATOMIC_F32; g.a_mn = 1; g.b_mn = 1;
             const int tiles = ((3 * H + 127) / 128) * ((I + 127) / 128) * D;
-            g.splitk = (int)std::max<int64_t>(1, std::min<int64_t>((R + 63) / 64, (148 * 3 + tiles - 1) / tiles));
+            g.splitk = (int)std::max<int64_t>(1, std::min<int64_t>((R + 63) / 64, (148 * 2 + tiles / 2) / tiles));    // one full wave at 2 CTAs/SM
             g.C = grads + p.off_wih(l, 0); g.ldc = I; g.zC = p.ld_block(l);
             for (int d = 0; d < D; ++d) { g.a_row_off[d] = d * 3 * H; g.b_row_off[d] = 0; g.b_k_off[d] = 0; }
             g.dbg = dbg;
@@ -419,7 +429,7 @@ static int backward_bf16(const bigru_plan& p, const float* params, const float* 
             tcg::Params g{};
             g.M = part == 0 ? 2 * H : H; g.N = H; g.K = (int)R; g.batch = D; g.mode = tcg::OUT_ATOMIC_F32; g.a_mn = 1; g.b_mn = 1;
             const int tiles = ((g.M + 127) / 128) * ((H + 127) / 128) * D;
-            g.splitk = (int)std::max<int64_t>(1, std::min<int64_t>((R + 63) / 64, (148 * 2 + tiles - 1) / tiles));
+            g.splitk = (int)std::max<int64_t>(1, std::min<int64_t>((R + 63) / 64, (148 * 2 + tiles / 2) / tiles));
             g.C = grads + p.off_whh(l, 0) + (part == 0 ? 0 : (int64_t)2 * H * H); g.ldc = H; g.zC = p.ld_block(l);
             for (int d = 0; d < D; ++d) {
                 g.a_row_off[d] = part == 0 ? d * 3 * H : d * H;

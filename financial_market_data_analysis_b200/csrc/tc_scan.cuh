@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_c
 #pragma unroll 1
                     for (int g = 0; g < 3; ++g) {
                         const uint32_t ta = tmem + FWD_A_COL + (uint32_t)(g * (H / 2));     // gate g: H/2 columns per row
-#pragma unroll 1
+#pragma unroll 2
                         for (int kc = kc_lo; kc < kc_hi; ++kc) {
                             const uint64_t db = tc::umma_desc_k_sw128(hb + (uint32_t)kc * H_CHUNK);
 #pragma unroll
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
                 auto issue = [&](int u_lo, int u_hi, bool first_pass) {      // u = chunk index inside a gate, [0, KC)
 #pragma unroll 1
                     for (int g = 0; g < 3; ++g) {
-#pragma unroll 1
+#pragma unroll 2
                         for (int u = u_lo; u < u_hi; ++u) {
                             const int kc = g * KC + u;
                             const uint64_t db = tc::umma_desc_k_sw128(db0 + (uint32_t)kc * H_CHUNK);
