@@ -110,6 +110,18 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
     return r;
 }
 
+// 16-byte store into the shared memory of another CTA of the cluster (address from mapa)
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, const uint4& v) {
+    asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// asynchronous 16-byte store into another CTA's shared memory; completes `16` tx bytes on THAT CTA's mbarrier
+// (both addresses are shared::cluster addresses from mapa)
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, const uint4& v, uint32_t cluster_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cluster_mbar) : "memory");
+}
+
 // ---- TMA ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -28,6 +28,12 @@
 
 namespace tcs {
 
+#ifdef BIGRU_SCAN_TIMING
+#define SCAN_TS(slot) do { if (blockIdx.x == 0 && s >= 64 && s < 72) p.ts[(s - 64) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define SCAN_TS(slot) do { } while (0)
+#endif
+
 constexpr int NB = 16;            // batch rows per tile = UMMA N
 constexpr int UNITS = 128;        // hidden units per CTA = UMMA M
 constexpr int EPI_WARPS = 8;
@@ -121,21 +127,44 @@ struct FwdParams {
     float* hn_out;                // [D][B][H] fp32, nullable
     unsigned int* dbg;
     CUtensorMap tmY;              // Yrow as [R rows][D*H], box 64 x 16, 128B swizzle (filled by launch_fwd)
+#ifdef BIGRU_SCAN_TIMING
+    unsigned long long* ts;       // bring-up only: clock64 stamps of CTA 0, steps [64, 72), 16 slots per step
+#endif
 };
 
+// One group of K chunks (NCH x 64 columns of h) of all three gates, fully unrolled: every operand address is a base
+// that is fixed for the step plus a compile-time constant, so the 12*NCH tcgen05.mma issue back to back (~9 cycles
+// each; a rolled loop with run-time descriptors costs ~26).
+template <int H, int NCH, bool FIRST>
+__device__ __forceinline__ void fwd_issue_group(uint32_t tmem_d, uint32_t tmem_a_grp, uint64_t desc_grp) {
+    constexpr uint32_t idesc = tc::umma_idesc_bf16(UNITS, NB);
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+#pragma unroll
+        for (int u = 0; u < NCH; ++u) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)       // K = 16 bf16 = 8 TMEM columns of A, 32 B of B
+                umma_bf16_ts(tmem_d + (uint32_t)(g * NB), tmem_a_grp + (uint32_t)(g * (H / 2) + (u * 4 + kk) * 8),
+                             desc_grp + (uint64_t)(u * (H_CHUNK >> 4) + 2 * kk), idesc, (FIRST && u == 0 && kk == 0) ? 0u : 1u);
+        }
+    }
+}
+
+template <int H>
 __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int H = p.H, KC = H / 64, CS = H / UNITS, B = p.B, T = p.T, D = p.D;
+    constexpr int KC = H / 64, CS = H / UNITS, MYCH = UNITS / 64;
+    const int B = p.B, T = p.T, D = p.D;
     uint8_t* sH = smem;                                    // [2][KC][H_CHUNK]  h operand tiles
     uint8_t* sIn = sH + (size_t)2 * KC * H_CHUNK;          // [NSF][GI_BLOCK]   prefetched gi blocks
     uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + (size_t)NSF * GI_BLOCK);
-    uint64_t* h_full = bars;           // [2]  peers' h chunks landed (tx bytes), armed by the control thread
+    uint64_t* h_full = bars;           // [2]  the peer's h chunk landed (tx bytes of its st.async stores), armed by the control thread
     uint64_t* mma_done = bars + 2;
-    uint64_t* epi_done = bars + 3;     // one arrival per epilogue warp: local h chunk written
-    uint64_t* in_full = bars + 4;      // [NSF]
-    uint64_t* in_empty = bars + 4 + NSF;   // [NSF]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * NSF);
+    uint64_t* epi_done = bars + 5;     // one arrival per epilogue warp: local h chunk written
+    uint64_t* in_full = bars + 6;      // [NSF]
+    uint64_t* in_empty = bars + 6 + NSF;   // [NSF]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * NSF);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t c = CS > 1 ? tc::cluster_ctarank() : 0u;
@@ -185,53 +214,45 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_c
         // written the local chunk (epi_done) and the peers' chunks have landed (h_full, DSMEM bulk copies that
         // this thread also issues for the local chunk); then it issues the 48 MMAs of step s.
         if (tc::elect_one()) {
-            constexpr uint32_t idesc = tc::umma_idesc_bf16(UNITS, NB);
             bool ok = true;
             if (CS > 1 && T > 1) tc::mbar_arrive_expect_tx(&h_full[0], (uint32_t)(CS - 1) * chunk_bytes_mine);
             auto store_tile = [&](int step) {             // this CTA's 128 columns of Yrow for time step `step`
                 const int tt = d == 0 ? step : T - 1 - step;
                 const uint8_t* src = sH + (size_t)(step & 1) * KC * H_CHUNK + (size_t)c * chunk_bytes_mine;
-                for (int k = 0; k < UNITS / 64; ++k)
+                for (int k = 0; k < MYCH; ++k)
                     tc::tma_store_2d(&p.tmY, src + (size_t)k * H_CHUNK, d * H + (int)c * UNITS + 64 * k, tt * B + tile * NB);
                 tc::tma_store_commit();
             };
+            // per-step operand bases: K chunks [2c, 2c+2) of h_{s-1} are produced by this CTA (local group), the others
+            // arrive from the peer over DSMEM (remote group, CS == 2)
+            const uint32_t a_loc = tmem + FWD_A_COL + (uint32_t)c * (MYCH * 32);
+            const uint32_t a_rem = tmem + FWD_A_COL + (uint32_t)(1 - (int)c) * (MYCH * 32);
+            const uint32_t hb0 = tc::smem_u32(sH);
+            const uint64_t d_loc0 = tc::umma_desc_k_sw128(hb0 + (uint32_t)c * chunk_bytes_mine);
+            const uint64_t d_rem0 = tc::umma_desc_k_sw128(hb0 + (uint32_t)(1 - (int)c) * chunk_bytes_mine);
+            constexpr uint64_t BUF_DESC = (uint64_t)((KC * H_CHUNK) >> 4);        // descriptor distance of the two h buffers
             for (int s = 1; s < T; ++s) {                  // after a watchdog hit: keep signalling, stop waiting
                 const int pb = (s - 1) & 1;
                 if (ok) ok = tc::mbar_wait(epi_done, (s - 1) & 1, p.dbg, 0x400 + (s & 0xff));
-                const uint32_t hb = tc::smem_u32(sH + (size_t)pb * KC * H_CHUNK);
-                // K chunks [2c, 2c+1] of h_{s-1} were produced by this CTA: their MMAs are issued right away and run
-                // while the peers' chunks are still in flight over DSMEM; the remaining chunks follow after h_full.
-                auto issue = [&](int kc_lo, int kc_hi, bool first_pass) {
-#pragma unroll 1
-                    for (int g = 0; g < 3; ++g) {
-                        const uint32_t ta = tmem + FWD_A_COL + (uint32_t)(g * (H / 2));     // gate g: H/2 columns per row
-#pragma unroll 2
-                        for (int kc = kc_lo; kc < kc_hi; ++kc) {
-                            const uint64_t db = tc::umma_desc_k_sw128(hb + (uint32_t)kc * H_CHUNK);
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)       // K = 16 bf16 = 8 TMEM columns of A, 32 B of B
-                                umma_bf16_ts(tmem + g * NB, ta + (uint32_t)((kc * 4 + kk) * 8), db + 2 * kk, idesc,
-                                             (!first_pass || kc > kc_lo || kk) ? 1u : 0u);
-                        }
-                    }
-                };
-                const int my_lo = (int)c * (UNITS / 64), my_hi = my_lo + UNITS / 64;
+                SCAN_TS(0);
                 tc::tcgen05_fence_after();
                 if (CS > 1) {
-                    uint8_t* mine = sH + (size_t)pb * KC * H_CHUNK + (size_t)c * chunk_bytes_mine;
-                    for (uint32_t peer = 0; peer < (uint32_t)CS; ++peer)
-                        if (peer != c) tc::bulk_s2cluster(mine, mine, chunk_bytes_mine, &h_full[pb], peer);
-                    issue(my_lo, my_hi, true);
+                    // the local group's MMAs are issued right away and run while the peer's chunks (written straight into
+                    // this CTA's operand tile by the peer's epilogue threads) are still in flight
+                    fwd_issue_group<H, MYCH, true>(tmem, a_loc, d_loc0 + (pb ? BUF_DESC : 0));
+                    SCAN_TS(1);
                     if (ok) ok = tc::mbar_wait(&h_full[pb], ((s - 1) >> 1) & 1, p.dbg, 0x500 + (s & 0xff));
+                    SCAN_TS(2);
                     if (s + 1 < T) tc::mbar_arrive_expect_tx(&h_full[s & 1], (uint32_t)(CS - 1) * chunk_bytes_mine);
                     tc::tcgen05_fence_after();
-                    if (my_lo > 0) issue(0, my_lo, false);
-                    if (my_hi < KC) issue(my_hi, KC, false);
+                    fwd_issue_group<H, MYCH, false>(tmem, a_rem, d_rem0 + (pb ? BUF_DESC : 0));
                 } else {
-                    issue(0, KC, true);
+                    fwd_issue_group<H, KC, true>(tmem, a_loc, d_loc0 + (pb ? BUF_DESC : 0));
                 }
                 tc::tma_store_wait_read();                // the tile stored two steps ago is re-written after this commit
                 tc::umma_commit(mma_done);
+                SCAN_TS(3);
+                SCAN_TS(4);
                 // layer output rows of step s-1: TMA tile store straight from the operand tile (off the chain)
                 store_tile(s - 1);
             }
@@ -258,6 +279,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_c
             float gr[8], gz[8], gn[8];
             {
                 const int st = s % NSF;
+                if (tid == 0) SCAN_TS(5);
                 if (ok) ok = tc::mbar_wait(&in_full[st], (s / NSF) & 1, p.dbg, 0x200 + (s & 0xff));
                 const uint4* gp = reinterpret_cast<const uint4*>(sIn + (size_t)st * GI_BLOCK) + tid;
                 const uint4 u0 = gp[0], u1 = gp[256], u2 = gp[512];
@@ -273,39 +295,63 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_c
 #pragma unroll
                 for (int i = 0; i < 8; ++i) gn[i] = __bfloat162float(t8[i]);
             }
-            float ar[8], az[8], an[8];
-            if (s > 0) {
-                if (ok) ok = tc::mbar_wait(mma_done, (s - 1) & 1, p.dbg, 0x600 + (s & 0xff));
-                tc::tcgen05_fence_after();
-                const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + col0;
-                tmem_ld8(ta, ar); tmem_ld8(ta + NB, az); tmem_ld8(ta + 2 * NB, an);
-                tc::tmem_ld_wait();
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { ar[i] = 0.f; az[i] = 0.f; an[i] = 0.f; }
-            }
             const int buf = s & 1;
             uint8_t* hb = sH + (size_t)buf * KC * H_CHUNK + (size_t)(unit >> 6) * H_CHUNK;
-            __nv_bfloat16 hv[8], sr[8], sz[8], sn[8], shn[8];
+            const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + col0;
+            const uint32_t par = (s - 1) & 1;
+            float r8[8], z8[8], an[8];
+            if (s > 0) {
+                if (tid == 0) SCAN_TS(6);
+                if (ok) ok = tc::mbar_wait(mma_done, par, p.dbg, 0x600 + (s & 0xff));
+                if (tid == 0) SCAN_TS(7);
+                if (tid == 224) SCAN_TS(12);
+                tc::tcgen05_fence_after();
+                tmem_ld8(ta, r8); tmem_ld8(ta + NB, z8); tmem_ld8(ta + 2 * NB, an);
+                tc::tmem_ld_wait();
+                if (tid == 0) SCAN_TS(8);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { r8[i] = 0.f; z8[i] = 0.f; an[i] = 0.f; }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { r8[i] = sigmoid_fast(gr[i] + r8[i]); z8[i] = sigmoid_fast(gz[i] + z8[i]); }
+            float hn8[8], n8[8];
+            __nv_bfloat16 hv[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float r = sigmoid_fast(gr[i] + ar[i]);
-                const float z = sigmoid_fast(gz[i] + az[i]);
-                const float hn = an[i] + bhn;
-                const float n = tanh_fast(fmaf(r, hn, gn[i]));
-                const float h = fmaf(z, hprev[i] - n, n);
+                hn8[i] = an[i] + bhn;
+                n8[i] = tanh_fast(fmaf(r8[i], hn8[i], gn[i]));
+                const float h = fmaf(z8[i], hprev[i] - n8[i], n8[i]);
                 hprev[i] = h;
                 hv[i] = __float2bfloat16(h);
-                sr[i] = __float2bfloat16(r); sz[i] = __float2bfloat16(z); sn[i] = __float2bfloat16(n); shn[i] = __float2bfloat16(hn);
                 *reinterpret_cast<__nv_bfloat16*>(hb + tc::sw128_offset(col0 + i, unit & 63)) = hv[i];
             }
             // hand h_t to the control thread (this is the step chain): smem writes -> async proxy, one arrival per
             // warp; everything that only feeds HBM is issued afterwards, off the chain
+            if (tid == 0) SCAN_TS(9);
             tc::tcgen05_fence_before();
+            if (CS > 1 && s + 1 < T) {
+                // peer hand-off without the control thread: after the warp's 2-byte writes, lane L re-reads one 16-byte
+                // chunk (8 units of lane group L/8, batch column L%8) and stores it asynchronously into the same place of
+                // the peer's operand tile; the store completes its bytes on the peer's h_full (async proxy end to end)
+                __syncwarp();
+                const int gu = (int)c * UNITS + q * 32 + (lane >> 3) * 8;
+                uint8_t* cp = sH + (size_t)buf * KC * H_CHUNK + (size_t)(gu >> 6) * H_CHUNK + tc::sw128_offset(col0 + (lane & 7), gu & 63);
+                const uint4 v = *reinterpret_cast<const uint4*>(cp);
+                tc::st_async_v4(tc::mapa_u32(tc::smem_u32(cp), 1u - c), v, tc::mapa_u32(tc::smem_u32(&h_full[buf]), 1u - c));
+            }
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(epi_done);
+            if (tid == 0) SCAN_TS(10);
+            if (tid == 224) SCAN_TS(13);
             {
+                __nv_bfloat16 sr[8], sz[8], sn[8], shn[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    sr[i] = __float2bfloat16(r8[i]); sz[i] = __float2bfloat16(z8[i]);
+                    sn[i] = __float2bfloat16(n8[i]); shn[i] = __float2bfloat16(hn8[i]);
+                }
                 uint4* gs = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.G) + blk * G_BLOCK) + tid;
                 gs[0] = *reinterpret_cast<uint4*>(sr); gs[256] = *reinterpret_cast<uint4*>(sz);
                 gs[512] = *reinterpret_cast<uint4*>(sn); gs[768] = *reinterpret_cast<uint4*>(shn);
@@ -315,6 +361,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_c
 #pragma unroll
                 for (int i = 0; i < 8; ++i) p.hn_out[((int64_t)d * B + tile * NB + col0 + i) * H + unit] = hprev[i];
             }
+            if (tid == 0) SCAN_TS(11);
         }
     }
     tc::tcgen05_fence_before();
@@ -332,12 +379,14 @@ static inline cudaError_t launch_fwd(const FwdParams& p_in, cudaStream_t st) {
         if (make_tmap_bf16(&p.tmY, p.Yrow, 2, dims, strides, box) != 0) return cudaErrorInvalidValue;
     }
     const int CS = p.H / UNITS;
+    if (p.H != 128 && p.H != 256) return cudaErrorInvalidValue;
     const size_t smem = fwd_smem_bytes(p.H);
-    static size_t attr = 0;
-    if (attr < smem) {
-        cudaError_t e = cudaFuncSetAttribute(gru_scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    void (*kern)(FwdParams) = p.H == 128 ? gru_scan_fwd_kernel<128> : gru_scan_fwd_kernel<256>;
+    static bool attr[2] = {false, false};
+    if (!attr[CS - 1]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr = smem;
+        attr[CS - 1] = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(p.D * (p.B / NB) * CS));
@@ -348,7 +397,7 @@ static inline cudaError_t launch_fwd(const FwdParams& p_in, cudaStream_t st) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, gru_scan_fwd_kernel, p);
+    return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 // ---- packed weights: W_hh fp32 [3H][H] (rows r|z|n) -> Wpk[unit u][g][k] bf16 (row of unit u = its three gate rows)
@@ -403,10 +452,29 @@ struct BwdParams {
     unsigned int* dbg;
 };
 
+// K chunks [u0, u0 + NCH) of each of the three gate blocks of the [16 x 3H] dgh tile, fully unrolled (see fwd_issue_group)
+template <int H, int NCH, bool FIRST>
+__device__ __forceinline__ void bwd_issue_group(uint32_t tmem_d, uint32_t tmem_a_grp, uint64_t desc_grp) {
+    constexpr uint32_t idesc = tc::umma_idesc_bf16(UNITS, NB);
+    constexpr int KC = H / 64;
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+#pragma unroll
+        for (int u = 0; u < NCH; ++u) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                umma_bf16_ts(tmem_d, tmem_a_grp + (uint32_t)(((g * KC + u) * 4 + kk) * 8),
+                             desc_grp + (uint64_t)((g * KC + u) * (H_CHUNK >> 4) + 2 * kk), idesc, (FIRST && g == 0 && u == 0 && kk == 0) ? 0u : 1u);
+        }
+    }
+}
+
+template <int H>
 __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_constant__ BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int H = p.H, KC = H / 64, KC3 = 3 * KC, CS = H / UNITS, B = p.B, T = p.T, D = p.D;
+    constexpr int KC = H / 64, KC3 = 3 * KC, CS = H / UNITS, MYCH = UNITS / 64;
+    const int B = p.B, T = p.T, D = p.D;
     uint8_t* sD = smem;                                    // [2][KC3][H_CHUNK]  dgh operand tiles
     uint8_t* sN = sD + (size_t)2 * KC3 * H_CHUNK;          // [2][UNITS/64][H_CHUNK]  da_n of this CTA's units (dgi n-gate, store only)
     uint8_t* sIn = sN + (size_t)2 * (UNITS / 64) * H_CHUNK;   // [NSB][G | YB | dY]
@@ -417,7 +485,8 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
     uint64_t* epi_done = bars + 3;
     uint64_t* in_full = bars + 4;      // [NSB]
     uint64_t* in_empty = bars + 4 + NSB;   // [NSB]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * NSB);
+    uint64_t* st_done = bars + 4 + 2 * NSB;    // n-gate tile written (only the TMA row stores wait for it)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * NSB);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t c = CS > 1 ? tc::cluster_ctarank() : 0u;
@@ -432,6 +501,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
         tc::mbar_init(&d_full[1], 1);
         tc::mbar_init(mma_done, 1);
         tc::mbar_init(epi_done, EPI_WARPS);
+        tc::mbar_init(st_done, EPI_WARPS);
         for (int i = 0; i < NSB; ++i) { tc::mbar_init(&in_full[i], 1); tc::mbar_init(&in_empty[i], EPI_WARPS); }
         tc::fence_mbar_init();
     }
@@ -471,17 +541,16 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
     } else if (warp == EPI_WARPS) {
         // ---- control thread (see forward kernel)
         if (tc::elect_one()) {
-            constexpr uint32_t idesc = tc::umma_idesc_bf16(UNITS, NB);
             bool ok = true;
             if (CS > 1 && T > 1) tc::mbar_arrive_expect_tx(&d_full[0], (uint32_t)(CS - 1) * 3 * gate_bytes_mine);
             auto store_tile = [&](int step) {             // dgi / dgh_n rows of time step `step`, this CTA's 128 units
                 const int tt = d == 0 ? T - 1 - step : step;
                 const int row = tt * B + tile * NB;
                 const uint8_t* tb = sD + (size_t)(step & 1) * KC3 * H_CHUNK;
-                const uint8_t* nb = sN + (size_t)(step & 1) * (UNITS / 64) * H_CHUNK;
-                for (int k = 0; k < UNITS / 64; ++k) {
+                const uint8_t* nb = sN + (size_t)(step & 1) * MYCH * H_CHUNK;
+                for (int k = 0; k < MYCH; ++k) {
                     const int cu = (int)c * UNITS + 64 * k;
-                    const size_t co = ((size_t)c * (UNITS / 64) + k) * H_CHUNK;
+                    const size_t co = ((size_t)c * MYCH + k) * H_CHUNK;
                     tc::tma_store_2d(&p.tmGI, tb + (size_t)(0 * KC) * H_CHUNK + co, d * 3 * H + cu, row);            // da_r
                     tc::tma_store_2d(&p.tmGI, tb + (size_t)(1 * KC) * H_CHUNK + co, d * 3 * H + H + cu, row);        // da_z
                     tc::tma_store_2d(&p.tmGI, nb + (size_t)k * H_CHUNK, d * 3 * H + 2 * H + cu, row);                 // da_n
@@ -489,50 +558,33 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
                 }
                 tc::tma_store_commit();
             };
+            // operand bases: inside each gate block, K chunks [2c, 2c+2) are this CTA's own (local group)
+            const uint32_t a_loc = tmem + BWD_A_COL + (uint32_t)c * (MYCH * 32);
+            const uint32_t a_rem = tmem + BWD_A_COL + (uint32_t)(1 - (int)c) * (MYCH * 32);
+            const uint32_t db0 = tc::smem_u32(sD);
+            const uint64_t d_loc0 = tc::umma_desc_k_sw128(db0 + (uint32_t)c * gate_bytes_mine);
+            const uint64_t d_rem0 = tc::umma_desc_k_sw128(db0 + (uint32_t)(1 - (int)c) * gate_bytes_mine);
+            constexpr uint64_t BUF_DESC = (uint64_t)((KC3 * H_CHUNK) >> 4);
             for (int s = 1; s < T; ++s) {
                 const int pb = (s - 1) & 1;
-                uint8_t* tileb = sD + (size_t)pb * KC3 * H_CHUNK;
                 if (ok) ok = tc::mbar_wait(epi_done, (s - 1) & 1, p.dbg, 0x700 + (s & 0xff));
-                const uint32_t db0 = tc::smem_u32(tileb);
-                // K chunks of the three gates that this CTA produced itself go first (see forward kernel)
-                auto issue = [&](int u_lo, int u_hi, bool first_pass) {      // u = chunk index inside a gate, [0, KC)
-#pragma unroll 1
-                    for (int g = 0; g < 3; ++g) {
-#pragma unroll 2
-                        for (int u = u_lo; u < u_hi; ++u) {
-                            const int kc = g * KC + u;
-                            const uint64_t db = tc::umma_desc_k_sw128(db0 + (uint32_t)kc * H_CHUNK);
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                umma_bf16_ts(tmem, tmem + BWD_A_COL + (uint32_t)((kc * 4 + kk) * 8), db + 2 * kk, idesc,
-                                             (!first_pass || g > 0 || u > u_lo || kk) ? 1u : 0u);
-                        }
-                    }
-                };
-                const int my_lo = (int)c * (UNITS / 64), my_hi = my_lo + UNITS / 64;
                 tc::tcgen05_fence_after();
                 if (CS > 1) {
-                    for (uint32_t peer = 0; peer < (uint32_t)CS; ++peer) {
-                        if (peer == c) continue;
-                        for (int g = 0; g < 3; ++g) {
-                            uint8_t* mine = tileb + (size_t)(g * KC) * H_CHUNK + (size_t)c * gate_bytes_mine;
-                            tc::bulk_s2cluster(mine, mine, gate_bytes_mine, &d_full[pb], peer);
-                        }
-                    }
-                    issue(my_lo, my_hi, true);
+                    bwd_issue_group<H, MYCH, true>(tmem, a_loc, d_loc0 + (pb ? BUF_DESC : 0));
                     if (ok) ok = tc::mbar_wait(&d_full[pb], ((s - 1) >> 1) & 1, p.dbg, 0x800 + (s & 0xff));
                     if (s + 1 < T) tc::mbar_arrive_expect_tx(&d_full[s & 1], (uint32_t)(CS - 1) * 3 * gate_bytes_mine);
                     tc::tcgen05_fence_after();
-                    if (my_lo > 0) issue(0, my_lo, false);
-                    if (my_hi < KC) issue(my_hi, KC, false);
+                    bwd_issue_group<H, MYCH, false>(tmem, a_rem, d_rem0 + (pb ? BUF_DESC : 0));
                 } else {
-                    issue(0, KC, true);
+                    bwd_issue_group<H, KC, true>(tmem, a_loc, d_loc0 + (pb ? BUF_DESC : 0));
                 }
                 tc::tma_store_wait_read();
                 tc::umma_commit(mma_done);
+                if (ok) ok = tc::mbar_wait(st_done, (s - 1) & 1, p.dbg, 0xa00 + (s & 0xff));
                 store_tile(s - 1);
             }
             if (ok) ok = tc::mbar_wait(epi_done, (T - 1) & 1, p.dbg, 0x700);
+            if (ok) ok = tc::mbar_wait(st_done, (T - 1) & 1, p.dbg, 0xa00);
             store_tile(T - 1);
             tc::tma_store_wait_all();
         }
@@ -611,6 +663,16 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
                 for (int i = 0; i < 8; ++i) vhp[i] = __bfloat162float(t8[i]);
                 vdy[0] = a.x; vdy[1] = a.y; vdy[2] = a.z; vdy[3] = a.w; vdy[4] = b.x; vdy[5] = b.y; vdy[6] = b.z; vdy[7] = b.w;
             }
+            // everything that does not depend on the recurrent product is formed before the wait on the tensor pipe
+            float c_n[8], c_r[8], c_z[8], pre[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float r = vr[i], z = vz[i], n = vn[i];
+                c_n[i] = (1.f - z) * (1.f - n * n);                 // da_n = dh * c_n
+                c_r[i] = vhn[i] * r * (1.f - r);                    // da_r = da_n * c_r
+                c_z[i] = (vhp[i] - n) * z * (1.f - z);              // da_z = dh * c_z
+                pre[i] = dhz[i] + vdy[i];
+            }
             float acc[8];
             if (s > 0) {
                 if (ok) ok = tc::mbar_wait(mma_done, (s - 1) & 1, p.dbg, 0x900 + (s & 0xff));
@@ -621,32 +683,49 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[i] = 0.f;
             }
-            uint8_t* tileb = sD + (size_t)(s & 1) * KC3 * H_CHUNK;
-            __nv_bfloat16 tr[8], tz[8], tn[8], tnr[8];
+            const int buf = s & 1;
+            uint8_t* tileb = sD + (size_t)buf * KC3 * H_CHUNK;
+            const int kc_u = unit >> 6;
+            float dar[8], daz[8], dan[8], danr[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float dh = acc[i] + dhz[i] + vdy[i];
-                const float r = vr[i], z = vz[i], n = vn[i];
-                const float dan = dh * (1.f - z) * (1.f - n * n);
-                const float dar = dan * vhn[i] * r * (1.f - r);
-                const float daz = dh * (vhp[i] - n) * z * (1.f - z);
-                const float danr = dan * r;
-                dhz[i] = dh * z;
-                sb_r += dar; sb_z += daz; sb_n += dan; sb_nr += danr;
-                tr[i] = __float2bfloat16(dar); tz[i] = __float2bfloat16(daz);
-                tn[i] = __float2bfloat16(dan); tnr[i] = __float2bfloat16(danr);
+                const float dh = acc[i] + pre[i];
+                dan[i] = dh * c_n[i];
+                dar[i] = dan[i] * c_r[i];
+                daz[i] = dh * c_z[i];
+                danr[i] = dan[i] * vr[i];
+                dhz[i] = dh * vz[i];
                 const uint32_t so = tc::sw128_offset(col0 + i, unit & 63);
-                const int kc_u = unit >> 6;
-                *reinterpret_cast<__nv_bfloat16*>(tileb + (size_t)(0 * KC + kc_u) * H_CHUNK + so) = tr[i];
-                *reinterpret_cast<__nv_bfloat16*>(tileb + (size_t)(1 * KC + kc_u) * H_CHUNK + so) = tz[i];
-                *reinterpret_cast<__nv_bfloat16*>(tileb + (size_t)(2 * KC + kc_u) * H_CHUNK + so) = tnr[i];
-                *reinterpret_cast<__nv_bfloat16*>(sN + (size_t)((s & 1) * (UNITS / 64) + ((unit & (UNITS - 1)) >> 6)) * H_CHUNK + so) = tn[i];
+                *reinterpret_cast<__nv_bfloat16*>(tileb + (size_t)(0 * KC + kc_u) * H_CHUNK + so) = __float2bfloat16(dar[i]);
+                *reinterpret_cast<__nv_bfloat16*>(tileb + (size_t)(1 * KC + kc_u) * H_CHUNK + so) = __float2bfloat16(daz[i]);
+                *reinterpret_cast<__nv_bfloat16*>(tileb + (size_t)(2 * KC + kc_u) * H_CHUNK + so) = __float2bfloat16(danr[i]);
             }
-            // hand dgh_s to the control thread (the step chain); HBM stores follow, off the chain
+            // hand dgh_s to the tensor pipe (the step chain): own chunks -> peer with st.async (see forward kernel), then
+            // the local arrival; the n-gate tile (TMA store only) and the bias sums follow, off the chain
             tc::tcgen05_fence_before();
+            if (CS > 1 && s + 1 < T) {
+                __syncwarp();
+                const int gu = (int)c * UNITS + q * 32 + (lane >> 3) * 8;
+                const uint32_t so = tc::sw128_offset(col0 + (lane & 7), gu & 63);
+                const uint32_t rbar = tc::mapa_u32(tc::smem_u32(&d_full[buf]), 1u - c);
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                    uint8_t* cp = tileb + (size_t)(g * KC + (gu >> 6)) * H_CHUNK + so;
+                    const uint4 v = *reinterpret_cast<const uint4*>(cp);
+                    tc::st_async_v4(tc::mapa_u32(tc::smem_u32(cp), 1u - c), v, rbar);
+                }
+            }
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(epi_done);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<__nv_bfloat16*>(sN + (size_t)(buf * MYCH + ((unit & (UNITS - 1)) >> 6)) * H_CHUNK + tc::sw128_offset(col0 + i, unit & 63)) = __float2bfloat16(dan[i]);
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(st_done);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { sb_r += dar[i]; sb_z += daz[i]; sb_n += dan[i]; sb_nr += danr[i]; }
         }
         // bias gradients: sum the 8 columns of this thread; the two column halves and all tiles add atomically
         float* dbi = p.db_ih + (int64_t)d * p.dir_stride;
@@ -672,12 +751,14 @@ static inline cudaError_t launch_bwd(const BwdParams& p_in, cudaStream_t st) {
             return cudaErrorInvalidValue;
     }
     const int CS = p.H / UNITS;
+    if (p.H != 128 && p.H != 256) return cudaErrorInvalidValue;
     const size_t smem = bwd_smem_bytes(p.H);
-    static size_t attr = 0;
-    if (attr < smem) {
-        cudaError_t e = cudaFuncSetAttribute(gru_scan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    void (*kern)(BwdParams) = p.H == 128 ? gru_scan_bwd_kernel<128> : gru_scan_bwd_kernel<256>;
+    static bool attr[2] = {false, false};
+    if (!attr[CS - 1]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr = smem;
+        attr[CS - 1] = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(p.D * (p.B / NB) * CS));
@@ -688,7 +769,7 @@ static inline cudaError_t launch_bwd(const BwdParams& p_in, cudaStream_t st) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, gru_scan_bwd_kernel, p);
+    return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 // W_hh fp32 [3H][H] -> packed W_hh^T: WTpk[unit k][q] = W_hh[q][k]   (row of unit k = column k of W_hh, 3H long)

@@ -43,6 +43,9 @@ static int run_case(int B, int T, int H, int D, int reps) {
     p.B = B; p.T = T; p.H = H; p.D = D; p.Wimg = d_img; p.giB = d_gi; p.b_hn = d_bhn; p.Yrow = d_Y; p.G = d_G;
     __nv_bfloat16* d_YB; CK(cudaMalloc(&d_YB, (size_t)R * D * H * 2)); p.YB = d_YB;
     p.hn_out = d_hn; p.dbg = dbg;
+#ifdef BIGRU_SCAN_TIMING
+    unsigned long long* d_ts; CK(cudaMalloc(&d_ts, 8 * 16 * 8)); CK(cudaMemset(d_ts, 0, 8 * 16 * 8)); p.ts = d_ts;
+#endif
     CK(tcs::launch_fwd(p, 0));
     CK(cudaDeviceSynchronize());
     float ms = 0;
@@ -54,6 +57,22 @@ static int run_case(int B, int T, int H, int D, int reps) {
         cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
     }
     unsigned int h[8]; CK(cudaMemcpy(h, dbg, 32, cudaMemcpyDeviceToHost));
+#ifdef BIGRU_SCAN_TIMING
+    if (T >= 80) {
+        unsigned long long ts[8 * 16]; CK(cudaMemcpy(ts, d_ts, sizeof(ts), cudaMemcpyDeviceToHost));
+        // slots: control 0 epi_done seen, 1 local MMAs issued, 2 h_full seen, 3 all MMAs issued, 4 committed;
+        // epilogue thread 0: 5 loop top, 6 gi ready, 7 mma_done seen, 8 tmem loaded, 9 h written, 10 arrived, 11 stores issued;
+        // epilogue thread 224: 12 mma_done seen, 13 arrived
+        printf("timing (cycles, CTA 0, H=%d): step | c:wait->loc | loc->hfull | hfull->issued | commit || e: commit->mma_done | ld | math+sts | fence+arrive | arrive->c.wake | stores | step total\n", H);
+        for (int k = 1; k < 7; ++k) {
+            const unsigned long long* a = ts + k * 16; const unsigned long long* nx = ts + (k + 1) * 16;
+            printf("  s=%d | %5lld | %5lld | %5lld | %5lld || %5lld (w7 %5lld) | %5lld | %5lld | %5lld (w7 %5lld) | %5lld | %5lld | %5lld   [gi wait %lld]\n", 64 + k,
+                   (long long)(a[1] - a[0]), (long long)(a[2] - a[1]), (long long)(a[3] - a[2]), (long long)(a[4] - a[3]),
+                   (long long)(a[7] - a[4]), (long long)(a[12] - a[4]), (long long)(a[8] - a[7]), (long long)(a[9] - a[8]), (long long)(a[10] - a[9]),
+                   (long long)(a[13] - a[9]), (long long)(nx[0] - a[10]), (long long)(a[11] - a[10]), (long long)(nx[0] - a[0]), (long long)(a[6] - a[5]));
+        }
+    }
+#endif
     std::vector<__nv_bfloat16> Y((size_t)R * D * H), YT((size_t)R * D * H), G((size_t)R * D * 4 * H);
     std::vector<float> hn((size_t)D * B * H);
     CK(cudaMemcpy(Y.data(), d_Y, Y.size() * 2, cudaMemcpyDeviceToHost));
