@@ -78,29 +78,44 @@ __global__ void cast_x_kernel(const float* __restrict__ x, WindowSrc w, bf16_t* 
     const float scale = pdrop > 0.f ? 1.f / (1.f - pdrop) : 1.f;
     const int F4 = F >> 2;                          // F % 8 == 0 on the tensor-core path
     const int64_t total = (int64_t)B * T * F4;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int f = (int)(i % F4) * 4;
-        const int64_t r = i / F4;                // output row t*B + b
-        const int64_t b = r % B, t = r / B;
-        float4 v;
-        if (w.src) {
-            v = *reinterpret_cast<const float4*>(w.src + (w.start + b + t) * F + f);
-            if (w.xmin) {
-                const float4 mn = *reinterpret_cast<const float4*>(w.xmin + f), mx = *reinterpret_cast<const float4*>(w.xmax + f);
-                v.x = (v.x - mn.x) / (mx.x - mn.x); v.y = (v.y - mn.y) / (mx.y - mn.y);
-                v.z = (v.z - mn.z) / (mx.z - mn.z); v.w = (v.w - mn.w) / (mx.w - mn.w);
-            }
-        } else v = *reinterpret_cast<const float4*>(x + (b * T + t) * F + f);
-        if (pdrop > 0.f) {
-            float* e = &v.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    constexpr int U = 4;                            // loads in flight per thread (the kernel is pure latency otherwise)
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += U * nthr) {
+        float4 v[U];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint64_t key = spatial ? (uint64_t)b * F + f + k : ((uint64_t)b * T + t) * F + f + k;
-                e[k] = bigru_uniform(seed, 0u, key) < pdrop ? 0.f : e[k] * scale;
-            }
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * nthr;
+            if (i >= total) break;
+            const int f = (int)(i % F4) * 4;
+            const int64_t r = i / F4;                // output row t*B + b
+            const int64_t b = r % B, t = r / B;
+            v[u] = w.src ? *reinterpret_cast<const float4*>(w.src + (w.start + b + t) * F + f)
+                         : *reinterpret_cast<const float4*>(x + (b * T + t) * F + f);
         }
-        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-        *reinterpret_cast<uint2*>(Xrow + r * F + f) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * nthr;
+            if (i >= total) break;
+            const int f = (int)(i % F4) * 4;
+            const int64_t r = i / F4;
+            const int64_t b = r % B, t = r / B;
+            float4 q = v[u];
+            if (w.src && w.xmin) {
+                const float4 mn = *reinterpret_cast<const float4*>(w.xmin + f), mx = *reinterpret_cast<const float4*>(w.xmax + f);
+                q.x = (q.x - mn.x) / (mx.x - mn.x); q.y = (q.y - mn.y) / (mx.y - mn.y);
+                q.z = (q.z - mn.z) / (mx.z - mn.z); q.w = (q.w - mn.w) / (mx.w - mn.w);
+            }
+            if (pdrop > 0.f) {
+                float* e = &q.x;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t key = spatial ? (uint64_t)b * F + f + k : ((uint64_t)b * T + t) * F + f + k;
+                    e[k] = bigru_uniform(seed, 0u, key) < pdrop ? 0.f : e[k] * scale;
+                }
+            }
+            __nv_bfloat162 lo = __floats2bfloat162_rn(q.x, q.y), hi = __floats2bfloat162_rn(q.z, q.w);
+            *reinterpret_cast<uint2*>(Xrow + r * F + f) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        }
     }
 }
 
@@ -163,69 +178,119 @@ __global__ void pack_bias_kernel(const float* __restrict__ b_ih, const float* __
 struct PackJob { const float* w_ih; const float* w_hh; const float* b_ih; const float* b_hh;
                  bf16_t* Wih; bf16_t* WihT; bf16_t* Wimg; bf16_t* WTimg; float* bfold; float* bhn; int I; int d; };
 struct PackJobs { PackJob j[32]; };
-__global__ void pack_all_kernel(const PackJobs jobs, int H, int D) {
+// dst_rm[r][c] = dst_t[c][r] = bf16(src[r][c]) for a [rows][cols] fp32 matrix (cols % 32 == 0, rows % 32 == 0): 32 x 32 tiles
+// through shared memory so that the row-major AND the transposed image are both written coalesced.  ld_rm / ld_t are the
+// leading dimensions of the two images (elements).
+__device__ __forceinline__ void pack_tile_pair(const float* __restrict__ src, int rows, int cols, bf16_t* __restrict__ dst_rm, int64_t ld_rm,
+                                               bf16_t* __restrict__ dst_t, int64_t ld_t, int tile0, int tile_stride, float (*tile)[33]) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 256 threads: 32 x 8
+    const int tr = rows / 32, tcn = cols / 32;
+    for (int tl = tile0; tl < tr * tcn; tl += tile_stride) {
+        const int r0 = (tl / tcn) * 32, c0 = (tl % tcn) * 32;
+#pragma unroll
+        for (int i = ty; i < 32; i += 8) {
+            const float v = src[(int64_t)(r0 + i) * cols + c0 + tx];
+            tile[i][tx] = v;
+            dst_rm[(int64_t)(r0 + i) * ld_rm + c0 + tx] = __float2bfloat16(v);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = ty; i < 32; i += 8) dst_t[(int64_t)(c0 + i) * ld_t + r0 + tx] = __float2bfloat16(tile[tx][i]);
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) pack_all_kernel(const PackJobs jobs, int H, int D) {
+    __shared__ float tile[32][33];
     const PackJob& J = jobs.j[blockIdx.y];
     const int H3 = 3 * H, I = J.I, d = J.d;
-    const int64_t n_ih = (int64_t)H3 * I, n_hh = (int64_t)H3 * H;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x, i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (int64_t i = i0; i < n_ih; i += stride) {          // W_ih [3H][I] -> rows d*3H.. of Wih, columns of WihT
-        const int k = i % I, q = i / I;
-        const bf16_t v = __float2bfloat16(J.w_ih[i]);
-        J.Wih[((int64_t)d * H3 + q) * I + k] = v;
-        J.WihT[(int64_t)k * D * H3 + (int64_t)d * H3 + q] = v;
+    if (I % 32 == 0) {
+        // W_ih [3H][I] -> rows d*3H.. of Wih [D*3H][I] and columns d*3H.. of WihT [I][D*3H]
+        pack_tile_pair(J.w_ih, H3, I, J.Wih + (int64_t)d * H3 * I, I, J.WihT + (int64_t)d * H3, (int64_t)D * H3, blockIdx.x, gridDim.x, tile);
+    } else {
+        const int64_t n_ih = (int64_t)H3 * I;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ih; i += (int64_t)gridDim.x * blockDim.x) {
+            const int k = i % I, q = i / I;
+            const bf16_t v = __float2bfloat16(J.w_ih[i]);
+            J.Wih[((int64_t)d * H3 + q) * I + k] = v;
+            J.WihT[(int64_t)k * D * H3 + (int64_t)d * H3 + q] = v;
+        }
     }
-    for (int64_t i = i0; i < n_hh; i += stride) {          // W_hh [3H][H] -> per-unit rows (fwd) and rows of W_hh^T (bwd)
-        const int k = i % H, row = i / H, g = row / H, unit = row % H;
-        const bf16_t v = __float2bfloat16(J.w_hh[i]);
-        J.Wimg[((int64_t)unit * 3 + g) * H + k] = v;
-        J.WTimg[(int64_t)k * H3 + row] = v;
-    }
-    for (int64_t q = i0; q < H3; q += stride) {
+    // W_hh [3H][H]: gate g of unit u -> Wimg [unit][g][H] (row g*H+u of W_hh is row u*3+g of the image) and W_hh^T
+    // -> WTimg [H][3H]; one gate block ([H][H]) at a time so that the row-major image is a plain strided copy
+    for (int g = 0; g < 3; ++g)
+        pack_tile_pair(J.w_hh + (int64_t)g * H * H, H, H, J.Wimg + (int64_t)g * H, (int64_t)3 * H, J.WTimg + (int64_t)g * H, H3,
+                       blockIdx.x, gridDim.x, tile);
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < H3; q += (int64_t)gridDim.x * blockDim.x) {
         J.bfold[d * H3 + q] = J.b_ih[q] + (q < 2 * H ? J.b_hh[q] : 0.f);
         if (q >= 2 * H) J.bhn[d * H + q - 2 * H] = J.b_hh[q];
     }
 }
 
 // Head forward (biGRU_model.py:111-137) fused: direction sum, last hidden, max / mean pooling over T and the
-// Linear(3H -> C), one block per batch row (threads = hidden units; each time step is one contiguous 2*D*H-byte row).
-__global__ void head_fwd_kernel(const bf16_t* __restrict__ Y, const float* __restrict__ lin_w, const float* __restrict__ lin_b,
-                                float* __restrict__ cat, int* __restrict__ arg, float* __restrict__ logits,
-                                int B, int T, int H, int D, int C) {
-    extern __shared__ float red[];                     // [C][blockDim/32]
-    const int b = blockIdx.x, j = threadIdx.x;
-    const int ld = D * H;
-    float last = 0.f, mx = -INFINITY, sum = 0.f;
-    int am = 0;
+// Linear(3H -> C), one block (256 threads) per batch row.  Pooling: a thread owns 8 consecutive hidden units (one 16-byte
+// load per direction and time step), H/8 lanes cover a time step and the 256/(H/8) lane groups split the T steps; the
+// groups' partial (max, first argmax, sum) are combined through shared memory.  H % 8 == 0, H <= 256.
+__global__ void __launch_bounds__(256) head_fwd_kernel(const bf16_t* __restrict__ Y, const float* __restrict__ lin_w,
+                                                       const float* __restrict__ lin_b, float* __restrict__ cat, int* __restrict__ arg,
+                                                       float* __restrict__ logits, int B, int T, int H, int D, int C) {
+    extern __shared__ float hs[];                      // [G][H] max, [G][H] sum, [G][H] argmax (int), then [C][8] partial logits
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int ld = D * H, LPS = H >> 3, G = 256 / LPS;  // lanes per step, lane groups
+    const int grp = tid / LPS, u0 = (tid % LPS) * 8;
+    float* s_max = hs; float* s_sum = hs + G * H; int* s_arg = reinterpret_cast<int*>(hs + 2 * G * H);
+    float* red = hs + 3 * G * H;
+    float mx[8], sm[8]; int am[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { mx[i] = -INFINITY; sm[i] = 0.f; am[i] = 0; }
+    if (grp < G) {
+#pragma unroll 4
+        for (int t = grp; t < T; t += G) {
+            const bf16_t* y = Y + ((int64_t)t * B + b) * ld + u0;
+            const uint4 a = *reinterpret_cast<const uint4*>(y);
+            uint4 c = make_uint4(0u, 0u, 0u, 0u);
+            if (D == 2) c = *reinterpret_cast<const uint4*>(y + H);
+            const bf16_t* pa = reinterpret_cast<const bf16_t*>(&a);
+            const bf16_t* pc = reinterpret_cast<const bf16_t*>(&c);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float v = __bfloat162float(pa[i]) + __bfloat162float(pc[i]);
+                if (v > mx[i]) { mx[i] = v; am[i] = t; }
+                sm[i] += v;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s_max[grp * H + u0 + i] = mx[i]; s_sum[grp * H + u0 + i] = sm[i]; s_arg[grp * H + u0 + i] = am[i]; }
+    }
+    __syncthreads();
+    const int j = tid;
+    float last = 0.f, m = -INFINITY, sum = 0.f;
+    int a_t = 0;
     if (j < H) {
         last = __bfloat162float(Y[((int64_t)(T - 1) * B + b) * ld + j]);
         if (D == 2) last += __bfloat162float(Y[(int64_t)b * ld + H + j]);
-#pragma unroll 8
-        for (int t = 0; t < T; ++t) {
-            const bf16_t* y = Y + ((int64_t)t * B + b) * ld;
-            float s = __bfloat162float(y[j]);
-            if (D == 2) s += __bfloat162float(y[H + j]);
-            if (s > mx) { mx = s; am = t; }
-            sum += s;
+        for (int g = 0; g < G; ++g) {                  // first occurrence of the maximum, as a sequential scan over t finds it
+            const float v = s_max[g * H + j]; const int at = s_arg[g * H + j];
+            if (v > m || (v == m && at < a_t)) { m = v; a_t = at; }
+            sum += s_sum[g * H + j];
         }
         float* c = cat + (int64_t)b * 3 * H;
-        c[j] = last; c[H + j] = mx; c[2 * H + j] = sum / (float)T;
-        arg[(int64_t)b * H + j] = am;
+        c[j] = last; c[H + j] = m; c[2 * H + j] = sum / (float)T;
+        arg[(int64_t)b * H + j] = a_t;
     }
     const float avg = sum / (float)T;
-    const int nw = blockDim.x >> 5;
     for (int cc = 0; cc < C; ++cc) {
         float v = 0.f;
         if (j < H) {
             const float* w = lin_w + (int64_t)cc * 3 * H;
-            v = last * w[j] + mx * w[H + j] + avg * w[2 * H + j];
+            v = last * w[j] + m * w[H + j] + avg * w[2 * H + j];
         }
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((j & 31) == 0) red[cc * nw + (j >> 5)] = v;
+        if ((j & 31) == 0) red[cc * 8 + (j >> 5)] = v;
     }
     __syncthreads();
     if (j < C) {
         float v = lin_b[j];
-        for (int w = 0; w < nw; ++w) v += red[j * nw + w];
+        for (int w = 0; w < 8; ++w) v += red[j * 8 + w];
         logits[(int64_t)b * C + j] = v;
     }
 }
@@ -325,7 +390,7 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
                 J.Wimg = (bf16_t*)(S + L.Wimg[l]) + (size_t)d * 3 * H * H; J.WTimg = (bf16_t*)(S + L.WTimg[l]) + (size_t)d * 3 * H * H;
                 J.bfold = (float*)(S + L.bfold[l]); J.bhn = (float*)(S + L.bhn[l]); J.I = (int)p.in_size(l); J.d = d;
             }
-        KLAUNCH(KC_PACK, 0.0, 0.0, st, pack_all_kernel<<<dim3(64, nj), 256, 0, st>>>(jobs, H, D));
+        KLAUNCH(KC_PACK, 0.0, 0.0, st, pack_all_kernel<<<dim3(148, nj), 256, 0, st>>>(jobs, H, D));
     }
     // 2. layer-0 input: cast to bf16, time-major rows (+ input dropout)
     KLAUNCH(KC_PACK, 0.0, 6.0 * R * F, st, cast_x_kernel<<<148 * 8, 256, 0, st>>>(x, win, (bf16_t*)(S + L.Xrow[0]), B, T, F,
@@ -361,8 +426,9 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
     }
     // 5. head: pooling + Linear fused
     {
-        const int threads = ((H + 31) / 32) * 32;
-        KLAUNCH(KC_HEAD, 0.0, 2.0 * R * D * H, st, head_fwd_kernel<<<B, threads, sizeof(float) * p.C * (threads / 32), st>>>(
+        const int G = 256 / (H / 8);
+        const size_t hsm = sizeof(float) * ((size_t)3 * G * H + (size_t)p.C * 8);
+        KLAUNCH(KC_HEAD, 0.0, 2.0 * R * D * H, st, head_fwd_kernel<<<B, 256, hsm, st>>>(
                     (const bf16_t*)(S + L.Yrow[p.L - 1]), params + p.off_linw(), params + p.off_linb(), (float*)(S + L.cat),
                     (int*)(S + L.arg), logits, B, T, H, D, p.C));
     }
