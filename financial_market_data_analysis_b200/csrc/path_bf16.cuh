@@ -407,18 +407,24 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
                 Xrow = (const bf16_t*)(S + L.Yrow[l - 1]);
             }
         }
-        // 3. input projection for all t, both directions, written in the scan kernel's blocked layout:  W_ih X^T + bias(row)
-        tcg::Params g{};
-        g.M = D * 3 * H; g.N = (int)R; g.K = I; g.batch = 1; g.splitk = 1; g.mode = tcg::OUT_SCAN_BF16;
-        g.blk = tcg::ScanBlk{T, B, H, 3}; g.m_fast = 1;      // the few weight m-tiles share each activation tile via L2
-        g.C = W + L.gi; g.ldc = R; g.bias = (const float*)(S + L.bfold[l]); g.bias_per_row = 1; g.dbg = dbg;
-        TRY(tc_gemm(S + L.Wih[l], D * 3 * H, I, Xrow, R, I, g, st));
+        // 3. input projection for all t, both directions, written in the scan kernel's blocked layout:  W_ih X^T + bias(row).
+        //    With 64 input features (layer 0 of the reference configurations) the projection is formed inside the scan
+        //    kernel instead (tc_scan.cuh, fuse_x): no gi round trip through HBM and no GEMM launch.
+        const bool fuse_x = (I == 64);
+        if (!fuse_x) {
+            tcg::Params g{};
+            g.M = D * 3 * H; g.N = (int)R; g.K = I; g.batch = 1; g.splitk = 1; g.mode = tcg::OUT_SCAN_BF16;
+            g.blk = tcg::ScanBlk{T, B, H, 3}; g.m_fast = 1;      // the few weight m-tiles share each activation tile via L2
+            g.C = W + L.gi; g.ldc = R; g.bias = (const float*)(S + L.bfold[l]); g.bias_per_row = 1; g.dbg = dbg;
+            TRY(tc_gemm(S + L.Wih[l], D * 3 * H, I, Xrow, R, I, g, st));
+        }
         // 4. recurrence
         tcs::FwdParams f{};
         f.B = B; f.T = T; f.H = H; f.D = D;
         f.Wimg = (const bf16_t*)(S + L.Wimg[l]); f.giB = (const bf16_t*)(W + L.gi); f.b_hn = (const float*)(S + L.bhn[l]);
         f.Yrow = (bf16_t*)(S + L.Yrow[l]); f.G = (bf16_t*)(S + L.G[l]); f.YB = (bf16_t*)(S + L.YB[l]);
         f.hn_out = hn ? hn + (int64_t)l * D * B * H : nullptr; f.dbg = dbg;
+        f.fuse_x = fuse_x ? 1 : 0; f.Xrow = Xrow; f.Wih = (const bf16_t*)(S + L.Wih[l]); f.bfold = (const float*)(S + L.bfold[l]);
         {
             ProfScope ps(KC_TC_SCAN_FWD, 2.0 * 3 * H * H * (double)R * D, 0.0, st);
             CUDA_TRY(tcs::launch_fwd(f, st));

@@ -109,12 +109,16 @@ constexpr int NSB = 3;                    // backward input ring depth
 constexpr int BWD_STAGE = G_BLOCK + YB_BLOCK + DY_BLOCK;
 constexpr int HEAD_CONST = 3 * 256 * 32;   // top layer: per-thread davg/T, dmax, argmax (8 values each)
 
-static inline size_t fwd_smem_bytes(int H) {
+constexpr int NSX = 8;                    // fused input projection: x-tile ring depth
+constexpr int X_TILE = NB * 128;          // one [16 rows x 64 features] bf16 tile, K-major / 128B swizzle (2 KB)
+constexpr int WX_TILE = UNITS * 128;      // n-gate rows of W_ih of this CTA: [128 units x 64 features] (16 KB)
+static inline size_t fwd_smem_bytes(int H, bool fuse_x = false) {
     const int KC = H / 64;
+    if (fuse_x) return (size_t)2 * KC * H_CHUNK + (size_t)NSX * X_TILE + WX_TILE + 1024 + 256;
     return (size_t)2 * KC * H_CHUNK + (size_t)NSF * GI_BLOCK + 1024 + 256;
 }
-constexpr uint32_t FWD_A_COL = 64;        // accumulators in columns [0, 48), weights from column 64
-__host__ __device__ static inline uint32_t fwd_tmem_cols(int H) { return 64 + 3 * H / 2 <= 256 ? 256u : 512u; }
+constexpr uint32_t FWD_A_COL = 64;        // accumulators in columns [0, 64): r, z, W_hn h, (fused: W_in x); weights from column 64
+__host__ __device__ static inline uint32_t fwd_tmem_cols(int H, bool fuse_x = false) { return (64 + 3 * H / 2 + (fuse_x ? 64 : 0)) <= 256 ? 256u : 512u; }
 
 struct FwdParams {
     int B, T, H, D;
@@ -126,7 +130,14 @@ struct FwdParams {
     __nv_bfloat16* YB;
     float* hn_out;                // [D][B][H] fp32, nullable
     unsigned int* dbg;
+    // fused input projection (layer 0, n_features == 64): gi_t = W_ih x_t + b is formed by the same tensor pipe between
+    // the recurrent products (it is idle while the epilogue works), giB is not read
+    int fuse_x;
+    const __nv_bfloat16* Xrow;    // [R][64] time-major input rows
+    const __nv_bfloat16* Wih;     // [D*3H][64] (rows r|z|n of direction d at d*3H)
+    const float* bfold;           // [D*3H]  b_ih (+ b_hh for r, z)
     CUtensorMap tmY;              // Yrow as [R rows][D*H], box 64 x 16, 128B swizzle (filled by launch_fwd)
+    CUtensorMap tmX, tmW;         // fused: Xrow box 64 x 16, Wih box 64 x 128 (filled by launch_fwd)
 #ifdef BIGRU_SCAN_TIMING
     unsigned long long* ts;       // bring-up only: clock64 stamps of CTA 0, steps [64, 72), 16 slots per step
 #endif
@@ -135,7 +146,7 @@ struct FwdParams {
 // One group of K chunks (NCH x 64 columns of h) of all three gates, fully unrolled: every operand address is a base
 // that is fixed for the step plus a compile-time constant, so the 12*NCH tcgen05.mma issue back to back (~9 cycles
 // each; a rolled loop with run-time descriptors costs ~26).
-template <int H, int NCH, bool FIRST>
+template <int H, int NCH, bool FIRST, bool FX = false>
 __device__ __forceinline__ void fwd_issue_group(uint32_t tmem_d, uint32_t tmem_a_grp, uint64_t desc_grp) {
     constexpr uint32_t idesc = tc::umma_idesc_bf16(UNITS, NB);
 #pragma unroll
@@ -145,26 +156,46 @@ __device__ __forceinline__ void fwd_issue_group(uint32_t tmem_d, uint32_t tmem_a
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)       // K = 16 bf16 = 8 TMEM columns of A, 32 B of B
                 umma_bf16_ts(tmem_d + (uint32_t)(g * NB), tmem_a_grp + (uint32_t)(g * (H / 2) + (u * 4 + kk) * 8),
-                             desc_grp + (uint64_t)(u * (H_CHUNK >> 4) + 2 * kk), idesc, (FIRST && u == 0 && kk == 0) ? 0u : 1u);
+                             desc_grp + (uint64_t)(u * (H_CHUNK >> 4) + 2 * kk), idesc,
+                             (FIRST && u == 0 && kk == 0 && (!FX || g == 2)) ? 0u : 1u);
         }
     }
 }
+// fused input projection of one step: D_r, D_z = W_ir x, W_iz x (A in tensor memory, columns xw_col..), D_nx = W_in x
+// (A in shared memory: tensor memory is full) - 12 MMAs, all overwrite their accumulators
+__device__ __forceinline__ void fwd_issue_x(uint32_t tmem, uint32_t xw_col, uint64_t desc_wn, uint64_t desc_x) {
+    constexpr uint32_t idesc = tc::umma_idesc_bf16(UNITS, NB);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+            umma_bf16_ts(tmem + (uint32_t)(g * NB), tmem + xw_col + (uint32_t)(g * 32 + kk * 8), desc_x + (uint64_t)(2 * kk), idesc, kk ? 1u : 0u);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+        tc::umma_bf16(tmem + 3 * NB, desc_wn + (uint64_t)(2 * kk), desc_x + (uint64_t)(2 * kk), idesc, kk ? 1u : 0u);
+}
 
-template <int H>
+template <int H, bool FX>
 __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int KC = H / 64, CS = H / UNITS, MYCH = UNITS / 64;
     const int B = p.B, T = p.T, D = p.D;
     uint8_t* sH = smem;                                    // [2][KC][H_CHUNK]  h operand tiles
-    uint8_t* sIn = sH + (size_t)2 * KC * H_CHUNK;          // [NSF][GI_BLOCK]   prefetched gi blocks
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + (size_t)NSF * GI_BLOCK);
+    uint8_t* sIn = sH + (size_t)2 * KC * H_CHUNK;          // [NSF][GI_BLOCK] prefetched gi blocks, or (FX) [NSX][X_TILE] x tiles + W_in tile
+    uint8_t* sWn = sIn + (size_t)NSX * X_TILE;             // FX only
+    constexpr int NS = FX ? NSX : NSF;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(FX ? sWn + WX_TILE : sIn + (size_t)NSF * GI_BLOCK);
     uint64_t* h_full = bars;           // [2]  the peer's h chunk landed (tx bytes of its st.async stores), armed by the control thread
     uint64_t* mma_done = bars + 2;
+    uint64_t* acc_free = bars + 3;     // FX: the epilogue has read the accumulators of this step (one arrival per warp)
+    uint64_t* w_full = bars + 4;       // FX: W_in tile landed
     uint64_t* epi_done = bars + 5;     // one arrival per epilogue warp: local h chunk written
-    uint64_t* in_full = bars + 6;      // [NSF]
-    uint64_t* in_empty = bars + 6 + NSF;   // [NSF]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * NSF);
+    uint64_t* in_full = bars + 6;      // [NS]
+    uint64_t* in_empty = bars + 6 + NS;    // [NS]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * NS);
+    constexpr uint32_t XW_COL = FWD_A_COL + 3 * H / 2;     // FX: W_ir | W_iz of this CTA's units, 32 columns each
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t c = CS > 1 ? tc::cluster_ctarank() : 0u;
@@ -177,11 +208,13 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_c
         tc::mbar_init(&h_full[0], 1);
         tc::mbar_init(&h_full[1], 1);
         tc::mbar_init(mma_done, 1);
+        tc::mbar_init(acc_free, EPI_WARPS);
+        tc::mbar_init(w_full, 1);
         tc::mbar_init(epi_done, EPI_WARPS);
-        for (int i = 0; i < NSF; ++i) { tc::mbar_init(&in_full[i], 1); tc::mbar_init(&in_empty[i], EPI_WARPS); }
+        for (int i = 0; i < NS; ++i) { tc::mbar_init(&in_full[i], 1); tc::mbar_init(&in_empty[i], FX ? 1 : EPI_WARPS); }
         tc::fence_mbar_init();
     }
-    if (warp == EPI_WARPS) tc::tmem_alloc(tmem_slot, fwd_tmem_cols(H));
+    if (warp == EPI_WARPS) tc::tmem_alloc(tmem_slot, fwd_tmem_cols(H, FX));
     tc::tcgen05_fence_before();
     __syncthreads();
     if (CS > 1) tc::cluster_sync_all();        // every CTA's barriers exist before any peer signals them
@@ -191,11 +224,35 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_c
     // W_hh slice of this CTA -> tensor memory (stays there for all T steps)
     if (warp < EPI_WARPS)
         load_weights_to_tmem(p.Wimg + ((size_t)d * CS + c) * UNITS * 3 * H, 3 * H, tmem, FWD_A_COL, warp, lane);
+    if (FX && warp < EPI_WARPS) {
+        // W_ir (warps 0-3) / W_iz (warps 4-7) rows of this CTA's units -> 32 columns each: lane = unit, 64 bf16 = one tcgen05.st
+        const int q = warp & 3, g = warp >> 2;
+        const uint4* src = reinterpret_cast<const uint4*>(p.Wih + ((size_t)d * 3 * H + (size_t)g * H + (size_t)c * UNITS + q * 32 + lane) * 64);
+        uint32_t v[32];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const uint4 u = src[k]; v[4 * k] = u.x; v[4 * k + 1] = u.y; v[4 * k + 2] = u.z; v[4 * k + 3] = u.w; }
+        tmem_st32(tmem + ((uint32_t)(q * 32) << 16) + XW_COL + (uint32_t)(g * 32), v);
+        tmem_st_wait();
+    }
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
 
-    if (warp == EPI_WARPS + 1) {
+    if (FX && warp == EPI_WARPS + 1) {
+        // ---- fused projection: W_in tile once, then one x tile (2 KB, TMA box 64 x 16 -> UMMA K-major layout) per step
+        if (tc::elect_one()) {
+            bool ok = true;
+            tc::mbar_arrive_expect_tx(w_full, WX_TILE);
+            tc::tma_load_2d(sWn, &p.tmW, w_full, 0, d * 3 * H + 2 * H + (int)c * UNITS);
+            for (int s = 0; s < T; ++s) {
+                const int st = s % NSX;
+                if (s >= NSX && ok) ok = tc::mbar_wait(&in_empty[st], ((s / NSX) - 1) & 1, p.dbg, 0x300 + (s & 0xff));
+                const int t = d == 0 ? s : T - 1 - s;
+                tc::mbar_arrive_expect_tx(&in_full[st], X_TILE);
+                tc::tma_load_2d(sIn + (size_t)st * X_TILE, &p.tmX, &in_full[st], 0, t * B + tile * NB);
+            }
+        }
+    } else if (warp == EPI_WARPS + 1) {
         // ---- input prefetch: one bulk copy (12 KB) per step into the ring, up to NSF steps ahead
         if (tc::elect_one()) {
             bool ok = true;
@@ -231,23 +288,40 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_c
             const uint64_t d_loc0 = tc::umma_desc_k_sw128(hb0 + (uint32_t)c * chunk_bytes_mine);
             const uint64_t d_rem0 = tc::umma_desc_k_sw128(hb0 + (uint32_t)(1 - (int)c) * chunk_bytes_mine);
             constexpr uint64_t BUF_DESC = (uint64_t)((KC * H_CHUNK) >> 4);        // descriptor distance of the two h buffers
-            for (int s = 1; s < T; ++s) {                  // after a watchdog hit: keep signalling, stop waiting
+            uint64_t desc_wn = 0, desc_x0 = 0;
+            if (FX) {
+                desc_wn = tc::umma_desc_k_sw128(tc::smem_u32(sWn));
+                desc_x0 = tc::umma_desc_k_sw128(tc::smem_u32(sIn));
+                if (ok) ok = tc::mbar_wait(w_full, 0, p.dbg, 0xb00);
+            }
+            for (int s = FX ? 0 : 1; s < T; ++s) {         // after a watchdog hit: keep signalling, stop waiting
                 const int pb = (s - 1) & 1;
+                if (FX) {
+                    // the input projection of step s goes into the accumulators as soon as the epilogue of step s-1 has
+                    // read them, and runs while that epilogue does its gate math
+                    const int st = s % NSX;
+                    if (s > 0 && ok) ok = tc::mbar_wait(acc_free, (s - 1) & 1, p.dbg, 0xc00 + (s & 0xff));
+                    if (ok) ok = tc::mbar_wait(&in_full[st], (s / NSX) & 1, p.dbg, 0xd00 + (s & 0xff));
+                    tc::tcgen05_fence_after();
+                    fwd_issue_x(tmem, XW_COL, desc_wn, desc_x0 + (uint64_t)(st * (X_TILE >> 4)));
+                    tc::umma_commit(&in_empty[st]);        // the x tile may be refilled when these MMAs have retired
+                    if (s == 0) { tc::umma_commit(mma_done); continue; }      // h_{-1} = 0: no recurrent product
+                }
                 if (ok) ok = tc::mbar_wait(epi_done, (s - 1) & 1, p.dbg, 0x400 + (s & 0xff));
                 SCAN_TS(0);
                 tc::tcgen05_fence_after();
                 if (CS > 1) {
                     // the local group's MMAs are issued right away and run while the peer's chunks (written straight into
                     // this CTA's operand tile by the peer's epilogue threads) are still in flight
-                    fwd_issue_group<H, MYCH, true>(tmem, a_loc, d_loc0 + (pb ? BUF_DESC : 0));
+                    fwd_issue_group<H, MYCH, true, FX>(tmem, a_loc, d_loc0 + (pb ? BUF_DESC : 0));
                     SCAN_TS(1);
                     if (ok) ok = tc::mbar_wait(&h_full[pb], ((s - 1) >> 1) & 1, p.dbg, 0x500 + (s & 0xff));
                     SCAN_TS(2);
                     if (s + 1 < T) tc::mbar_arrive_expect_tx(&h_full[s & 1], (uint32_t)(CS - 1) * chunk_bytes_mine);
                     tc::tcgen05_fence_after();
-                    fwd_issue_group<H, MYCH, false>(tmem, a_rem, d_rem0 + (pb ? BUF_DESC : 0));
+                    fwd_issue_group<H, MYCH, false, FX>(tmem, a_rem, d_rem0 + (pb ? BUF_DESC : 0));
                 } else {
-                    fwd_issue_group<H, KC, true>(tmem, a_loc, d_loc0 + (pb ? BUF_DESC : 0));
+                    fwd_issue_group<H, KC, true, FX>(tmem, a_loc, d_loc0 + (pb ? BUF_DESC : 0));
                 }
                 tc::tma_store_wait_read();                // the tile stored two steps ago is re-written after this commit
                 tc::umma_commit(mma_done);
@@ -268,6 +342,8 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_c
         const int col0 = half * 8;
         const int tid = threadIdx.x;
         const float bhn = p.b_hn[d * H + unit];
+        const float bx_r = FX ? p.bfold[d * 3 * H + unit] : 0.f, bx_z = FX ? p.bfold[d * 3 * H + H + unit] : 0.f,
+                    bx_n = FX ? p.bfold[d * 3 * H + 2 * H + unit] : 0.f;
         float hprev[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) hprev[i] = 0.f;
@@ -275,9 +351,12 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_c
         for (int s = 0; s < T; ++s) {
             const int t = d == 0 ? s : T - 1 - s;
             const size_t blk = blk_index(d, tile, t, (int)c, ntiles, T, CS);
-            // this step's gi from the prefetch ring
+            // this step's gi: from the prefetch ring, or (FX) bias now + W_i x from the accumulators below
             float gr[8], gz[8], gn[8];
-            {
+            if (FX) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { gr[i] = bx_r; gz[i] = bx_z; }
+            } else {
                 const int st = s % NSF;
                 if (tid == 0) SCAN_TS(5);
                 if (ok) ok = tc::mbar_wait(&in_full[st], (s / NSF) & 1, p.dbg, 0x200 + (s & 0xff));
@@ -298,16 +377,30 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_c
             const int buf = s & 1;
             uint8_t* hb = sH + (size_t)buf * KC * H_CHUNK + (size_t)(unit >> 6) * H_CHUNK;
             const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + col0;
-            const uint32_t par = (s - 1) & 1;
+            const uint32_t par = FX ? (uint32_t)(s & 1) : (uint32_t)((s - 1) & 1);
             float r8[8], z8[8], an[8];
-            if (s > 0) {
+            if (FX || s > 0) {
                 if (tid == 0) SCAN_TS(6);
                 if (ok) ok = tc::mbar_wait(mma_done, par, p.dbg, 0x600 + (s & 0xff));
                 if (tid == 0) SCAN_TS(7);
                 if (tid == 224) SCAN_TS(12);
                 tc::tcgen05_fence_after();
-                tmem_ld8(ta, r8); tmem_ld8(ta + NB, z8); tmem_ld8(ta + 2 * NB, an);
+                tmem_ld8(ta, r8); tmem_ld8(ta + NB, z8);
+                if (!FX || s > 0) tmem_ld8(ta + 2 * NB, an);
+                if (FX) tmem_ld8(ta + 3 * NB, gn);
                 tc::tmem_ld_wait();
+                if (FX) {
+                    // accumulators read: the control thread may start the input projection of the next step
+                    tc::tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(acc_free);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) gn[i] += bx_n;
+                    if (s == 0) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) an[i] = 0.f;
+                    }
+                }
                 if (tid == 0) SCAN_TS(8);
             } else {
 #pragma unroll
@@ -367,7 +460,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_c
     tc::tcgen05_fence_before();
     __syncthreads();
     if (CS > 1) tc::cluster_sync_all();        // no CTA leaves while a peer may still target its smem
-    if (warp == EPI_WARPS) tc::tmem_dealloc(tmem, fwd_tmem_cols(H));
+    if (warp == EPI_WARPS) tc::tmem_dealloc(tmem, fwd_tmem_cols(H, FX));
 }
 
 static inline cudaError_t launch_fwd(const FwdParams& p_in, cudaStream_t st) {
@@ -380,13 +473,24 @@ static inline cudaError_t launch_fwd(const FwdParams& p_in, cudaStream_t st) {
     }
     const int CS = p.H / UNITS;
     if (p.H != 128 && p.H != 256) return cudaErrorInvalidValue;
-    const size_t smem = fwd_smem_bytes(p.H);
-    void (*kern)(FwdParams) = p.H == 128 ? gru_scan_fwd_kernel<128> : gru_scan_fwd_kernel<256>;
-    static bool attr[2] = {false, false};
-    if (!attr[CS - 1]) {
+    const bool fx = p.fuse_x != 0;
+    if (fx) {
+        const uint64_t dx[2] = {64u, (uint64_t)p.T * p.B};
+        const uint64_t sx[1] = {64u * 2};
+        const uint32_t bx[2] = {64u, (uint32_t)NB};
+        const uint64_t dw[2] = {64u, (uint64_t)p.D * 3 * p.H};
+        const uint32_t bw[2] = {64u, (uint32_t)UNITS};
+        if (make_tmap_bf16(&p.tmX, p.Xrow, 2, dx, sx, bx) != 0 || make_tmap_bf16(&p.tmW, p.Wih, 2, dw, sx, bw) != 0) return cudaErrorInvalidValue;
+    }
+    const size_t smem = fwd_smem_bytes(p.H, fx);
+    void (*kern)(FwdParams) = p.H == 128 ? (fx ? gru_scan_fwd_kernel<128, true> : gru_scan_fwd_kernel<128, false>)
+                                         : (fx ? gru_scan_fwd_kernel<256, true> : gru_scan_fwd_kernel<256, false>);
+    static bool attr[4] = {false, false, false, false};
+    const int ai = (CS - 1) * 2 + (fx ? 1 : 0);
+    if (!attr[ai]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr[CS - 1] = true;
+        attr[ai] = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(p.D * (p.B / NB) * CS));

@@ -9,7 +9,7 @@
 static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
 static float frand() { return (rand() % 20001 - 10000) / 10000.f; }
 
-static int run_case(int B, int T, int H, int D, int reps) {
+static int run_case(int B, int T, int H, int D, int reps, int fuse = 0) {
     const int CS = H / 128; const long R = (long)T * B;
     srand(B + 3 * T + H);
     std::vector<float> whh((size_t)D * 3 * H * H), bhn((size_t)D * H), gi((size_t)R * D * 3 * H);
@@ -17,6 +17,28 @@ static int run_case(int B, int T, int H, int D, int reps) {
     for (auto& v : whh) v = frand() * sc;
     for (auto& v : bhn) v = frand() * sc;
     for (auto& v : gi) v = bf(frand() * 1.5f);
+    // fused input projection: gi = W_ih x + b is formed inside the kernel from x [R][64], W_ih [D*3H][64], b [D*3H]
+    std::vector<float> xs, wih, bfold;
+    __nv_bfloat16 *d_x = nullptr, *d_wih = nullptr; float* d_bfold = nullptr;
+    if (fuse) {
+        xs.resize((size_t)R * 64); wih.resize((size_t)D * 3 * H * 64); bfold.resize((size_t)D * 3 * H);
+        for (auto& v : xs) v = bf(frand());
+        for (auto& v : wih) v = bf(frand() * 0.2f);
+        for (auto& v : bfold) v = frand() * 0.3f;
+        for (long r = 0; r < R; ++r)
+            for (int q = 0; q < D * 3 * H; ++q) {
+                double a = bfold[q];
+                for (int k = 0; k < 64; ++k) a += (double)wih[(size_t)q * 64 + k] * xs[(size_t)r * 64 + k];
+                gi[(size_t)r * D * 3 * H + q] = (float)a;
+            }
+        std::vector<__nv_bfloat16> xb(xs.size()), wb(wih.size());
+        for (size_t i = 0; i < xs.size(); ++i) xb[i] = __float2bfloat16(xs[i]);
+        for (size_t i = 0; i < wih.size(); ++i) wb[i] = __float2bfloat16(wih[i]);
+        CK(cudaMalloc(&d_x, xb.size() * 2)); CK(cudaMalloc(&d_wih, wb.size() * 2)); CK(cudaMalloc(&d_bfold, bfold.size() * 4));
+        CK(cudaMemcpy(d_x, xb.data(), xb.size() * 2, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_wih, wb.data(), wb.size() * 2, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_bfold, bfold.data(), bfold.size() * 4, cudaMemcpyHostToDevice));
+    }
     float* d_whh; float* d_bhn; __nv_bfloat16 *d_img, *d_gi, *d_Y, *d_YT, *d_G; float* d_hn; unsigned int* dbg;
     const size_t img_elems = (size_t)D * 3 * H * H;
     CK(cudaMalloc(&d_whh, whh.size() * 4)); CK(cudaMalloc(&d_bhn, bhn.size() * 4)); CK(cudaMalloc(&d_img, img_elems * 2));
@@ -43,6 +65,7 @@ static int run_case(int B, int T, int H, int D, int reps) {
     p.B = B; p.T = T; p.H = H; p.D = D; p.Wimg = d_img; p.giB = d_gi; p.b_hn = d_bhn; p.Yrow = d_Y; p.G = d_G;
     __nv_bfloat16* d_YB; CK(cudaMalloc(&d_YB, (size_t)R * D * H * 2)); p.YB = d_YB;
     p.hn_out = d_hn; p.dbg = dbg;
+    p.fuse_x = fuse; p.Xrow = d_x; p.Wih = d_wih; p.bfold = d_bfold;
 #ifdef BIGRU_SCAN_TIMING
     unsigned long long* d_ts; CK(cudaMalloc(&d_ts, 8 * 16 * 8)); CK(cudaMemset(d_ts, 0, 8 * 16 * 8)); p.ts = d_ts;
 #endif
@@ -123,8 +146,8 @@ static int run_case(int B, int T, int H, int D, int reps) {
             for (int j = 0; j < H; ++j) eHn = fmax(eHn, fabs(hs[j] - hn[((size_t)d * B + b) * H + j]));
         }
     const bool pass = h[0] == 0 && eY < 2e-2 && eYT < 2e-2 && eG < 3e-2 && eHn < 2e-2;
-    printf("%s scan_fwd B=%d T=%d H=%d D=%d (cluster %d, grid %d): errY=%.2e errYT=%.2e errG=%.2e errHn=%.2e dbg=%x blk=%u thr=%u a=%u  %.3f ms (%.2f us/step)\n",
-           pass ? "PASS" : "FAIL", B, T, H, D, CS, D * (B / 16) * CS, eY, eYT, eG, eHn, h[0], h[1], h[2], h[3], ms, ms * 1e3 / T);
+    printf("%s scan_fwd%s B=%d T=%d H=%d D=%d (cluster %d, grid %d): errY=%.2e errYT=%.2e errG=%.2e errHn=%.2e dbg=%x blk=%u thr=%u a=%u  %.3f ms (%.2f us/step)\n",
+           pass ? "PASS" : "FAIL", fuse ? "+x" : "", B, T, H, D, CS, D * (B / 16) * CS, eY, eYT, eG, eHn, h[0], h[1], h[2], h[3], ms, ms * 1e3 / T);
     cudaFree(d_whh); cudaFree(d_bhn); cudaFree(d_img); cudaFree(d_gi); cudaFree(d_Y); cudaFree(d_YT); cudaFree(d_G); cudaFree(d_hn); cudaFree(dbg);
     return pass ? 0 : 2;
 }
@@ -140,6 +163,11 @@ int main() {
     bad += run_case(64, 9, 256, 2, 0);
     bad += run_case(512, 128, 256, 2, 10);
     bad += run_case(512, 64, 128, 2, 10);
+    bad += run_case(16, 1, 128, 1, 0, 1);
+    bad += run_case(16, 3, 128, 1, 0, 1);
+    bad += run_case(32, 12, 256, 2, 0, 1);
+    bad += run_case(512, 128, 256, 2, 10, 1);
+    bad += run_case(512, 64, 128, 2, 10, 1);
     printf(bad ? "SOME FAILED\n" : "ALL PASSED\n");
     return bad ? 1 : 0;
 }
