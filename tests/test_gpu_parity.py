@@ -170,6 +170,8 @@ SWEEP = [  # B, T, F, H, L, C, bidir, h0
     (64, 16, 32, 128, 2, 3, True, False),
     (48, 7, 40, 256, 2, 3, True, False),
     (32, 5, 8, 128, 1, 2, False, False),
+    (32, 9, 64, 128, 2, 3, True, False),      # F == 64: layer-0 input projection fused into the forward scan (bf16 path)
+    (16, 5, 64, 256, 1, 2, False, False),
 ]
 
 
