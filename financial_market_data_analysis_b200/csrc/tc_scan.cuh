@@ -554,6 +554,9 @@ struct BwdParams {
     float* db_hh;
     int64_t dir_stride;
     unsigned int* dbg;
+#ifdef BIGRU_SCAN_TIMING
+    unsigned long long* ts;
+#endif
 };
 
 // K chunks [u0, u0 + NCH) of each of the three gate blocks of the [16 x 3H] dgh tile, fully unrolled (see fwd_issue_group)
@@ -672,10 +675,13 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
             for (int s = 1; s < T; ++s) {
                 const int pb = (s - 1) & 1;
                 if (ok) ok = tc::mbar_wait(epi_done, (s - 1) & 1, p.dbg, 0x700 + (s & 0xff));
+                SCAN_TS(0);
                 tc::tcgen05_fence_after();
                 if (CS > 1) {
                     bwd_issue_group<H, MYCH, true>(tmem, a_loc, d_loc0 + (pb ? BUF_DESC : 0));
+                    SCAN_TS(1);
                     if (ok) ok = tc::mbar_wait(&d_full[pb], ((s - 1) >> 1) & 1, p.dbg, 0x800 + (s & 0xff));
+                    SCAN_TS(2);
                     if (s + 1 < T) tc::mbar_arrive_expect_tx(&d_full[s & 1], (uint32_t)(CS - 1) * 3 * gate_bytes_mine);
                     tc::tcgen05_fence_after();
                     bwd_issue_group<H, MYCH, false>(tmem, a_rem, d_rem0 + (pb ? BUF_DESC : 0));
@@ -684,6 +690,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
                 }
                 tc::tma_store_wait_read();
                 tc::umma_commit(mma_done);
+                SCAN_TS(3);
                 if (ok) ok = tc::mbar_wait(st_done, (s - 1) & 1, p.dbg, 0xa00 + (s & 0xff));
                 store_tile(s - 1);
             }
@@ -728,7 +735,9 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
             float vr[8], vz[8], vn[8], vhn[8], vhp[8], vdy[8];
             {
                 const int st = s % NSB;
+                if (tid == 0) SCAN_TS(5);
                 if (ok) ok = tc::mbar_wait(&in_full[st], (s / NSB) & 1, p.dbg, 0x200 + (s & 0xff));
+                if (tid == 0) SCAN_TS(6);
                 const uint8_t* base = sIn + (size_t)st * BWD_STAGE;
                 const uint4* gp = reinterpret_cast<const uint4*>(base) + tid;
                 const uint4 u0 = gp[0], u1 = gp[256], u2 = gp[512], u3 = gp[768];
@@ -779,10 +788,13 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
             }
             float acc[8];
             if (s > 0) {
+                if (tid == 0) SCAN_TS(4);
                 if (ok) ok = tc::mbar_wait(mma_done, (s - 1) & 1, p.dbg, 0x900 + (s & 0xff));
+                if (tid == 0) SCAN_TS(7);
                 tc::tcgen05_fence_after();
                 tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + col0, acc);
                 tc::tmem_ld_wait();
+                if (tid == 0) SCAN_TS(8);
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -806,6 +818,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
             }
             // hand dgh_s to the tensor pipe (the step chain): own chunks -> peer with st.async (see forward kernel), then
             // the local arrival; the n-gate tile (TMA store only) and the bias sums follow, off the chain
+            if (tid == 0) SCAN_TS(9);
             tc::tcgen05_fence_before();
             if (CS > 1 && s + 1 < T) {
                 __syncwarp();
@@ -822,6 +835,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(epi_done);
+            if (tid == 0) SCAN_TS(10);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
                 *reinterpret_cast<__nv_bfloat16*>(sN + (size_t)(buf * MYCH + ((unit & (UNITS - 1)) >> 6)) * H_CHUNK + tc::sw128_offset(col0 + i, unit & 63)) = __float2bfloat16(dan[i]);
@@ -830,6 +844,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
             if (lane == 0) tc::mbar_arrive(st_done);
 #pragma unroll
             for (int i = 0; i < 8; ++i) { sb_r += dar[i]; sb_z += daz[i]; sb_n += dan[i]; sb_nr += danr[i]; }
+            if (tid == 0) SCAN_TS(11);
         }
         // bias gradients: sum the 8 columns of this thread; the two column halves and all tiles add atomically
         float* dbi = p.db_ih + (int64_t)d * p.dir_stride;

@@ -152,6 +152,51 @@ static int run_case(int B, int T, int H, int D, int reps, int fuse = 0) {
     return pass ? 0 : 2;
 }
 
+// timing-only run of the backward scan (zero-filled inputs: there is no data-dependent control flow)
+static int run_bwd_timing(int B, int T, int H, int D, int top) {
+    const long R = (long)T * B;
+    __nv_bfloat16 *WT, *G, *YB, *dgi, *dghn; float *dYB, *db, *dlog, *linw; int* arg; unsigned int* dbg;
+    CK(cudaMalloc(&WT, (size_t)D * 3 * H * H * 2)); CK(cudaMemset(WT, 0, (size_t)D * 3 * H * H * 2));
+    CK(cudaMalloc(&G, (size_t)R * D * 4 * H * 2)); CK(cudaMemset(G, 0, (size_t)R * D * 4 * H * 2));
+    CK(cudaMalloc(&YB, (size_t)R * D * H * 2)); CK(cudaMemset(YB, 0, (size_t)R * D * H * 2));
+    CK(cudaMalloc(&dYB, (size_t)R * D * H * 4)); CK(cudaMemset(dYB, 0, (size_t)R * D * H * 4));
+    CK(cudaMalloc(&dgi, (size_t)R * D * 3 * H * 2)); CK(cudaMalloc(&dghn, (size_t)R * D * H * 2));
+    CK(cudaMalloc(&db, (size_t)4 * D * 3 * H * 4)); CK(cudaMemset(db, 0, (size_t)4 * D * 3 * H * 4));
+    CK(cudaMalloc(&dlog, (size_t)B * 3 * 4)); CK(cudaMemset(dlog, 0, (size_t)B * 3 * 4));
+    CK(cudaMalloc(&linw, (size_t)3 * 3 * H * 4)); CK(cudaMemset(linw, 0, (size_t)3 * 3 * H * 4));
+    CK(cudaMalloc(&arg, (size_t)B * H * 4)); CK(cudaMemset(arg, 0, (size_t)B * H * 4));
+    CK(cudaMalloc(&dbg, 64)); CK(cudaMemset(dbg, 0, 64));
+    tcs::BwdParams p{};
+    p.B = B; p.T = T; p.H = H; p.D = D; p.WTimg = WT; p.G = G; p.YB = YB; p.dYB = dYB;
+    if (top) { p.dlogits = dlog; p.lin_w = linw; p.arg = arg; p.C = 3; }
+    p.dgi_row = dgi; p.dghn_row = dghn; p.db_ih = db; p.db_hh = db + (size_t)2 * D * 3 * H; p.dir_stride = 3 * H; p.dbg = dbg;
+#ifdef BIGRU_SCAN_TIMING
+    unsigned long long* d_ts; CK(cudaMalloc(&d_ts, 8 * 16 * 8)); CK(cudaMemset(d_ts, 0, 8 * 16 * 8)); p.ts = d_ts;
+#endif
+    CK(tcs::launch_bwd(p, 0)); CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    for (int i = 0; i < 10; ++i) CK(tcs::launch_bwd(p, 0));
+    cudaEventRecord(e1); CK(cudaDeviceSynchronize());
+    float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 10;
+    unsigned int h[8]; CK(cudaMemcpy(h, dbg, 32, cudaMemcpyDeviceToHost));
+    printf("scan_bwd timing B=%d T=%d H=%d D=%d top=%d: %.3f ms (%.2f us/step) dbg=%x\n", B, T, H, D, top, ms, ms * 1e3 / T, h[0]);
+#ifdef BIGRU_SCAN_TIMING
+    if (T >= 80) {
+        unsigned long long ts[8 * 16]; CK(cudaMemcpy(ts, d_ts, sizeof(ts), cudaMemcpyDeviceToHost));
+        printf("  bwd cycles: step | c:wake->loc | loc->dfull | dfull->commit || e: commit->wake | ld | math+sts | st.async+fence+arrive | arrive->c.wake | tail | total  [in wait %s, mma wait]\n", "");
+        for (int k = 1; k < 7; ++k) {
+            const unsigned long long* a = ts + k * 16; const unsigned long long* nx = ts + (k + 1) * 16;
+            printf("   s=%d | %5lld | %5lld | %5lld || %5lld | %5lld | %5lld | %5lld | %5lld | %5lld | %5lld  [%lld, %lld]\n", 64 + k,
+                   (long long)(a[1] - a[0]), (long long)(a[2] - a[1]), (long long)(a[3] - a[2]), (long long)(a[7] - a[3]), (long long)(a[8] - a[7]),
+                   (long long)(a[9] - a[8]), (long long)(a[10] - a[9]), (long long)(nx[0] - a[10]), (long long)(a[11] - a[10]), (long long)(nx[0] - a[0]),
+                   (long long)(a[6] - a[5]), (long long)(a[7] - a[4]));
+        }
+    }
+#endif
+    return h[0] ? 1 : 0;
+}
+
 int main() {
     setvbuf(stdout, NULL, _IONBF, 0);
     int bad = 0;
@@ -168,6 +213,8 @@ int main() {
     bad += run_case(32, 12, 256, 2, 0, 1);
     bad += run_case(512, 128, 256, 2, 10, 1);
     bad += run_case(512, 64, 128, 2, 10, 1);
+    bad += run_bwd_timing(512, 128, 256, 2, 0);
+    bad += run_bwd_timing(512, 128, 256, 2, 1);
     printf(bad ? "SOME FAILED\n" : "ALL PASSED\n");
     return bad ? 1 : 0;
 }
