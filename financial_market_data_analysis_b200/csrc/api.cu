@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "kernels_f32.cuh"
 #include "path_bf16.cuh"
+#include "features.cuh"
 
 #include <cstring>
 #include <new>
@@ -354,6 +355,39 @@ extern "C" int bigru_chunk_minmax(const float* d_table, int64_t N, int F, int64_
     }
     KLAUNCH(KC_GATHER, 0.0, 4.0 * (row_hi - row_lo) * F, (cudaStream_t)stream,
             chunk_minmax_kernel<<<(F + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(d_table, F, row_lo, row_hi, d_min, d_max));
+    return BIGRU_OK;
+}
+
+extern "C" int bigru_window_features(const float* d_close, const float* d_high, const float* d_low, const float* d_volume,
+                                     const float* d_delta, int64_t n, const int* vol_periods, int n_vol, const int* price_periods,
+                                     int n_price, const int* delta_periods, int n_delta, int bb_period, float bb_std, int stochastic,
+                                     float n1, float n2, float* d_out, float* d_targets, int* n_out, void* stream) {
+    if (n_vol < 0 || n_vol > 8 || n_price < 0 || n_price > 8 || n_delta < 0 || n_delta > 8 || bb_period < 0 || n < 0 ||
+        (n_vol && !vol_periods) || (n_price && !price_periods) || (n_delta && !delta_periods)) {
+        bigru_set_error("window_features: bad argument (at most 8 periods per list)");
+        return BIGRU_ERR_ARG;
+    }
+    FeatureCfg cfg{};
+    cfg.n_vol = n_vol; cfg.n_price = n_price; cfg.n_delta = n_delta;
+    for (int i = 0; i < n_vol; ++i) cfg.vol_p[i] = vol_periods[i];
+    for (int i = 0; i < n_price; ++i) cfg.price_p[i] = price_periods[i];
+    for (int i = 0; i < n_delta; ++i) cfg.delta_p[i] = delta_periods[i];
+    for (int i = 0; i < 8; ++i)
+        if ((i < n_vol && cfg.vol_p[i] < 1) || (i < n_price && cfg.price_p[i] < 1) || (i < n_delta && cfg.delta_p[i] < 1)) {
+            bigru_set_error("window_features: periods must be >= 1");
+            return BIGRU_ERR_ARG;
+        }
+    cfg.bb_period = bb_period; cfg.bb_std = bb_std; cfg.stochastic = stochastic ? 1 : 0; cfg.n1 = n1; cfg.n2 = n2;
+    cfg.n_out = (bb_period > 0 ? 2 : 0) + n_vol + n_price + n_delta + (stochastic ? 1 : 0) + 2;
+    if (n_out) *n_out = cfg.n_out;
+    if (!d_out || n == 0) return BIGRU_OK;
+    if (!d_close || !d_high || !d_low || (n_vol && !d_volume) || (n_delta && !d_delta)) {
+        bigru_set_error("window_features: null column");
+        return BIGRU_ERR_ARG;
+    }
+    const unsigned blocks = (unsigned)std::min<int64_t>((n + 127) / 128, 148 * 16);
+    KLAUNCH(KC_GATHER, 0.0, 4.0 * n * (5 + cfg.n_out + 4), (cudaStream_t)stream,
+            window_features_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(d_close, d_high, d_low, d_volume, d_delta, n, cfg, d_out, d_targets));
     return BIGRU_OK;
 }
 

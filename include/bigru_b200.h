@@ -119,6 +119,19 @@ int  bigru_forward_windows(const bigru_plan* plan, const float* d_params, const 
 int  bigru_chunk_minmax(const float* d_table, int64_t N, int F, int64_t row_lo, int64_t row_hi, float* d_min,
                         float* d_max, void* stream);
 
+/* --- SURVEY.md 8(f) N4, the SQL window-function features of the reference (create_database.py:76-190) over the joined
+ *  table's columns (device pointers, n rows, time order): per row, in the order of the reference's join statement
+ *  (create_database.py:239-240): [upper_BB_dist, lower_BB_dist] (bb_period > 0; STD is the population std), vol_MA{p},
+ *  price_MA{p}, delta_MA{p} (AVG over ROWS BETWEEN p-1 PRECEDING AND CURRENT ROW, shorter at the head of the table),
+ *  [stoch] (15-row MIN / MAX of close; NaN = SQL NULL when max == min), ATR (15-row AVG(high - low)), price_change
+ *  (close - LAG(close, 1); NaN on the first row) -> d_out[n][n_out]; and the four targets up1, up2, down1, down2
+ *  (create_database.py:163-185: LEAD(close, 8 / 15) against close +- n1 / n2 * ATR, 0 where the lead is NULL)
+ *  -> d_targets[n][4] (nullable).  At most 8 periods per list.  Returns n_out through *n_out (pass d_out = NULL to query). */
+int  bigru_window_features(const float* d_close, const float* d_high, const float* d_low, const float* d_volume,
+                           const float* d_delta, int64_t n, const int* vol_periods, int n_vol, const int* price_periods,
+                           int n_price, const int* delta_periods, int n_delta, int bb_period, float bb_std,
+                           int stochastic, float n1, float n2, float* d_out, float* d_targets, int* n_out, void* stream);
+
 /* --- train_model/evaluate_model metrics (biGRU_model.py:213-221): pred = sigmoid(logit) > 0.5;
  *  d_counts[0] += #rows with all labels right; [1] += #label mismatches;
  *  [2+3c], [3+3c], [4+3c] += tp, fp, fn of class c.  int64 accumulators, caller zeroes. */

@@ -575,3 +575,61 @@ def test_chunk_statistics_on_gpu_match_sql_path(golden_dir, tmp_path):
         ids, (mn, mx) = cl[i]
         assert np.array_equal(np.array(ids), z[f"chunk{i}_ids"])
         assert np.array_equal(mn.numpy(), z[f"chunk{i}_min"]) and np.array_equal(mx.numpy(), z[f"chunk{i}_max"])
+
+
+# ---- SQL window-function features on the GPU --------------------------------------------------------
+def _market_columns(n, seed=5):
+    rng = np.random.default_rng(seed)
+    close = 2900 + np.cumsum(rng.normal(0, 2.0, n))
+    cols = [close, close + rng.uniform(0.1, 3.0, n), close - rng.uniform(0.1, 3.0, n),
+            rng.integers(100, 50000, n).astype(np.float64), rng.normal(0, 300, n)]
+    return [np.float32(c) for c in cols]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 7, 16, 500, 20000])
+def test_window_features_match_oracle(n):
+    from oracle import features_oracle as fo
+    from financial_market_data_analysis_b200.features import window_features, feature_names
+    cols = _market_columns(n)
+    if n == 500:
+        cols[0][100:140] = cols[0][100]                                       # flat stretch: stochastic max == min -> NULL
+    kw = dict(volume_MA_periods=[6, 20], price_MA_periods=[20], delta_MA_periods=[12], bollinger_bands_period=20,
+              bollinger_bands_std=2, stochastic_oscillator=True)
+    ref_f, ref_t = fo.window_features(*[c.astype(np.float64) for c in cols], **kw)
+    got_f, got_t = window_features(*[torch.from_numpy(c).cuda() for c in cols], **kw)
+    assert got_f.shape == (n, len(feature_names(**kw))) and got_t.shape == (n, 4)
+    g = got_f.cpu().numpy()
+    assert np.array_equal(np.isnan(g), np.isnan(ref_f))                        # SQL NULLs in the same places
+    # double arithmetic rounded once to fp32: differences of large prices keep an absolute error of one fp32 ulp of the price
+    np.testing.assert_allclose(np.nan_to_num(g), np.nan_to_num(ref_f), rtol=2e-6, atol=5e-4)
+    assert np.array_equal(got_t.cpu().numpy(), ref_t)                          # labels are exact
+
+
+@pytest.mark.gpu
+def test_window_features_properties_large():
+    from financial_market_data_analysis_b200.features import window_features
+    n = 2_000_000
+    g = torch.Generator(device="cuda").manual_seed(3)
+    close = 3000 + torch.cumsum(torch.randn(n, device="cuda", generator=g), 0)
+    spread = torch.rand(n, device="cuda", generator=g) + 0.5
+    f, t = window_features(close, close + spread, close - spread, torch.full((n,), 7.0, device="cuda"), torch.zeros(n, device="cuda"))
+    assert torch.all(f[:, 2] == 7) and torch.all(f[:, 3] == 7) and torch.all(f[:, 5] == 0)      # averages of constants
+    assert torch.all((f[:, 0] + f[:, 1]) >= -1e-2)                              # upper + lower distance = 4 * std >= 0
+    s = f[15:, 6]
+    assert torch.all((s >= 0) & (s <= 1) | torch.isnan(s))                      # stochastic oscillator in [0, 1]
+    assert torch.allclose(f[1:, 8], close[1:] - close[:-1], atol=1e-3)          # price change telescopes
+    assert t[-8:, 0].sum() == 0 and t[-15:, 1].sum() == 0 and float((t[:, 0] * t[:, 2]).sum()) == 0   # up and down exclude each other
+
+
+@pytest.mark.gpu
+def test_window_features_errors():
+    from financial_market_data_analysis_b200.features import window_features
+    x = torch.ones(8)
+    with pytest.raises(RuntimeError):
+        window_features(x, x, x, x, x)                                           # CPU tensors: no fallback
+    xc = x.cuda()
+    with pytest.raises(ValueError):
+        window_features(xc, xc, xc, None, xc)                                    # volume MA without the column
+    with pytest.raises(ValueError):
+        window_features(xc, xc, xc, xc, xc, volume_MA_periods=list(range(1, 10)))   # more than 8 periods

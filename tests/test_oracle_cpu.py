@@ -153,3 +153,58 @@ def test_loader_oracle(golden_dir):
         np.testing.assert_array_equal(xg, xb)
     assert lo.window_indices(5, 3) == [(0, 1, 2), (1, 2, 3), (2, 3, 4)]
     assert lo.window_indices(2, 3) == []
+
+
+# ---- window-function features (oracle/features_oracle.py) -----------------------------------------
+def _market(n, seed=5):
+    rng = np.random.default_rng(seed)
+    close = 2900 + np.cumsum(rng.normal(0, 2.0, n))
+    high = close + rng.uniform(0.1, 3.0, n)
+    low = close - rng.uniform(0.1, 3.0, n)
+    volume = rng.integers(100, 50000, n).astype(np.float64)
+    delta = rng.normal(0, 300, n)
+    return [np.float32(v).astype(np.float64) for v in (close, high, low, volume, delta)]
+
+
+def test_features_oracle_against_pandas_rolling():
+    import pandas as pd
+    from oracle import features_oracle as fo
+    close, high, low, volume, delta = _market(300)
+    feats, tgt = fo.window_features(close, high, low, volume, delta)
+    s = pd.Series(close)
+    avg, sd = s.rolling(20, min_periods=1).mean(), s.rolling(20, min_periods=1).std(ddof=0)
+    np.testing.assert_allclose(feats[:, 0], (avg + 2 * sd - s).values, rtol=0, atol=1e-7)
+    np.testing.assert_allclose(feats[:, 1], (s - (avg - 2 * sd)).values, rtol=0, atol=1e-7)
+    np.testing.assert_allclose(feats[:, 2], pd.Series(volume).rolling(6, min_periods=1).mean().values, rtol=1e-12)
+    np.testing.assert_allclose(feats[:, 3], pd.Series(volume).rolling(20, min_periods=1).mean().values, rtol=1e-12)
+    np.testing.assert_allclose(feats[:, 4], avg.values, rtol=1e-12)
+    np.testing.assert_allclose(feats[:, 5], pd.Series(delta).rolling(12, min_periods=1).mean().values, rtol=1e-9, atol=1e-9)
+    mn, mx = s.rolling(15, min_periods=1).min(), s.rolling(15, min_periods=1).max()
+    stoch = ((s - mn) / (mx - mn)).values
+    assert np.isnan(feats[0, 6]) and np.isnan(stoch[0])                       # one-row frame: max == min -> NULL
+    np.testing.assert_allclose(feats[1:, 6], stoch[1:], rtol=1e-12)
+    atr = pd.Series(high - low).rolling(15, min_periods=1).mean().values
+    np.testing.assert_allclose(feats[:, 7], atr, rtol=1e-12)
+    assert np.isnan(feats[0, 8])
+    np.testing.assert_allclose(feats[1:, 8], np.diff(close), rtol=0, atol=0)
+    # targets: LEAD(close, 8 / 15); NULL past the end -> 0
+    p8, p15 = s.shift(-8).values, s.shift(-15).values
+    np.testing.assert_array_equal(tgt[:, 0], np.nan_to_num(p8 >= close + 1.5 * atr, nan=0).astype(float) * ~np.isnan(p8))
+    np.testing.assert_array_equal(tgt[:, 3], (np.where(np.isnan(p15), np.inf, p15) <= close - 3 * atr).astype(float))
+    assert tgt[-8:, 0].sum() == 0 and tgt[-15:, 1].sum() == 0 and tgt[-8:, 2].sum() == 0 and tgt[-15:, 3].sum() == 0
+
+
+def test_features_oracle_hand_rows_and_shapes():
+    from oracle import features_oracle as fo
+    close = np.array([10., 12., 11., 15.]); high = close + 1; low = close - 2
+    feats, tgt = fo.window_features(close, high, low, np.ones(4), np.arange(4.), volume_MA_periods=[2], price_MA_periods=[3],
+                                    delta_MA_periods=[], bollinger_bands_period=2, bollinger_bands_std=1, stochastic_oscillator=True)
+    assert feats.shape == (4, 7) and tgt.shape == (4, 4) and not tgt.any()
+    # row 2: BB over (12, 11): avg 11.5, pop-std 0.5 -> upper 12 - 11 = 1, lower 11 - 11 = 0
+    np.testing.assert_allclose(feats[2, :2], [1.0, 0.0])
+    np.testing.assert_allclose(feats[:, 3], [10, 11, 11, 38 / 3])             # price_MA3 with clipped frames
+    np.testing.assert_allclose(feats[:, 5], [3, 3, 3, 3])                     # ATR: high - low == 3
+    np.testing.assert_allclose(feats[1:, 6], [2, -1, 4])
+    np.testing.assert_allclose(feats[1:, 4], [1.0, 0.5, 1.0])                 # stoch over all rows so far
+    f0, t0 = fo.window_features(np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0))
+    assert f0.shape == (0, 9) and t0.shape == (0, 4)
