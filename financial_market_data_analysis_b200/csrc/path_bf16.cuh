@@ -1,6 +1,6 @@
 // path_bf16.cuh - BIGRU_PREC_BF16: the tensor-core path.
 //   input projections, dX and weight gradients : tc_gemm.cuh  (tcgen05 + TMA, bf16 operands, fp32 accumulate)
-//   recurrences forward / backward              : tc_scan.cuh  (persistent cluster kernels, W_hh resident in smem)
+//   recurrences forward / backward              : tc_scan.cuh  (persistent cluster kernels, W_hh resident in tensor memory)
 //   head, loss glue, optimiser                  : the fp32 kernels of kernels_f32.cuh
 // All activations inside this path are TIME-MAJOR (row r = t*B + b) so that one step of one batch tile is a
 // contiguous block of rows.  Supported: H in {128, 256}, B % 16 == 0, F % 8 == 0, no initial hidden state;
