@@ -385,9 +385,32 @@ extern "C" int bigru_window_features(const float* d_close, const float* d_high, 
         bigru_set_error("window_features: null column");
         return BIGRU_ERR_ARG;
     }
-    const unsigned blocks = (unsigned)std::min<int64_t>((n + 127) / 128, 148 * 16);
-    KLAUNCH(KC_GATHER, 0.0, 4.0 * n * (5 + cfg.n_out + 4), (cudaStream_t)stream,
-            window_features_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(d_close, d_high, d_low, d_volume, d_delta, n, cfg, d_out, d_targets));
+    int halo = 14;
+    for (int i = 0; i < n_vol; ++i) halo = std::max(halo, cfg.vol_p[i] - 1);
+    for (int i = 0; i < n_price; ++i) halo = std::max(halo, cfg.price_p[i] - 1);
+    for (int i = 0; i < n_delta; ++i) halo = std::max(halo, cfg.delta_p[i] - 1);
+    halo = std::max(halo, bb_period - 1);
+    if (halo > 4095) { bigru_set_error("window_features: periods above 4096 rows are not supported"); return BIGRU_ERR_UNSUPPORTED; }
+    const int span = FEAT_TR + halo;
+    const size_t smem = sizeof(float) * ((size_t)4 * span + 16 + (size_t)FEAT_TR * (cfg.n_out + 4));
+    // the reference's own configuration (config.py:40-49) runs with compile-time periods
+    const bool fast = n_vol == 2 && cfg.vol_p[0] == 6 && cfg.vol_p[1] == 20 && n_price == 1 && cfg.price_p[0] == 20 && n_delta == 1 &&
+                      cfg.delta_p[0] == 12 && bb_period == 20 && stochastic;
+    static size_t smem_attr[2] = {0, 0};
+    if (smem > smem_attr[fast]) {
+        CUDA_TRY(fast ? cudaFuncSetAttribute(window_features_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                      : cudaFuncSetAttribute(window_features_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_attr[fast] = smem;
+    }
+    const unsigned blocks = (unsigned)std::min<int64_t>((n + FEAT_TR - 1) / FEAT_TR, 148 * 8);
+    if (fast)
+        KLAUNCH(KC_GATHER, 0.0, 4.0 * n * (5 + cfg.n_out + 4), (cudaStream_t)stream,
+                window_features_kernel<true><<<blocks, FEAT_TR, smem, (cudaStream_t)stream>>>(d_close, d_high, d_low, d_volume, d_delta, n, cfg,
+                                                                                              halo, d_out, d_targets));
+    else
+        KLAUNCH(KC_GATHER, 0.0, 4.0 * n * (5 + cfg.n_out + 4), (cudaStream_t)stream,
+                window_features_kernel<false><<<blocks, FEAT_TR, smem, (cudaStream_t)stream>>>(d_close, d_high, d_low, d_volume, d_delta, n, cfg,
+                                                                                               halo, d_out, d_targets));
     return BIGRU_OK;
 }
 

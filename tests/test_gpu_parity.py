@@ -587,6 +587,24 @@ def _market_columns(n, seed=5):
 
 
 @pytest.mark.gpu
+def test_window_features_other_periods_match_oracle():
+    """periods other than the reference's config.py take the generic (run-time period) code path"""
+    from oracle import features_oracle as fo
+    from financial_market_data_analysis_b200.features import window_features
+    for kw in (dict(volume_MA_periods=[3, 10], price_MA_periods=[7, 31], delta_MA_periods=[5], bollinger_bands_period=10,
+                    bollinger_bands_std=1.5, stochastic_oscillator=False),
+               dict(volume_MA_periods=[], price_MA_periods=[300], delta_MA_periods=[], bollinger_bands_period=False,
+                    bollinger_bands_std=2, stochastic_oscillator=True)):
+        cols = _market_columns(3000, seed=9)
+        ref_f, ref_t = fo.window_features(*[c.astype(np.float64) for c in cols], **kw)
+        got_f, got_t = window_features(*[torch.from_numpy(c).cuda() for c in cols], **kw)
+        g = got_f.cpu().numpy()
+        assert g.shape == ref_f.shape and np.array_equal(np.isnan(g), np.isnan(ref_f))
+        np.testing.assert_allclose(np.nan_to_num(g), np.nan_to_num(ref_f), rtol=2e-6, atol=5e-4)
+        assert np.array_equal(got_t.cpu().numpy(), ref_t)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n", [1, 7, 16, 500, 20000])
 def test_window_features_match_oracle(n):
     from oracle import features_oracle as fo
