@@ -3,6 +3,7 @@
 #include "kernels_f32.cuh"
 #include "path_bf16.cuh"
 #include "features.cuh"
+#include "infer_small.cuh"
 
 #include <cstring>
 #include <new>
@@ -411,6 +412,29 @@ extern "C" int bigru_window_features(const float* d_close, const float* d_high, 
         KLAUNCH(KC_GATHER, 0.0, 4.0 * n * (5 + cfg.n_out + 4), (cudaStream_t)stream,
                 window_features_kernel<false><<<blocks, FEAT_TR, smem, (cudaStream_t)stream>>>(d_close, d_high, d_low, d_volume, d_delta, n, cfg,
                                                                                                halo, d_out, d_targets));
+    return BIGRU_OK;
+}
+
+extern "C" int bigru_infer_window(const float* d_params, const float* d_x, const float* d_xmin, const float* d_xmax, int B, int T,
+                                  int F, int H, int L, int C, int bidirectional, float* d_logits, float* d_probs, void* stream) {
+    if (!d_params || !d_x || !d_logits || B <= 0 || T <= 0 || F <= 0 || H <= 0 || L <= 0 || C <= 0 || ((d_xmin == nullptr) != (d_xmax == nullptr))) {
+        bigru_set_error("infer_window: bad argument");
+        return BIGRU_ERR_ARG;
+    }
+    const int D = bidirectional ? 2 : 1, DH = D * H, W = F > DH ? F : DH;
+    const size_t smem = sizeof(float) * ((size_t)T * W + (size_t)T * DH + 2 * (size_t)DH + 3 * (size_t)H);
+    if (DH > 1024 || smem > 200 * 1024) {
+        bigru_set_error("infer_window: window too large for the single-CTA path (D*H=%d, %zu bytes of shared memory); use bigru_forward", DH, smem);
+        return BIGRU_ERR_UNSUPPORTED;
+    }
+    static size_t smem_attr = 0;
+    if (smem > 48 * 1024 && smem > smem_attr) {
+        CUDA_TRY(cudaFuncSetAttribute(infer_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_attr = smem;
+    }
+    const int threads = std::max(32, ((DH + 31) / 32) * 32);
+    KLAUNCH(KC_MISC, 0.0, 0.0, (cudaStream_t)stream,
+            infer_window_kernel<<<B, threads, smem, (cudaStream_t)stream>>>(d_params, d_x, d_xmin, d_xmax, T, F, H, L, C, D, d_logits, d_probs));
     return BIGRU_OK;
 }
 

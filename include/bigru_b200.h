@@ -132,6 +132,14 @@ int  bigru_window_features(const float* d_close, const float* d_high, const floa
                            int n_price, const int* delta_periods, int n_delta, int bb_period, float bb_std,
                            int stochastic, float n1, float n2, float* d_out, float* d_targets, int* n_out, void* stream);
 
+/* --- SURVEY.md 8(f) N5, the live predictor's forward pass in one launch (predict.py:165-181): normalise the raw
+ *  window(s) d_x[B,T,F] with d_xmin/d_xmax[F] (nullable: already normalised), eval-mode forward of the flat parameters
+ *  (order above), d_logits[B,C] and d_probs[B,C] = sigmoid(logits) (nullable).  One CTA per window, activations in shared
+ *  memory, fp32 exact math; for small live windows only: D*H <= 1024 and T*(max(F,D*H)+D*H)*4 bytes of shared memory
+ *  (BIGRU_ERR_UNSUPPORTED beyond) - batches belong to bigru_forward. */
+int  bigru_infer_window(const float* d_params, const float* d_x, const float* d_xmin, const float* d_xmax, int B, int T,
+                        int F, int H, int L, int C, int bidirectional, float* d_logits, float* d_probs, void* stream);
+
 /* --- train_model/evaluate_model metrics (biGRU_model.py:213-221): pred = sigmoid(logit) > 0.5;
  *  d_counts[0] += #rows with all labels right; [1] += #label mismatches;
  *  [2+3c], [3+3c], [4+3c] += tp, fp, fn of class c.  int64 accumulators, caller zeroes. */

@@ -651,3 +651,53 @@ def test_window_features_errors():
         window_features(xc, xc, xc, None, xc)                                    # volume MA without the column
     with pytest.raises(ValueError):
         window_features(xc, xc, xc, xc, xc, volume_MA_periods=list(range(1, 10)))   # more than 8 periods
+
+
+# ---- the live predictor's forward in one launch -----------------------------------------------------
+@pytest.mark.gpu
+def test_live_predictor_known_answers(golden_dir):
+    """predict.py's model block on the shipped checkpoint: KAT logits (<= 1e-5), sigmoid, labels; raw windows + norm params."""
+    from financial_market_data_analysis_b200.predict import LivePredictor
+    z = np.load(os.path.join(golden_dir, "kat.npz"))
+    state = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("p:")}
+    lp = LivePredictor(state, None)
+    for i in (1, 2, 3):
+        logits, probs = lp.forward_windows(z[f"x{i}"])
+        assert np.abs(logits.cpu().numpy() - z[f"y{i}"]).max() < 1e-5
+        assert np.abs(probs.cpu().numpy() - 1 / (1 + np.exp(-z[f"y{i}"]))).max() < 1e-5
+        same = lp.model(torch.from_numpy(z[f"x{i}"]).cuda())                 # the step-by-step path of the same model
+        assert np.abs(same.detach().cpu().numpy() - logits.cpu().numpy()).max() < 1e-5
+    # raw rows + pickled-style norm params (predict.py:110-122, :170): same as normalising first
+    mn, mx = z["norm_min"].astype(np.float32), z["norm_max"].astype(np.float32)
+    lpn = LivePredictor(state, (mn, mx), prob_threshold=0.5)
+    rng = np.random.default_rng(0)
+    raw = (mn + rng.uniform(0, 1, (5, mn.size)) * (mx - mn)).astype(np.float32)
+    out = lpn.predict(raw, "2020-03-02 10:05:00")
+    want_logits, _ = lp.forward_windows(((raw - mn) / (mx - mn))[None])
+    want = 1 / (1 + np.exp(-want_logits.cpu().numpy()[0]))
+    assert np.abs(out["probabilities"].numpy() - want).max() < 1e-5
+    assert list(out["pred_indices"]) == list(np.where(want > 0.5)[0])
+    assert out["pred_labels"] == [lpn.y_fields[i] for i in out["pred_indices"]] and out["timestamp"] == "2020-03-02 10:05:00"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [(3, 7, 12, 16, 2, 3, True), (2, 9, 5, 33, 1, 2, False), (1, 4, 64, 128, 2, 4, True)])
+def test_infer_window_matches_c_oracle(cfg):
+    B, T, F, H, L, C, bidir = cfg
+    D = 2 if bidir else 1
+    torch.manual_seed(5)
+    m = _pkg().BiGRU(H, F, C, L, 50, 0.0, False, bidir, precision="fp32").cuda().eval()
+    x = torch.randn(B, T, F, generator=torch.Generator().manual_seed(2))
+    flat = m.flat_parameters().cpu().numpy()
+    ref_logits, _, _ = oracle_c.forward(flat, x.numpy(), H, L, C, D, None, keep=True)
+    from financial_market_data_analysis_b200 import _lib
+    lib = _lib.load()
+    logits = torch.empty(B, C, device="cuda"); probs = torch.empty(B, C, device="cuda")
+    xc = x.cuda()
+    _lib.check(lib.bigru_infer_window(_lib.ptr(m.flat_parameters()), _lib.ptr(xc), None, None, B, T, F, H, L, C, int(bidir), _lib.ptr(logits),
+                                      _lib.ptr(probs), torch.cuda.current_stream().cuda_stream), "bigru_infer_window")
+    scale = max(np.abs(ref_logits).max(), 1e-3)
+    assert np.abs(logits.cpu().numpy() - ref_logits).max() / scale < 1e-5
+    with pytest.raises(ValueError):                                          # D*H above one CTA: belongs to bigru_forward
+        _lib.check(lib.bigru_infer_window(_lib.ptr(m.flat_parameters()), _lib.ptr(xc), None, None, B, T, F, 1024, L, C, 1, _lib.ptr(logits),
+                                          _lib.ptr(probs), torch.cuda.current_stream().cuda_stream), "bigru_infer_window")
