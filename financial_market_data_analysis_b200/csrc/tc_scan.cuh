@@ -347,6 +347,13 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_c
         float hprev[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) hprev[i] = 0.f;
+        // loop-invariant shared-memory offsets: this thread's 8 elements of the h operand tile (inside its 64-unit chunk) and
+        // the 16-byte chunk it forwards to the peer
+        uint32_t h_off[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h_off[i] = (uint32_t)(unit >> 6) * H_CHUNK + tc::sw128_offset(col0 + i, unit & 63);
+        const int gu = (int)c * UNITS + q * 32 + (lane >> 3) * 8;
+        const uint32_t fwd_off = (uint32_t)(gu >> 6) * H_CHUNK + tc::sw128_offset(col0 + (lane & 7), gu & 63);
         bool ok = true;
         for (int s = 0; s < T; ++s) {
             const int t = d == 0 ? s : T - 1 - s;
@@ -374,8 +381,12 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_c
 #pragma unroll
                 for (int i = 0; i < 8; ++i) gn[i] = __bfloat162float(t8[i]);
             }
+            if (!FX) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) asm volatile("" ::"f"(gr[i]), "f"(gz[i]), "f"(gn[i]));     // converted before the wait below
+            }
             const int buf = s & 1;
-            uint8_t* hb = sH + (size_t)buf * KC * H_CHUNK + (size_t)(unit >> 6) * H_CHUNK;
+            uint8_t* hb = sH + (size_t)buf * KC * H_CHUNK;
             const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + col0;
             const uint32_t par = FX ? (uint32_t)(s & 1) : (uint32_t)((s - 1) & 1);
             float r8[8], z8[8], an[8];
@@ -417,7 +428,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_c
                 const float h = fmaf(z8[i], hprev[i] - n8[i], n8[i]);
                 hprev[i] = h;
                 hv[i] = __float2bfloat16(h);
-                *reinterpret_cast<__nv_bfloat16*>(hb + tc::sw128_offset(col0 + i, unit & 63)) = hv[i];
+                *reinterpret_cast<__nv_bfloat16*>(hb + h_off[i]) = hv[i];
             }
             // hand h_t to the control thread (this is the step chain): smem writes -> async proxy, one arrival per
             // warp; everything that only feeds HBM is issued afterwards, off the chain
@@ -428,8 +439,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_c
                 // chunk (8 units of lane group L/8, batch column L%8) and stores it asynchronously into the same place of
                 // the peer's operand tile; the store completes its bytes on the peer's h_full (async proxy end to end)
                 __syncwarp();
-                const int gu = (int)c * UNITS + q * 32 + (lane >> 3) * 8;
-                uint8_t* cp = sH + (size_t)buf * KC * H_CHUNK + (size_t)(gu >> 6) * H_CHUNK + tc::sw128_offset(col0 + (lane & 7), gu & 63);
+                uint8_t* cp = hb + fwd_off;
                 const uint4 v = *reinterpret_cast<const uint4*>(cp);
                 tc::st_async_v4(tc::mapa_u32(tc::smem_u32(cp), 1u - c), v, tc::mapa_u32(tc::smem_u32(&h_full[buf]), 1u - c));
             }
@@ -727,6 +737,13 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
             }
         }
         float sb_r = 0.f, sb_z = 0.f, sb_n = 0.f, sb_nr = 0.f;
+        // loop-invariant shared-memory offsets (see forward kernel)
+        uint32_t e_off[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e_off[i] = tc::sw128_offset(col0 + i, unit & 63);
+        const int kc_u = unit >> 6;
+        const int gu = (int)c * UNITS + q * 32 + (lane >> 3) * 8;
+        const uint32_t fwd_off = (uint32_t)(gu >> 6) * H_CHUNK + tc::sw128_offset(col0 + (lane & 7), gu & 63);
         bool ok = true;
         for (int s = 0; s < T; ++s) {
             const int t = d == 0 ? T - 1 - s : s;
@@ -786,6 +803,10 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
                 c_z[i] = (vhp[i] - n) * z * (1.f - z);              // da_z = dh * c_z
                 pre[i] = dhz[i] + vdy[i];
             }
+            // pin these values BEFORE the spin on the tensor pipe (the compiler otherwise sinks the arithmetic below the wait,
+            // onto the step chain)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) asm volatile("" ::"f"(c_n[i]), "f"(c_r[i]), "f"(c_z[i]), "f"(pre[i]), "f"(vr[i]), "f"(vz[i]));
             float acc[8];
             if (s > 0) {
                 if (tid == 0) SCAN_TS(4);
@@ -801,8 +822,11 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
             }
             const int buf = s & 1;
             uint8_t* tileb = sD + (size_t)buf * KC3 * H_CHUNK;
-            const int kc_u = unit >> 6;
+            uint8_t* t_r = tileb + (size_t)(0 * KC + kc_u) * H_CHUNK;
+            uint8_t* t_z = tileb + (size_t)(1 * KC + kc_u) * H_CHUNK;
+            uint8_t* t_n = tileb + (size_t)(2 * KC + kc_u) * H_CHUNK;
             float dar[8], daz[8], dan[8], danr[8];
+            __nv_bfloat16 dan_bf[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float dh = acc[i] + pre[i];
@@ -811,10 +835,13 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
                 daz[i] = dh * c_z[i];
                 danr[i] = dan[i] * vr[i];
                 dhz[i] = dh * vz[i];
-                const uint32_t so = tc::sw128_offset(col0 + i, unit & 63);
-                *reinterpret_cast<__nv_bfloat16*>(tileb + (size_t)(0 * KC + kc_u) * H_CHUNK + so) = __float2bfloat16(dar[i]);
-                *reinterpret_cast<__nv_bfloat16*>(tileb + (size_t)(1 * KC + kc_u) * H_CHUNK + so) = __float2bfloat16(daz[i]);
-                *reinterpret_cast<__nv_bfloat16*>(tileb + (size_t)(2 * KC + kc_u) * H_CHUNK + so) = __float2bfloat16(danr[i]);
+                // one packed conversion per two values (the conversion pipe is the narrow one here)
+                const __nv_bfloat162 rz = __floats2bfloat162_rn(dar[i], daz[i]);
+                *reinterpret_cast<__nv_bfloat16*>(t_r + e_off[i]) = rz.x;
+                *reinterpret_cast<__nv_bfloat16*>(t_z + e_off[i]) = rz.y;
+                const __nv_bfloat162 nn = __floats2bfloat162_rn(danr[i], dan[i]);
+                *reinterpret_cast<__nv_bfloat16*>(t_n + e_off[i]) = nn.x;
+                dan_bf[i] = nn.y;
             }
             // hand dgh_s to the tensor pipe (the step chain): own chunks -> peer with st.async (see forward kernel), then
             // the local arrival; the n-gate tile (TMA store only) and the bias sums follow, off the chain
@@ -822,12 +849,10 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
             tc::tcgen05_fence_before();
             if (CS > 1 && s + 1 < T) {
                 __syncwarp();
-                const int gu = (int)c * UNITS + q * 32 + (lane >> 3) * 8;
-                const uint32_t so = tc::sw128_offset(col0 + (lane & 7), gu & 63);
                 const uint32_t rbar = tc::mapa_u32(tc::smem_u32(&d_full[buf]), 1u - c);
 #pragma unroll
                 for (int g = 0; g < 3; ++g) {
-                    uint8_t* cp = tileb + (size_t)(g * KC + (gu >> 6)) * H_CHUNK + so;
+                    uint8_t* cp = tileb + (size_t)(g * KC) * H_CHUNK + fwd_off;
                     const uint4 v = *reinterpret_cast<const uint4*>(cp);
                     tc::st_async_v4(tc::mapa_u32(tc::smem_u32(cp), 1u - c), v, rbar);
                 }
@@ -838,7 +863,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
             if (tid == 0) SCAN_TS(10);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-                *reinterpret_cast<__nv_bfloat16*>(sN + (size_t)(buf * MYCH + ((unit & (UNITS - 1)) >> 6)) * H_CHUNK + tc::sw128_offset(col0 + i, unit & 63)) = __float2bfloat16(dan[i]);
+                *reinterpret_cast<__nv_bfloat16*>(sN + (size_t)(buf * MYCH + ((unit & (UNITS - 1)) >> 6)) * H_CHUNK + e_off[i]) = dan_bf[i];
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(st_done);
