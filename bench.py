@@ -262,25 +262,29 @@ def main():
     # ---- end to end through the public API with HOST buffers (`e2e`) ---------------------------------
     # Every step's inputs start in pinned host memory and are copied to the GPU inside the timed region
     # (DevicePrefetcher: side-stream copy, one step ahead); every step's loss is read back to the host
-    # inside the timed region (the read of step i is issued after step i and consumed one step later, so
-    # the host never stalls the launch queue).
+    # inside the timed region (the read of step i is issued after step i and consumed LAG - 1 steps later, so
+    # a hiccup of the host - or of another rank, through the all-reduce - does not drain the launch queue).
     from financial_market_data_analysis_b200.prefetch import DevicePrefetcher
-    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    LAG = 3                                   # the host consumes the loss of step i while step i + LAG - 1 is being queued
+    loss_host = torch.zeros(LAG, dtype=torch.float32).pin_memory()
     last_loss = [0.0]
 
     def run_e2e(n):
-        prev_ev = None
-        for x, t in DevicePrefetcher((host[i % NBUF] for i in range(n)), dev):
+        evs = [None] * LAG
+        for i, (x, t) in enumerate(DevicePrefetcher((host[k % NBUF] for k in range(n)), dev, depth=LAG)):
+            k = i % LAG
+            if evs[k] is not None:                               # slot k holds the loss of step i - LAG: consume it before reuse
+                evs[k].synchronize()
+                last_loss[0] = float(loss_host[k])
             loss, _ = model.train_step(x, t)
-            if prev_ev is not None:
-                prev_ev.synchronize()
-                last_loss[0] = float(loss_host[0])              # loss of the previous step, now on the host
-            loss_host.copy_(loss, non_blocking=True)             # D2H read of this step's loss
-            prev_ev = torch.cuda.Event()
-            prev_ev.record()
-        if prev_ev is not None:
-            prev_ev.synchronize()
-            last_loss[0] = float(loss_host[0])
+            loss_host[k:k + 1].copy_(loss, non_blocking=True)    # D2H read of this step's loss
+            evs[k] = torch.cuda.Event()
+            evs[k].record()
+        for j in range(LAG):                                     # drain in step order: every step's loss reaches the host
+            k = (n + j) % LAG
+            if evs[k] is not None:
+                evs[k].synchronize()
+                last_loss[0] = float(loss_host[k])
 
     run_e2e(args.warmup)
     barrier()
@@ -297,7 +301,8 @@ def main():
     e2e = {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
            "ms_per_step": ms_e / args.steps, "loss": last_loss[0],
            "how": "BiGRU.train_step on DevicePrefetcher batches: pinned host -> device copy of every step's inputs on a "
-                  "side stream one step ahead, per-step loss read back through a pinned buffer"}
+                  "side stream ahead of their use, every step's loss read back through a pinned ring and consumed by the host "
+                  "%d steps later (all reads complete inside the timed region)" % (LAG - 1)}
 
     # ---- live roofline of the dominant kernel (separate pass with per-launch events) ------------------
     roofline = None

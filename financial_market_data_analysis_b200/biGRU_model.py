@@ -335,6 +335,18 @@ class BiGRU(nn.Module):
             hit = self._loss_cache[key] = v.contiguous()
         return hit
 
+    def _fused_state(self, dev):
+        """Optimiser state of the fused step.  The flat gradient and the scalar loss share one buffer (``gext`` = P gradients
+        + 1 loss), so that data parallelism needs exactly one all-reduce per step."""
+        st = self._adam
+        if st is None:
+            P = self._flat.numel()
+            gext = torch.empty(P + 1, device=dev, dtype=torch.float32)
+            st = self._adam = {"m": torch.zeros_like(self._flat), "v": torch.zeros_like(self._flat), "step": 0,
+                               "gext": gext, "grad": gext[:P], "loss": gext[P:P + 1],
+                               "scal": torch.zeros(2, device=dev, dtype=torch.float32)}
+        return st
+
     def train_step(self, input_seq, target, hidden=None):
         """One optimisation step = the body of the reference loop (biGRU_model.py:198-210):
         zero_grad, forward, loss, backward, clip_grad_norm_(clip), Adam step - as six C-ABI calls with
@@ -359,11 +371,7 @@ class BiGRU(nn.Module):
                 raise ValueError(f"target must be [{B}, {C}]")
             denom = float(B * C * self._dp_world)
         plan = self._plan_for(x)
-        st = self._adam
-        if st is None:
-            st = self._adam = {"m": torch.zeros_like(self._flat), "v": torch.zeros_like(self._flat), "step": 0,
-                               "grad": torch.empty_like(self._flat),
-                               "scal": torch.zeros(2, device=dev, dtype=torch.float32)}
+        st = self._fused_state(dev)
         logits = torch.empty(B, C, device=dev, dtype=torch.float32)
         dlogits = torch.empty_like(logits)
         stash = plan.acquire_stash()
@@ -373,8 +381,7 @@ class BiGRU(nn.Module):
         args = (float(self.dropout_p), int(bool(self.spatial_dropout)), int(training), seed)
         _lib.check(lib.bigru_forward(plan.handle, _lib.ptr(self._flat), _lib.ptr(x), _lib.ptr(h0), *args,
                                      _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(logits), None, s), "bigru_forward")
-        loss = st["scal"][0:1]
-        sq = st["scal"][1:2]
+        loss, sq = st["loss"], st["scal"][1:2]
         wv, pwv = self._loss_vec(w, C), self._loss_vec(pw, C)
         _lib.check(lib.bigru_loss(kind, _lib.ptr(logits), _lib.ptr(tgt), _lib.ptr(wv), _lib.ptr(pwv), B, C, denom,
                                   _lib.ptr(loss), _lib.ptr(dlogits), s), "bigru_loss")
@@ -383,8 +390,7 @@ class BiGRU(nn.Module):
                                       None, None, s), "bigru_backward")
         plan.release_stash(stash)
         if self._dp_world > 1:
-            allreduce_flat_(st["grad"], self._dp_group)          # sum of shard gradients of the global-mean loss
-            allreduce_flat_(loss, self._dp_group)
+            allreduce_flat_(st["gext"], self._dp_group)          # ONE all-reduce: shard gradients of the global-mean loss + the loss
         sq.zero_()
         _lib.check(lib.bigru_sqnorm(_lib.ptr(st["grad"]), st["grad"].numel(), _lib.ptr(sq), s), "bigru_sqnorm")
         st["step"] += 1
@@ -445,13 +451,9 @@ class BiGRU(nn.Module):
         else:
             tgt = y.reshape(count, C).contiguous()
             denom = float(B * C * self._dp_world)
-        st = self._adam
-        if st is None:
-            st = self._adam = {"m": torch.zeros_like(self._flat), "v": torch.zeros_like(self._flat), "step": 0,
-                               "grad": torch.empty_like(self._flat),
-                               "scal": torch.zeros(2, device=dev, dtype=torch.float32)}
+        st = self._fused_state(dev)
         dlogits = torch.empty_like(logits)
-        loss, sq = st["scal"][0:1], st["scal"][1:2]
+        loss, sq = st["loss"], st["scal"][1:2]
         wv, pwv = self._loss_vec(w, C), self._loss_vec(pw, C)
         _lib.check(lib.bigru_loss(kind, _lib.ptr(logits), _lib.ptr(tgt), _lib.ptr(wv), _lib.ptr(pwv), B, C, denom,
                                   _lib.ptr(loss), _lib.ptr(dlogits), s), "bigru_loss")
@@ -462,8 +464,7 @@ class BiGRU(nn.Module):
         plan.release_stash(stash)
         self._win_ctx = None
         if self._dp_world > 1:
-            allreduce_flat_(st["grad"], self._dp_group)
-            allreduce_flat_(loss, self._dp_group)
+            allreduce_flat_(st["gext"], self._dp_group)
         sq.zero_()
         _lib.check(lib.bigru_sqnorm(_lib.ptr(st["grad"]), st["grad"].numel(), _lib.ptr(sq), s), "bigru_sqnorm")
         st["step"] += 1
