@@ -189,3 +189,27 @@ def test_data_parallel_allreduce_gloo_world2():
     assert shard_bounds(4096, 3, 8) == (1536, 2048)
     with pytest.raises(ValueError):
         shard_bounds(10, 0, 4)
+
+
+def test_next_row_entry_points_refuse_the_cpu(pkg):
+    """features.window_features / predict.LivePredictor: host-side argument logic, and no CPU fallback."""
+    from financial_market_data_analysis_b200 import features, predict
+    kw = dict(volume_MA_periods=[6, 20], price_MA_periods=[20], delta_MA_periods=[12], bollinger_bands_period=20,
+              bollinger_bands_std=2, stochastic_oscillator=True)
+    assert features.feature_names(**kw) == ["upper_BB_dist", "lower_BB_dist", "vol_MA6", "vol_MA20", "price_MA20", "delta_MA12",
+                                            "stoch", "ATR", "price_change"]            # create_database.py:239-240 join order
+    assert features.feature_names([], [], [], False, 2, False) == ["ATR", "price_change"]
+    x = torch.ones(16)
+    with pytest.raises(RuntimeError, match="GPU only"):
+        features.window_features(x, x, x, x, x)
+    with pytest.raises(RuntimeError, match="GPU only"):
+        predict.LivePredictor({}, None, n_features=4, device="cpu")
+    assert predict.Y_FIELDS == ["up1", "up2", "down1", "down2"]                          # predict.py:33
+    # the n_out query of the C entry point needs no device
+    lib, C = pkg._lib.load(), pkg._lib.C
+    n_out = C.c_int(0)
+    assert lib.bigru_window_features(None, None, None, None, None, 0, (C.c_int * 2)(6, 20), 2, (C.c_int * 1)(20), 1, (C.c_int * 1)(12), 1,
+                                     20, 2.0, 1, 1.5, 3.0, None, None, C.byref(n_out), None) == 0
+    assert n_out.value == 9
+    assert lib.bigru_window_features(None, None, None, None, None, 0, None, 9, None, 0, None, 0, 0, 2.0, 0, 1.5, 3.0, None, None,
+                                     C.byref(n_out), None) == pkg._lib.ERR_ARG
