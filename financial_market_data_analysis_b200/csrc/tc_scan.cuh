@@ -718,11 +718,12 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
         float dhz[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) dhz[i] = 0.f;
+        // top layer: d(concat) rows of this thread's 8 batch columns ([last | max | avg] x lin_w^T) stay in registers for all steps
+        float h_avg[8], h_max[8];
+        int h_arg[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { h_avg[i] = 0.f; h_max[i] = 0.f; h_arg[i] = -1; }
         if (top) {
-            // d(concat) rows of this thread's 8 batch columns: [last | max | avg] x lin_w^T
-            float* c_avg = sHead + (size_t)tid * 8;
-            float* c_max = sHead + 256 * 8 + (size_t)tid * 8;
-            int* c_arg = reinterpret_cast<int*>(sHead + 2 * 256 * 8) + (size_t)tid * 8;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int b = tile * NB + col0 + i;
@@ -733,7 +734,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
                     dl = fmaf(g, w[unit], dl); dm = fmaf(g, w[H + unit], dm); da = fmaf(g, w[2 * H + unit], da);
                 }
                 dhz[i] = dl;                                   // d(last hidden) enters the carry of both directions
-                c_avg[i] = da / (float)T; c_max[i] = dm; c_arg[i] = p.arg[(int64_t)b * H + unit];
+                h_avg[i] = da / (float)T; h_max[i] = dm; h_arg[i] = p.arg[(int64_t)b * H + unit];
             }
         }
         float sb_r = 0.f, sb_z = 0.f, sb_n = 0.f, sb_nr = 0.f;
@@ -759,18 +760,8 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
                 const uint4* gp = reinterpret_cast<const uint4*>(base) + tid;
                 const uint4 u0 = gp[0], u1 = gp[256], u2 = gp[512], u3 = gp[768];
                 const uint4 uh = first ? make_uint4(0u, 0u, 0u, 0u) : reinterpret_cast<const uint4*>(base + G_BLOCK)[tid];
-                float4 a, b;
-                if (top) {
-                    const float4* ca = reinterpret_cast<const float4*>(sHead + (size_t)tid * 8);
-                    const float4* cm = reinterpret_cast<const float4*>(sHead + 256 * 8 + (size_t)tid * 8);
-                    const int4* cg = reinterpret_cast<const int4*>(sHead + 2 * 256 * 8 + (size_t)tid * 8);
-                    const float4 a0 = ca[0], a1 = ca[1], m0 = cm[0], m1 = cm[1];
-                    const int4 g0 = cg[0], g1 = cg[1];
-                    a = make_float4(a0.x + (g0.x == t ? m0.x : 0.f), a0.y + (g0.y == t ? m0.y : 0.f),
-                                    a0.z + (g0.z == t ? m0.z : 0.f), a0.w + (g0.w == t ? m0.w : 0.f));
-                    b = make_float4(a1.x + (g1.x == t ? m1.x : 0.f), a1.y + (g1.y == t ? m1.y : 0.f),
-                                    a1.z + (g1.z == t ? m1.z : 0.f), a1.w + (g1.w == t ? m1.w : 0.f));
-                } else {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                if (!top) {
                     const float4* dyp = reinterpret_cast<const float4*>(base + G_BLOCK + YB_BLOCK) + 2 * tid;
                     a = dyp[0]; b = dyp[1];
                 }
@@ -792,6 +783,10 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
 #pragma unroll
                 for (int i = 0; i < 8; ++i) vhp[i] = __bfloat162float(t8[i]);
                 vdy[0] = a.x; vdy[1] = a.y; vdy[2] = a.z; vdy[3] = a.w; vdy[4] = b.x; vdy[5] = b.y; vdy[6] = b.z; vdy[7] = b.w;
+                if (top) {                                  // dY_t = davg / T + (argmax_t == t ? dmax : 0)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) vdy[i] = h_avg[i] + (h_arg[i] == t ? h_max[i] : 0.f);
+                }
             }
             // everything that does not depend on the recurrent product is formed before the wait on the tensor pipe
             float c_n[8], c_r[8], c_z[8], pre[8];
