@@ -23,7 +23,7 @@ import torch.nn as nn
 from . import _lib
 from .parallel import allreduce_flat_
 
-_PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+_PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "bf16x3": _lib.PREC_BF16X3}
 
 
 def _stream_ptr():

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "kernels_f32.cuh"
 #include "path_bf16.cuh"
+#include "path_x3.cuh"
 #include "features.cuh"
 #include "infer_small.cuh"
 
@@ -17,7 +18,7 @@ void bigru_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* bigru_last_error(void) { return g_err; }
-extern "C" int bigru_version(void) { return 100; }
+extern "C" int bigru_version(void) { return 200; }
 
 extern "C" int bigru_device_check(int dev) {
     int n = 0;
@@ -83,7 +84,7 @@ extern "C" int bigru_plan_create(int B, int T, int F, int H, int L, int C, int b
         bigru_set_error("plan_create: bad shape B=%d T=%d F=%d H=%d L=%d C=%d", B, T, F, H, L, C);
         return BIGRU_ERR_ARG;
     }
-    if (precision != BIGRU_PREC_FP32 && precision != BIGRU_PREC_BF16) {
+    if (precision != BIGRU_PREC_FP32 && precision != BIGRU_PREC_BF16 && precision != BIGRU_PREC_BF16X3) {
         bigru_set_error("plan_create: unknown precision %d", precision);
         return BIGRU_ERR_ARG;
     }
@@ -95,6 +96,10 @@ extern "C" int bigru_plan_create(int B, int T, int F, int H, int L, int C, int b
         int rc = bf16_plan_check(*p);
         if (rc != BIGRU_OK) { delete p; return rc; }
         bf16_workspace(*p, &p->stash_bytes, &p->scratch_bytes);
+    } else if (precision == BIGRU_PREC_BF16X3) {
+        int rc = x3_plan_check(*p);
+        if (rc != BIGRU_OK) { delete p; return rc; }
+        x3_workspace(*p, &p->stash_bytes, &p->scratch_bytes);
     } else {
         p->stash_bytes = (size_t)stash_layout(*p).total * sizeof(float);
         p->scratch_bytes = (size_t)scratch_layout(*p).total * sizeof(float);
@@ -303,6 +308,9 @@ extern "C" int bigru_forward(const bigru_plan* plan, const float* d_params, cons
     if (plan->prec == BIGRU_PREC_BF16)
         return forward_bf16(*plan, d_params, d_x, d_h0, dropout_p, spatial, training, seed, d_stash, d_scratch,
                             d_logits, d_hn, st);
+    if (plan->prec == BIGRU_PREC_BF16X3)
+        return forward_x3(*plan, d_params, d_x, d_h0, dropout_p, spatial, training, seed, d_stash, d_scratch,
+                          d_logits, d_hn, st);
     return forward_f32(*plan, d_params, d_x, d_h0, dropout_p, spatial, training, seed, (float*)d_stash,
                        (float*)d_scratch, d_logits, d_hn, st);
 }
@@ -319,6 +327,9 @@ extern "C" int bigru_backward(const bigru_plan* plan, const float* d_params, con
     if (plan->prec == BIGRU_PREC_BF16)
         return backward_bf16(*plan, d_params, d_x, d_h0, dropout_p, spatial, training, seed, d_stash, d_scratch,
                              d_dlogits, d_grads, d_dx, d_dh0, st);
+    if (plan->prec == BIGRU_PREC_BF16X3)
+        return backward_x3(*plan, d_params, d_x, d_h0, dropout_p, spatial, training, seed, d_stash, d_scratch,
+                           d_dlogits, d_grads, d_dx, d_dh0, st);
     return backward_f32(*plan, d_params, d_x, d_h0, dropout_p, spatial, training, seed, (const float*)d_stash,
                         (float*)d_scratch, d_dlogits, d_grads, d_dx, d_dh0, st);
 }
@@ -341,6 +352,9 @@ extern "C" int bigru_forward_windows(const bigru_plan* plan, const float* d_para
     if (plan->prec == BIGRU_PREC_BF16)
         return forward_bf16(*plan, d_params, nullptr, nullptr, dropout_p, spatial, training, seed, d_stash, d_scratch,
                             d_logits, d_hn, st, WindowSrc{d_src, d_xmin, d_xmax, start});
+    if (plan->prec == BIGRU_PREC_BF16X3)
+        return forward_x3(*plan, d_params, nullptr, nullptr, dropout_p, spatial, training, seed, d_stash, d_scratch,
+                          d_logits, d_hn, st, WindowSrc{d_src, d_xmin, d_xmax, start});
     // fp32 path: collate into the stash slot of the layer-0 input, then the ordinary forward
     float* xw = (float*)d_stash + stash_layout(*plan).X[0];
     TRY(bigru_window_gather_norm(d_src, d_xmin, d_xmax, start, N, plan->B, plan->T, plan->F, xw, stream));

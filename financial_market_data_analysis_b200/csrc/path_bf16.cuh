@@ -73,7 +73,7 @@ static void bf16_workspace(const bigru_plan& p, size_t* a, size_t* b) {
 // x fp32 [B][T][F] -> Xrow bf16 [(t*B+b)][F] (time-major rows), optional input dropout.  With `src` set the batch is
 // read straight from the chunk table: x[b,t,f] = (src[start+b+t, f] - xmin[f]) / (xmax[f] - xmin[f])  (zero-copy windows).
 struct WindowSrc { const float* src; const float* xmin; const float* xmax; int64_t start; };
-__global__ void cast_x_kernel(const float* __restrict__ x, WindowSrc w, bf16_t* __restrict__ Xrow, int B, int T, int F,
+__global__ void cast_x_kernel(const float* __restrict__ x, WindowSrc w, bf16_t* __restrict__ Xrow, bf16_t* __restrict__ Xlo, int B, int T, int F,
                               float pdrop, int spatial, uint64_t seed) {
     const float scale = pdrop > 0.f ? 1.f / (1.f - pdrop) : 1.f;
     const int F4 = F >> 2;                          // F % 8 == 0 on the tensor-core path
@@ -115,6 +115,11 @@ __global__ void cast_x_kernel(const float* __restrict__ x, WindowSrc w, bf16_t* 
             }
             __nv_bfloat162 lo = __floats2bfloat162_rn(q.x, q.y), hi = __floats2bfloat162_rn(q.z, q.w);
             *reinterpret_cast<uint2*>(Xrow + r * F + f) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+            if (Xlo) {          // x3 path: the residuals x - bf16(x), again as bf16
+                const float2 a = __bfloat1622float2(lo), b2 = __bfloat1622float2(hi);
+                __nv_bfloat162 rl = __floats2bfloat162_rn(q.x - a.x, q.y - a.y), rh = __floats2bfloat162_rn(q.z - b2.x, q.w - b2.y);
+                *reinterpret_cast<uint2*>(Xlo + r * F + f) = make_uint2(*reinterpret_cast<uint32_t*>(&rl), *reinterpret_cast<uint32_t*>(&rh));
+            }
         }
     }
 }
@@ -230,7 +235,7 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackJobs jobs, int 
 // Linear(3H -> C), one block (256 threads) per batch row.  Pooling: a thread owns 8 consecutive hidden units (one 16-byte
 // load per direction and time step), H/8 lanes cover a time step and the 256/(H/8) lane groups split the T steps; the
 // groups' partial (max, first argmax, sum) are combined through shared memory.  H % 8 == 0, H <= 256.
-__global__ void __launch_bounds__(256) head_fwd_kernel(const bf16_t* __restrict__ Y, const float* __restrict__ lin_w,
+__global__ void __launch_bounds__(256) head_fwd_kernel(const bf16_t* __restrict__ Y, const bf16_t* __restrict__ Ylo, const float* __restrict__ lin_w,
                                                        const float* __restrict__ lin_b, float* __restrict__ cat, int* __restrict__ arg,
                                                        float* __restrict__ logits, int B, int T, int H, int D, int C) {
     extern __shared__ float hs[];                      // [G][H] max, [G][H] sum, [G][H] argmax (int), then [C][8] partial logits
@@ -251,9 +256,17 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const bf16_t* __restrict_
             if (D == 2) c = *reinterpret_cast<const uint4*>(y + H);
             const bf16_t* pa = reinterpret_cast<const bf16_t*>(&a);
             const bf16_t* pc = reinterpret_cast<const bf16_t*>(&c);
+            uint4 al = make_uint4(0u, 0u, 0u, 0u), cl = al;
+            if (Ylo) {
+                const bf16_t* yl = Ylo + ((int64_t)t * B + b) * ld + u0;
+                al = *reinterpret_cast<const uint4*>(yl);
+                if (D == 2) cl = *reinterpret_cast<const uint4*>(yl + H);
+            }
+            const bf16_t* pal = reinterpret_cast<const bf16_t*>(&al);
+            const bf16_t* pcl = reinterpret_cast<const bf16_t*>(&cl);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float v = __bfloat162float(pa[i]) + __bfloat162float(pc[i]);
+                const float v = (__bfloat162float(pa[i]) + __bfloat162float(pal[i])) + (__bfloat162float(pc[i]) + __bfloat162float(pcl[i]));
                 if (v > mx[i]) { mx[i] = v; am[i] = t; }
                 sm[i] += v;
             }
@@ -267,7 +280,12 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const bf16_t* __restrict_
     int a_t = 0;
     if (j < H) {
         last = __bfloat162float(Y[((int64_t)(T - 1) * B + b) * ld + j]);
-        if (D == 2) last += __bfloat162float(Y[(int64_t)b * ld + H + j]);
+        if (Ylo) last += __bfloat162float(Ylo[((int64_t)(T - 1) * B + b) * ld + j]);
+        if (D == 2) {
+            float lr = __bfloat162float(Y[(int64_t)b * ld + H + j]);
+            if (Ylo) lr += __bfloat162float(Ylo[(int64_t)b * ld + H + j]);
+            last += lr;
+        }
         for (int g = 0; g < G; ++g) {                  // first occurrence of the maximum, as a sequential scan over t finds it
             const float v = s_max[g * H + j]; const int at = s_arg[g * H + j];
             if (v > m || (v == m && at < a_t)) { m = v; a_t = at; }
@@ -288,10 +306,10 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const bf16_t* __restrict_
         if ((j & 31) == 0) red[cc * 8 + (j >> 5)] = v;
     }
     __syncthreads();
-    if (j < C) {
-        float v = lin_b[j];
-        for (int w = 0; w < 8; ++w) v += red[j * 8 + w];
-        logits[(int64_t)b * C + j] = v;
+    for (int cc = j; cc < C; cc += 256) {                 // output_size may exceed the block size
+        float v = lin_b[cc];
+        for (int w = 0; w < 8; ++w) v += red[cc * 8 + w];
+        logits[(int64_t)b * C + cc] = v;
     }
 }
 // d(lin_w)[c][k] = sum_b dlogits[b][c] cat[b][k];  d(lin_b)[c] = sum_b dlogits[b][c]   (outputs pre-zeroed; the batch
@@ -343,8 +361,17 @@ __global__ void dx_to_batch_major_kernel(const float* __restrict__ dXT, float* _
 // ---------------------------------------------------------------------------------------------------
 // A / B operand descriptions: K-major [rows][K] (ld = row stride) or MN-major [K rows][MN] (p.a_mn / p.b_mn set)
 static int tc_gemm(const void* A, int64_t a_rows, int64_t lda, const void* Bm, int64_t b_rows, int64_t ldb,
-                   tcg::Params& p, cudaStream_t st, int kclass = KC_TC_GEMM) {
-    CUtensorMap tA, tB;
+                   tcg::Params& p, cudaStream_t st, int kclass = KC_TC_GEMM, const void* Alo = nullptr, const void* Blo = nullptr) {
+    CUtensorMap tA, tB, tAl, tBl;
+    const bool split = Alo != nullptr && Blo != nullptr;
+    p.nsplit = split ? 3 : 1;
+    if (split) {
+        const int e1 = p.a_mn ? tcg::make_operand_map_mn(&tAl, Alo, (uint64_t)p.K, (uint64_t)a_rows, (uint64_t)lda)
+                              : tcg::make_operand_map(&tAl, Alo, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda);
+        const int e2 = p.b_mn ? tcg::make_operand_map_mn(&tBl, Blo, (uint64_t)p.K, (uint64_t)b_rows, (uint64_t)ldb)
+                              : tcg::make_operand_map(&tBl, Blo, (uint64_t)b_rows, (uint64_t)p.K, (uint64_t)ldb);
+        if (e1 || e2) { bigru_set_error("cuTensorMapEncodeTiled failed (low operand parts)"); return BIGRU_ERR_CUDA; }
+    }
     const int ea = p.a_mn ? tcg::make_operand_map_mn(&tA, A, (uint64_t)p.K, (uint64_t)a_rows, (uint64_t)lda)
                           : tcg::make_operand_map(&tA, A, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda);
     const int eb = p.b_mn ? tcg::make_operand_map_mn(&tB, Bm, (uint64_t)p.K, (uint64_t)b_rows, (uint64_t)ldb)
@@ -355,7 +382,7 @@ static int tc_gemm(const void* A, int64_t a_rows, int64_t lda, const void* Bm, i
         return BIGRU_ERR_CUDA;
     }
     ProfScope ps(kclass, 2.0 * p.M * p.N * (double)p.K * p.batch, 0.0, st);
-    CUDA_TRY(tcg::launch(tA, tB, p, st));
+    CUDA_TRY(tcg::launch(tA, tB, p, st, split ? &tAl : nullptr, split ? &tBl : nullptr));
     return BIGRU_OK;
 }
 
@@ -393,7 +420,7 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
         KLAUNCH(KC_PACK, 0.0, 0.0, st, pack_all_kernel<<<dim3(148, nj), 256, 0, st>>>(jobs, H, D));
     }
     // 2. layer-0 input: cast to bf16, time-major rows (+ input dropout)
-    KLAUNCH(KC_PACK, 0.0, 6.0 * R * F, st, cast_x_kernel<<<148 * 8, 256, 0, st>>>(x, win, (bf16_t*)(S + L.Xrow[0]), B, T, F,
+    KLAUNCH(KC_PACK, 0.0, 6.0 * R * F, st, cast_x_kernel<<<148 * 8, 256, 0, st>>>(x, win, (bf16_t*)(S + L.Xrow[0]), nullptr, B, T, F,
                                                                                    do_drop ? drop : 0.f, spatial, seed));
     for (int l = 0; l < p.L; ++l) {
         const int I = (int)p.in_size(l);
@@ -435,7 +462,7 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
         const int G = 256 / (H / 8);
         const size_t hsm = sizeof(float) * ((size_t)3 * G * H + (size_t)p.C * 8);
         KLAUNCH(KC_HEAD, 0.0, 2.0 * R * D * H, st, head_fwd_kernel<<<B, 256, hsm, st>>>(
-                    (const bf16_t*)(S + L.Yrow[p.L - 1]), params + p.off_linw(), params + p.off_linb(), (float*)(S + L.cat),
+                    (const bf16_t*)(S + L.Yrow[p.L - 1]), nullptr, params + p.off_linw(), params + p.off_linb(), (float*)(S + L.cat),
                     (int*)(S + L.arg), logits, B, T, H, D, p.C));
     }
     return BIGRU_OK;

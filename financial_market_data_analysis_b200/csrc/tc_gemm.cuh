@@ -33,7 +33,8 @@ enum { OUT_F32 = 0, OUT_BF16 = 1, OUT_ATOMIC_F32 = 2, OUT_SCAN_BF16 = 3, OUT_SCA
 //   tile = b/16, c = unit/128, tid = ((unit%128)/32 + 4*((b%16)/8))*32 + unit%32, i = b%8
 // so one (direction, tile, step, CTA) block is G*4 KB contiguous (one bulk copy for the scan kernel) and a warp of
 // this epilogue (32 consecutive units, fixed b-run) writes 512 contiguous bytes.
-struct ScanBlk { int T, B, H, G; };
+struct ScanBlk { int T, B, H, G; int U, NB; };   // U units per CTA (128: bf16 scans, 64: x3 scans), NB batch rows per tile (16 / 32)
+// general form of the mapping above: tile = b/NB, c = unit/U, tid = unit%U + U*((b%NB)/8), i = b%8
 
 struct Params {
     int M, N, K;              // K = full reduction length (split across splitk slices)
@@ -50,11 +51,14 @@ struct Params {
     int m_fast;               // rasterisation: 1 = consecutive CTAs walk m-tiles first (B tile shared through L2)
     int stages;               // smem ring depth (1..4), chosen per problem: shallow rings let 3-4 CTAs share an SM
     int tma_store;            // 1: epilogue stages the tile in smem and writes it with TMA (store / reduce-add)
+    int nsplit;               // 1: plain bf16 product; 3: fp32-class product of split operands, A_hi B_hi + A_hi B_lo + A_lo B_hi
+                              //    (second pair of tensor maps = the low parts; three ring slots per k-block)
     unsigned int* dbg;        // watchdog record (nullable)
 };
 
 __global__ void __launch_bounds__(THREADS, 4)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
             const __grid_constant__ CUtensorMap tmC0, const __grid_constant__ CUtensorMap tmC1, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -94,26 +98,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (tc::elect_one()) {
             tc::tma_prefetch_desc(&tmA);
             tc::tma_prefetch_desc(&tmB);
-            for (int i = 0; i < nkb; ++i) {
+            if (p.nsplit > 1) { tc::tma_prefetch_desc(&tmAlo); tc::tma_prefetch_desc(&tmBlo); }
+            const int nit = nkb * p.nsplit;
+            for (int i = 0; i < nit; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
                 if (!tc::mbar_wait(&empty[s], ph ^ 1, p.dbg, 0x100 + s)) break;
                 tc::mbar_arrive_expect_tx(&full[s], A_BYTES + B_BYTES);
-                const int k = (kb0 + i) * BK;
+                const int combo = i % p.nsplit;                     // 0: hi x hi, 1: hi x lo, 2: lo x hi
+                const int k = (kb0 + i / p.nsplit) * BK;
+                const CUtensorMap* mA = combo == 2 ? &tmAlo : &tmA;
+                const CUtensorMap* mB = combo == 1 ? &tmBlo : &tmB;
                 if (p.a_mn) {        // two boxes of 64 (MN) x 64 (K rows)
-                    tc::tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], p.a_row_off[z] + m0, k);
-                    tc::tma_load_2d(sA + s * A_BYTES + A_BYTES / 2, &tmA, &full[s], p.a_row_off[z] + m0 + 64, k);
-                } else tc::tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], k, p.a_row_off[z] + m0);
+                    tc::tma_load_2d(sA + s * A_BYTES, mA, &full[s], p.a_row_off[z] + m0, k);
+                    tc::tma_load_2d(sA + s * A_BYTES + A_BYTES / 2, mA, &full[s], p.a_row_off[z] + m0 + 64, k);
+                } else tc::tma_load_2d(sA + s * A_BYTES, mA, &full[s], k, p.a_row_off[z] + m0);
                 if (p.b_mn) {
-                    tc::tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], p.b_row_off[z] + n0, k + p.b_k_off[z]);
-                    tc::tma_load_2d(sB + s * B_BYTES + B_BYTES / 2, &tmB, &full[s], p.b_row_off[z] + n0 + 64, k + p.b_k_off[z]);
-                } else tc::tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], k + p.b_k_off[z], p.b_row_off[z] + n0);
+                    tc::tma_load_2d(sB + s * B_BYTES, mB, &full[s], p.b_row_off[z] + n0, k + p.b_k_off[z]);
+                    tc::tma_load_2d(sB + s * B_BYTES + B_BYTES / 2, mB, &full[s], p.b_row_off[z] + n0 + 64, k + p.b_k_off[z]);
+                } else tc::tma_load_2d(sB + s * B_BYTES, mB, &full[s], k + p.b_k_off[z], p.b_row_off[z] + n0);
             }
         }
     } else if (warp == 1) {
         if (tc::elect_one()) {
             const uint32_t idesc = tc::umma_idesc_bf16(BM, BN, (uint32_t)p.a_mn, (uint32_t)p.b_mn);
-            for (int i = 0; i < nkb; ++i) {
+            const int nit = nkb * p.nsplit;
+            for (int i = 0; i < nit; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
                 if (!tc::mbar_wait(&full[s], ph, p.dbg, 0x200 + s)) break;
@@ -178,17 +188,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tc::fence_proxy_async_smem();
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (warp == 2 && tc::elect_one()) {
-                const int H = p.blk.H, G = p.blk.G, Bb = p.blk.B, Tt = p.blk.T;
-                const int dd = m0 / (G * H), gg = (m0 / H) % G, cc = (m0 % H) / 128;
-                const int CSs = H / 128, ntl = Bb / 16;
+                const int H = p.blk.H, G = p.blk.G, Bb = p.blk.B, Tt = p.blk.T, U = p.blk.U, NBt = p.blk.NB;
+                const int CSs = H / U, ntl = Bb / NBt;
                 const size_t es = bf ? 2 : 4;
                 for (int r = 0; r < BN / 8; ++r) {
                     const int n = n0 + r * 8;
                     if (n >= p.N) break;
                     const int t_ = n / Bb, b = n % Bb;
-                    const int tile_ = b >> 4, half = (b >> 3) & 1;
-                    const size_t e = ((((((size_t)dd * ntl + tile_) * Tt + t_) * CSs + cc) * G + gg) * 256 + (size_t)half * 128) * 8;
-                    tc::bulk_s2g(reinterpret_cast<uint8_t*>(p.C) + e * es, smem + (size_t)r * run_bytes, (uint32_t)run_bytes);
+                    const int tile_ = b / NBt, cbg = (b % NBt) >> 3;
+                    for (int hh = 0; hh < BM / U; ++hh) {          // the tile's 128 rows = BM/U runs of U units of one (d, gate, cta)
+                        const int mr = m0 + hh * U;
+                        const int dd = mr / (G * H), gg = (mr / H) % G, cc = (mr % H) / U;
+                        const size_t e = ((((((size_t)dd * ntl + tile_) * Tt + t_) * CSs + cc) * G + gg) * 256 + (size_t)cbg * U) * 8;
+                        tc::bulk_s2g(reinterpret_cast<uint8_t*>(p.C) + e * es, smem + (size_t)r * run_bytes + (size_t)hh * U * 8 * es,
+                                     (uint32_t)(U * 8 * es));
+                    }
                 }
                 tc::tma_store_commit();
                 tc::tma_store_wait_read();     // smem may be released once it has been read; the writes complete on their own
@@ -268,17 +282,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int nb = n0 + c * 32;
                 if (m < p.M && nb < p.N && p.mode >= OUT_SCAN_BF16) {
                     // blocked store: 8 consecutive b (one thread-run of the scan kernel) = one 16/32-byte store
-                    const int H = p.blk.H, G = p.blk.G, Bb = p.blk.B, Tt = p.blk.T;
+                    const int H = p.blk.H, G = p.blk.G, Bb = p.blk.B, Tt = p.blk.T, U = p.blk.U, NBt = p.blk.NB;
                     const int dd = m / (G * H), gg = (m / H) % G, unit = m % H;
-                    const int CSs = H / 128, cc = unit / 128, ju = unit % 128;
-                    const int ntl = Bb / 16;
+                    const int CSs = H / U, cc = unit / U, ju = unit % U;
+                    const int ntl = Bb / NBt;
 #pragma unroll
                     for (int i8 = 0; i8 < 32; i8 += 8) {
                         const int n = nb + i8;
                         if (n >= p.N) break;
                         const int t = n / Bb, b = n % Bb;
-                        const int tile = b >> 4, half = (b >> 3) & 1;
-                        const int tid = ((ju >> 5) + 4 * half) * 32 + (ju & 31);
+                        const int tile = b / NBt;
+                        const int tid = ju + U * ((b % NBt) >> 3);
                         const size_t e = ((((((size_t)dd * ntl + tile) * Tt + t) * CSs + cc) * G + gg) * 256 + tid) * 8;
                         float f[8];
 #pragma unroll
@@ -366,17 +380,24 @@ static inline int make_operand_map_mn(CUtensorMap* m, const void* base, uint64_t
     return make_tmap_bf16(m, base, 2, dims, strides, box);
 }
 
-static inline cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p_in, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(MAX_STAGES));
-        if (e != cudaSuccess) return e;
-        attr_set = true;
+static inline cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p_in, cudaStream_t st,
+                                 const CUtensorMap* tmAlo = nullptr, const CUtensorMap* tmBlo = nullptr) {
+    {   // the opt-in is per device: (re)apply it whenever the current device has not been seen (cheap, no process-wide flag)
+        static bool attr_set[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(MAX_STAGES));
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
     }
     Params p = p_in;
+    if (p.nsplit != 3 || !tmAlo || !tmBlo) p.nsplit = 1;
+    if (p.blk.U == 0) { p.blk.U = 128; p.blk.NB = 16; }
     {   // ring depth from the k-blocks one CTA walks: short reductions are latency-bound per tile, so trade ring depth
         // for more co-resident CTAs (2 stages -> 3 CTAs/SM); long ones keep 3 stages (2 CTAs/SM)
-        const int kblocks = ((p.K + BK - 1) / BK + p.splitk - 1) / p.splitk;
+        const int kblocks = (((p.K + BK - 1) / BK + p.splitk - 1) / p.splitk) * p.nsplit;
         p.stages = kblocks <= 2 ? kblocks : (kblocks <= 12 ? 2 : 3);
         if (p.stages < 1) p.stages = 1;
     }
@@ -392,11 +413,12 @@ static inline cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB,
         if (p.batch == 1) tmC[1] = tmC[0];
     }
     p.tma_store = tma_ok ? 1 : 0;
-    if (scan_mode && p.M % BM == 0 && p.blk.B % 16 == 0 && ((uintptr_t)p.C % 16 == 0)) p.tma_store = 1;   // bulk-store epilogue
+    if (scan_mode && p.M % BM == 0 && p.blk.H % p.blk.U == 0 && p.blk.B % p.blk.NB == 0 && ((uintptr_t)p.C % 16 == 0)) p.tma_store = 1;   // bulk-store epilogue
     dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.batch * p.splitk);
     if (p.m_fast) { const unsigned t = grid.x; grid.x = grid.y; grid.y = t; }
     const int stage_out = p.tma_store ? ((p.mode == OUT_BF16 || p.mode == OUT_SCAN_BF16) ? 32768 : 65536) : 0;
-    gemm_kernel<<<grid, THREADS, smem_bytes_for(p.stages, stage_out), st>>>(tmA, tmB, tmC[0], tmC[1], p);
+    gemm_kernel<<<grid, THREADS, smem_bytes_for(p.stages, stage_out), st>>>(tmA, tmB, p.nsplit == 3 ? *tmAlo : tmA, p.nsplit == 3 ? *tmBlo : tmB,
+                                                                            tmC[0], tmC[1], p);
     return cudaGetLastError();
 }
 

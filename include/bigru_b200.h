@@ -39,6 +39,8 @@ extern "C" {
 
 #define BIGRU_PREC_FP32 0          /* fp32 FFMA path: the parity reference (<=1e-4 rel on logits) */
 #define BIGRU_PREC_BF16 1          /* bf16 operands on tcgen05 tensor cores, fp32 accumulate/state */
+#define BIGRU_PREC_BF16X3 2        /* fp32-class on tensor cores: (hi, lo) bf16 operand pairs, 3-4 products per term,
+                                      fp32 accumulate / gate math / stash; meets the 1e-4 logit tolerance at tensor-core speed */
 
 #define BIGRU_LOSS_CE   0          /* torch.nn.CrossEntropyLoss (BASELINE.json configs) */
 #define BIGRU_LOSS_BCE  1          /* torch.nn.BCEWithLogitsLoss(weight,pos_weight) notebook raw :1192 */

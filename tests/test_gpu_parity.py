@@ -19,7 +19,10 @@ pytestmark = pytest.mark.gpu
 # fraction of lr (1e-3) and the whole update by rel-L2
 # bf16 path: operands, the gate stash and dgi/dgh are bf16 (fp32 accumulate/state), so the error of BPTT grows
 # with T and L; bounds: per-tensor rel-L2 "grads", whole flat gradient "gflat"
+# bf16x3 path ("fp32-class" on tensor cores: split bf16 operand pairs, fp32 accumulate / gate math / stash): the SAME bounds as
+# the fp32 path - it is the variant BASELINE.json configs[1] ("fp32 tolerance check") is measured on
 TOL = {"fp32": dict(logits=1e-4, grads=1e-3, gflat=1e-3, kat=1e-5, step=2e-4, update=2e-2),
+       "bf16x3": dict(logits=1e-4, grads=1e-3, gflat=1e-3, kat=1e-5, step=2e-4, update=2e-2),
        "bf16": dict(logits=3e-2, grads=0.15, gflat=6e-2, kat=3e-2, step=2e-3, update=0.5)}
 
 
@@ -33,6 +36,9 @@ def precisions():
     lib = pkg._lib.load()
     out = ["fp32"]
     h = pkg._lib.C.c_void_p()
+    if lib.bigru_plan_create(128, 16, 64, 256, 1, 3, 1, pkg._lib.PREC_BF16X3, pkg._lib.C.byref(h)) == 0:
+        lib.bigru_plan_destroy(h)
+        out.append("bf16x3")
     if lib.bigru_plan_create(128, 16, 64, 256, 1, 3, 1, pkg._lib.PREC_BF16, pkg._lib.C.byref(h)) == 0:
         lib.bigru_plan_destroy(h)
         out.append("bf16")
@@ -40,8 +46,13 @@ def precisions():
 
 
 def supported(precision, B, F, H, h0=False):
-    """BIGRU_PREC_BF16 covers H in {128, 256}, B % 16 == 0, F % 8 == 0, no initial hidden state."""
-    return precision == "fp32" or (H in (128, 256) and B % 16 == 0 and F % 8 == 0 and not h0)
+    """BIGRU_PREC_BF16 covers H in {128, 256}, B % 16 == 0, F % 8 == 0, no initial hidden state;
+    BIGRU_PREC_BF16X3 covers H in {128, 256}, B % 32 == 0, F % 8 == 0, with or without an initial hidden state."""
+    if precision == "fp32":
+        return True
+    if precision == "bf16x3":
+        return H in (128, 256) and B % 32 == 0 and F % 8 == 0
+    return H in (128, 256) and B % 16 == 0 and F % 8 == 0 and not h0
 
 
 def rel(a, b):
@@ -172,6 +183,9 @@ SWEEP = [  # B, T, F, H, L, C, bidir, h0
     (32, 5, 8, 128, 1, 2, False, False),
     (32, 9, 64, 128, 2, 3, True, False),      # F == 64: layer-0 input projection fused into the forward scan (bf16 path)
     (16, 5, 64, 256, 1, 2, False, False),
+    (32, 6, 16, 128, 2, 3, True, True),       # initial hidden state on the x3 tensor-core path (2-CTA clusters)
+    (64, 11, 24, 256, 2, 4, True, True),      # ... and with 4-CTA clusters, two batch tiles
+    (96, 3, 8, 256, 1, 2, False, False),
 ]
 
 
@@ -283,7 +297,7 @@ def test_dropout_modes():
     """Train-mode dropout: elementwise and channel-wise ('spatial', one mask per (b, f) over T) input
     masks, inter-layer dropout; same mask in backward (dx is zero exactly where the input was dropped)."""
     for precision, spatial in [(p, s) for p in precisions() for s in (False, True)]:
-        B, T, F, H, L, C = (16, 12, 24, 32, 2, 3) if precision == "fp32" else (16, 12, 24, 128, 2, 3)
+        B, T, F, H, L, C = (16, 12, 24, 32, 2, 3) if precision == "fp32" else (32, 12, 24, 128, 2, 3)
         torch.manual_seed(4)
         m = _pkg().BiGRU(H, F, C, L, 50, 0.5, spatial, True, precision=precision).cuda()
         m.train()

@@ -80,9 +80,69 @@ static int run_case(int M, int N, int K, int mode, int splitk, int kshift, bool 
     return pass ? 0 : 2;
 }
 
+// x3 product: fp32 operands split into (hi, lo) bf16 pairs, A_hi B_hi + A_hi B_lo + A_lo B_hi  (nsplit = 3)
+static int run_split_case(int M, int N, int K, int mode, int splitk, int a_mn, int b_mn) {
+    std::vector<float> A((size_t)M * K), B((size_t)N * K);
+    srand(M * 13 + N * 5 + K);
+    for (auto& v : A) v = (rand() % 200001 - 100000) / 100000.f;
+    for (auto& v : B) v = (rand() % 200001 - 100000) / 100000.f;
+    std::vector<__nv_bfloat16> Ah(A.size()), Al(A.size()), Bh(B.size()), Bl(B.size());
+    auto put = [](std::vector<__nv_bfloat16>& hi, std::vector<__nv_bfloat16>& lo, size_t i, float x) {
+        hi[i] = __float2bfloat16(x); lo[i] = __float2bfloat16(x - __bfloat162float(hi[i]));
+    };
+    for (int r = 0; r < M; ++r) for (int k = 0; k < K; ++k) put(Ah, Al, a_mn ? (size_t)k * M + r : (size_t)r * K + k, A[(size_t)r * K + k]);
+    for (int r = 0; r < N; ++r) for (int k = 0; k < K; ++k) put(Bh, Bl, b_mn ? (size_t)k * N + r : (size_t)r * K + k, B[(size_t)r * K + k]);
+    __nv_bfloat16 *dAh, *dAl, *dBh, *dBl; float* dC; unsigned int* dbg;
+    CK(cudaMalloc(&dAh, Ah.size() * 2)); CK(cudaMalloc(&dAl, Ah.size() * 2)); CK(cudaMalloc(&dBh, Bh.size() * 2)); CK(cudaMalloc(&dBl, Bh.size() * 2));
+    CK(cudaMalloc(&dC, (size_t)M * N * 4)); CK(cudaMalloc(&dbg, 64));
+    CK(cudaMemcpy(dAh, Ah.data(), Ah.size() * 2, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dAl, Al.data(), Al.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dBh, Bh.data(), Bh.size() * 2, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dBl, Bl.data(), Bl.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dC, 0, (size_t)M * N * 4)); CK(cudaMemset(dbg, 0, 64));
+    CUtensorMap tA, tB, tAl, tBl;
+    int e = a_mn ? tcg::make_operand_map_mn(&tA, dAh, K, M, M) | tcg::make_operand_map_mn(&tAl, dAl, K, M, M)
+                 : tcg::make_operand_map(&tA, dAh, M, K, K) | tcg::make_operand_map(&tAl, dAl, M, K, K);
+    e |= b_mn ? tcg::make_operand_map_mn(&tB, dBh, K, N, N) | tcg::make_operand_map_mn(&tBl, dBl, K, N, N)
+              : tcg::make_operand_map(&tB, dBh, N, K, K) | tcg::make_operand_map(&tBl, dBl, N, K, K);
+    if (e) { printf("tensor map failed\n"); return 1; }
+    tcg::Params p{};
+    p.M = M; p.N = N; p.K = K; p.batch = 1; p.splitk = splitk; p.mode = mode; p.C = dC; p.ldc = N; p.a_mn = a_mn; p.b_mn = b_mn; p.dbg = dbg; p.nsplit = 3;
+    CK(tcg::launch(tA, tB, p, 0, &tAl, &tBl));
+    CK(cudaDeviceSynchronize());
+    float ms = 0.f;
+    if (mode != tcg::OUT_ATOMIC_F32) {
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        for (int i = 0; i < 5; ++i) CK(tcg::launch(tA, tB, p, 0, &tAl, &tBl));
+        cudaEventRecord(e1); CK(cudaDeviceSynchronize());
+        cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
+    }
+    unsigned int h[8]; CK(cudaMemcpy(h, dbg, 32, cudaMemcpyDeviceToHost));
+    std::vector<float> C((size_t)M * N);
+    CK(cudaMemcpy(C.data(), dC, C.size() * 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0, maxref = 0, rms = 0; long checked = 0;
+    const long total = (long)M * N; const long stride = total > 200000 ? total / 100003 : 1;
+    for (long idx = 0; idx < total; idx += stride) {
+        const int m = idx / N, n = idx % N;
+        double s = 0, s2 = 0;
+        for (int k = 0; k < K; ++k) { const double t = (double)A[(size_t)m * K + k] * B[(size_t)n * K + k]; s += t; s2 += t * t; }
+        maxerr = fmax(maxerr, fabs(s - C[idx])); maxref = fmax(maxref, fabs(s)); rms = fmax(rms, sqrt(s2)); ++checked;
+    }
+    const bool pass = h[0] == 0 && maxerr < 3e-5 * (rms + 1e-3);
+    printf("%s x3 mn=%d%d M=%d N=%d K=%d mode=%d splitk=%d: maxerr=%.3e (ref max %.2f, term rms %.2f, %ld checked) dbg=%x  %.3f ms %.1f fp32-class TFLOP/s\n",
+           pass ? "PASS" : "FAIL", a_mn, b_mn, M, N, K, mode, splitk, maxerr, maxref, rms, checked, h[0], ms, ms > 0 ? 2.0 * M * N * K / ms / 1e9 : 0.0);
+    cudaFree(dAh); cudaFree(dAl); cudaFree(dBh); cudaFree(dBl); cudaFree(dC); cudaFree(dbg);
+    return pass ? 0 : 2;
+}
+
 int main() {
     setvbuf(stdout, NULL, _IONBF, 0);
     int bad = 0;
+    bad += run_split_case(128, 128, 64, tcg::OUT_F32, 1, 0, 0);
+    bad += run_split_case(256, 384, 512, tcg::OUT_F32, 1, 0, 0);
+    bad += run_split_case(768, 256, 8192, tcg::OUT_ATOMIC_F32, 8, 1, 1);
+    bad += run_split_case(1536, 65536, 512, tcg::OUT_F32, 1, 0, 0);
+    bad += run_split_case(512, 65536, 1536, tcg::OUT_F32, 1, 0, 0);
+    bad += run_split_case(768, 512, 65536, tcg::OUT_ATOMIC_F32, 10, 1, 1);
     bad += run_case(128, 128, 64, tcg::OUT_F32, 1, 0, false, 0, 0);
     bad += run_case(128, 128, 256, tcg::OUT_F32, 1, 0, true, 0, 0);
     bad += run_case(256, 384, 512, tcg::OUT_BF16, 1, 0, true, 0, 0);
