@@ -20,14 +20,26 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import _lib
-from .parallel import allreduce_flat_
+if __package__:
+    from . import _lib
+    from .parallel import allreduce_flat_
+else:
+    # drop-in route of the reference's callers (`predict.py:16`, the notebook): this directory itself is on sys.path and
+    # the module is imported top-level as `biGRU_model`; bind the sibling modules through the package
+    import importlib as _importlib
+    import sys as _sys
+    _here = os.path.dirname(os.path.abspath(__file__))
+    if os.path.dirname(_here) not in _sys.path:
+        _sys.path.insert(0, os.path.dirname(_here))
+    _lib = _importlib.import_module(os.path.basename(_here) + "._lib")
+    allreduce_flat_ = _importlib.import_module(os.path.basename(_here) + ".parallel").allreduce_flat_
 
 _PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "bf16x3": _lib.PREC_BF16X3}
 
 
-def _stream_ptr():
-    return torch.cuda.current_stream().cuda_stream
+def _stream_ptr(device=None):
+    """Raw cudaStream_t of torch's current stream ON THE MODEL'S DEVICE (not the process-wide current device)."""
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 class _GRUWeights(nn.Module):
@@ -101,6 +113,15 @@ class _BiGRUFunction(torch.autograd.Function):
         lib = _lib.load()
         plan = model._plan_for(x)
         B = x.shape[0]
+        ctx.dev_guard = torch.cuda.device(x.device)      # the C ABI launches on the CURRENT device: make it the model's
+        ctx.dev_guard.__enter__()
+        try:
+            return _BiGRUFunction._forward(ctx, lib, plan, model, x, h0, B)
+        finally:
+            ctx.dev_guard.__exit__(None, None, None)
+
+    @staticmethod
+    def _forward(ctx, lib, plan, model, x, h0, B):
         logits = torch.empty(B, model.output_size, device=x.device, dtype=torch.float32)
         hn = torch.empty(model.n_layers * model.n_directions, B, model.hidden_size, device=x.device, dtype=torch.float32)
         need_grad = any(ctx.needs_input_grad)        # grad mode is off inside Function.forward; ask the ctx
@@ -110,8 +131,9 @@ class _BiGRUFunction(torch.autograd.Function):
         _lib.check(lib.bigru_forward(plan.handle, _lib.ptr(model._flat), _lib.ptr(x), _lib.ptr(h0),
                                      float(model.dropout_p), int(bool(model.spatial_dropout)), int(training), seed,
                                      _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(logits), _lib.ptr(hn),
-                                     _stream_ptr()), "bigru_forward")
+                                     _stream_ptr(x.device)), "bigru_forward")
         model._last_hidden = hn
+        model._last_plan_stash = (plan, stash)
         if need_grad:
             ctx.model, ctx.plan, ctx.stash, ctx.seed, ctx.training = model, plan, stash, seed, training
             ctx.save_for_backward(x, h0 if h0 is not None else torch.empty(0, device=x.device))
@@ -130,10 +152,11 @@ class _BiGRUFunction(torch.autograd.Function):
         grads = torch.empty_like(model._flat)
         dx = torch.empty_like(x) if ctx.needs_input_grad[1] else None
         dh0 = torch.empty_like(h0) if (h0 is not None and ctx.needs_input_grad[2]) else None
-        _lib.check(lib.bigru_backward(plan.handle, _lib.ptr(model._flat), _lib.ptr(x), _lib.ptr(h0),
-                                      float(model.dropout_p), int(bool(model.spatial_dropout)), int(ctx.training),
-                                      ctx.seed, _lib.ptr(ctx.stash), _lib.ptr(plan.scratch), _lib.ptr(dlogits),
-                                      _lib.ptr(grads), _lib.ptr(dx), _lib.ptr(dh0), _stream_ptr()), "bigru_backward")
+        with torch.cuda.device(x.device):
+            _lib.check(lib.bigru_backward(plan.handle, _lib.ptr(model._flat), _lib.ptr(x), _lib.ptr(h0),
+                                          float(model.dropout_p), int(bool(model.spatial_dropout)), int(ctx.training),
+                                          ctx.seed, _lib.ptr(ctx.stash), _lib.ptr(plan.scratch), _lib.ptr(dlogits),
+                                          _lib.ptr(grads), _lib.ptr(dx), _lib.ptr(dh0), _stream_ptr(x.device)), "bigru_backward")
         plan.release_stash(ctx.stash)
         ctx.stash = None
         pg = tuple(grads[o:o + n].view(shape) for (o, n, shape) in model._views)
@@ -183,6 +206,7 @@ class BiGRU(nn.Module):
         self._dp_group = None
         self._dp_world = 1
         self._last_hidden = None
+        self._last_plan_stash = None
         self._loss_cache = {}
         self._flatten()
 
@@ -262,6 +286,15 @@ class BiGRU(nn.Module):
                 raise RuntimeError(f"Expected hidden size {want}, got {tuple(hidden.shape)}")
             h0 = hidden.to(device=dev, dtype=torch.float32).contiguous()
         return x, h0
+
+    def pooled_argmax(self) -> torch.Tensor:
+        """argmax_t of the max-pooled direction sum [batch, hidden] as taken by the last ``forward`` (the routing of the
+        max-pool gradient, biGRU_model.py:125).  Valid until the next forward of the same shape."""
+        plan, stash = self._last_plan_stash
+        off = _lib.C.c_size_t()
+        _lib.check(_lib.load().bigru_stash_argmax_offset(plan.handle, _lib.C.byref(off)), "bigru_stash_argmax_offset")
+        n = plan.B * self.hidden_size * 4
+        return stash[off.value:off.value + n].view(torch.int32).view(plan.B, self.hidden_size).clone()
 
     # ------------------------------------------------------------------ reference surface
     def forward(self, input_seq, hidden=None):

@@ -139,6 +139,15 @@ extern "C" int bigru_workspace_bytes(const bigru_plan* p, size_t* stash_bytes, s
     return BIGRU_OK;
 }
 
+// where the head keeps argmax_t of the pooled output (int32 [B][H]) inside the stash of the last forward
+extern "C" int bigru_stash_argmax_offset(const bigru_plan* p, size_t* byte_offset) {
+    if (!p || !byte_offset) { bigru_set_error("stash_argmax_offset: null argument"); return BIGRU_ERR_ARG; }
+    if (p->prec == BIGRU_PREC_BF16) *byte_offset = bf16_layout(*p).arg;
+    else if (p->prec == BIGRU_PREC_BF16X3) *byte_offset = x3_layout(*p).arg;
+    else *byte_offset = (size_t)stash_layout(*p).arg * sizeof(float);
+    return BIGRU_OK;
+}
+
 static inline unsigned nblk(int64_t n, int bs) { return (unsigned)cdiv64(n, bs); }
 
 // ------------------------------------------------------------------------------------------
@@ -411,12 +420,9 @@ extern "C" int bigru_window_features(const float* d_close, const float* d_high, 
     // the reference's own configuration (config.py:40-49) runs with compile-time periods
     const bool fast = n_vol == 2 && cfg.vol_p[0] == 6 && cfg.vol_p[1] == 20 && n_price == 1 && cfg.price_p[0] == 20 && n_delta == 1 &&
                       cfg.delta_p[0] == 12 && bb_period == 20 && stochastic;
-    static size_t smem_attr[2] = {0, 0};
-    if (smem > smem_attr[fast]) {
+    if (smem > 48 * 1024)        // per-device opt-in, set on every call (no process-wide cache: a second GPU would miss it)
         CUDA_TRY(fast ? cudaFuncSetAttribute(window_features_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                       : cudaFuncSetAttribute(window_features_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_attr[fast] = smem;
-    }
     const unsigned blocks = (unsigned)std::min<int64_t>((n + FEAT_TR - 1) / FEAT_TR, 148 * 8);
     if (fast)
         KLAUNCH(KC_GATHER, 0.0, 4.0 * n * (5 + cfg.n_out + 4), (cudaStream_t)stream,
@@ -441,11 +447,8 @@ extern "C" int bigru_infer_window(const float* d_params, const float* d_x, const
         bigru_set_error("infer_window: window too large for the single-CTA path (D*H=%d, %zu bytes of shared memory); use bigru_forward", DH, smem);
         return BIGRU_ERR_UNSUPPORTED;
     }
-    static size_t smem_attr = 0;
-    if (smem > 48 * 1024 && smem > smem_attr) {
+    if (smem > 48 * 1024)
         CUDA_TRY(cudaFuncSetAttribute(infer_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_attr = smem;
-    }
     const int threads = std::max(32, ((DH + 31) / 32) * 32);
     KLAUNCH(KC_MISC, 0.0, 0.0, (cudaStream_t)stream,
             infer_window_kernel<<<B, threads, smem, (cudaStream_t)stream>>>(d_params, d_x, d_xmin, d_xmax, T, F, H, L, C, D, d_logits, d_probs));

@@ -22,7 +22,7 @@ struct X3Layout {              // byte offsets, 1024-aligned
     size_t Yhi[16], Ylo[16], YB[16], G[16], Xhi[16], Xlo[16];
     size_t Wih_hi[16], Wih_lo[16], WihT_hi[16], WihT_lo[16], Wimg[16], WTimg[16], bfold[16], bhn[16];
     size_t cat, arg, dbg, stash_total;
-    size_t gi, dghn_hi, dghn_lo, dYa, dYb, h0_hi, h0_lo, scratch_total;
+    size_t gi, dghn_hi, dghn_lo, dYa, dYb, gh0, scratch_total;
 };
 static X3Layout x3_layout(const bigru_plan& p) {
     X3Layout L{};
@@ -56,8 +56,7 @@ static X3Layout x3_layout(const bigru_plan& p) {
     L.dghn_lo = o; o = al(o + R * D * H * 2);
     L.dYa = o; o = al(o + R * wide * 4);
     L.dYb = o; o = al(o + R * wide * 4);
-    L.h0_hi = o; o = al(o + (size_t)p.B * DH * 2);
-    L.h0_lo = o; o = al(o + (size_t)p.B * DH * 2);
+    L.gh0 = o; o = al(o + (size_t)p.B * D * 3 * H * 4);          // W_hh h0 of the layer being scanned (initial state given)
     L.scratch_total = o;
     return L;
 }
@@ -259,10 +258,16 @@ static int forward_x3(const bigru_plan& p, const float* params, const float* x, 
             g.C = W + L.gi; g.ldc = R; g.bias = (const float*)(S + L.bfold[l]); g.bias_per_row = 1; g.dbg = dbg;
             TRY(tc_gemm(S + L.Wih_hi[l], D * 3 * H, I, Xhi, R, I, g, st, KC_TC_GEMM, S + L.Wih_lo[l], Xlo));
         }
+        if (h0) {   // recurrent product of the initial state, exact fp32 (tiny: B x 3H x H per direction); the scan starts at step 1
+            GemmArgs r = gemm_args(h0 + (int64_t)l * D * B * H, params + p.off_whh(l, 0), (float*)(W + L.gh0), B, 3 * H, H, H, 1, H, 1, 3 * H);
+            r.batch = D; r.zA = (int64_t)B * H; r.zB = p.ld_block(l); r.zC = (int64_t)B * 3 * H;
+            TRY(sgemm_launch(r, st));
+        }
         tcx::FwdParams f{};
         f.B = B; f.T = T; f.H = H; f.D = D;
         f.Wimg = (const bf16_t*)(S + L.Wimg[l]); f.giX = (const float*)(W + L.gi); f.b_hn = (const float*)(S + L.bhn[l]);
         f.h0 = h0 ? h0 + (int64_t)l * D * B * H : nullptr;
+        f.gh0 = h0 ? (const float*)(W + L.gh0) : nullptr;
         f.GX = (float*)(S + L.G[l]); f.YBX = (float*)(S + L.YB[l]);
         f.hn_out = hn ? hn + (int64_t)l * D * B * H : nullptr;
         f.Yhi = (bf16_t*)(S + L.Yhi[l]); f.Ylo = (bf16_t*)(S + L.Ylo[l]); f.dbg = dbg;

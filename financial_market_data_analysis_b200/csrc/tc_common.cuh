@@ -6,21 +6,23 @@
 #include <cuda_bf16.h>
 #include <cstdint>
 
-#ifndef BIGRU_SPIN_LIMIT
-#define BIGRU_SPIN_LIMIT (1u << 22)     // bounded waits: a protocol bug reports instead of hanging the GPU
-#endif
-
 namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---- debug / watchdog ---------------------------------------------------------------------------
-// dbg[0] = first error code (0 = none), dbg[1..] = context.  Written once with atomicCAS.
+// dbg[0] = first error code (0 = none), dbg[1..] = context.  Written once with atomicCAS.  A wait that ran into the
+// watchdog means the kernel's protocol stalled (or the GPU was preempted for seconds): the kernel must not carry on and
+// hand incomplete activations / gradients to the optimiser, so it traps - the stream reports cudaErrorLaunchFailure and
+// the next C-ABI call returns BIGRU_ERR_CUDA.  (Stand-alone bring-up tools define BIGRU_NO_TRAP to read `dbg` instead.)
 __device__ __forceinline__ void report_timeout(unsigned int* dbg, unsigned int code, unsigned int a, unsigned int b) {
     if (dbg && atomicCAS(dbg, 0u, code) == 0u) {
         dbg[1] = blockIdx.x; dbg[2] = threadIdx.x; dbg[3] = a; dbg[4] = b;
         __threadfence_system();
     }
+#ifndef BIGRU_NO_TRAP
+    __trap();
+#endif
 }
 
 // ---- mbarrier -----------------------------------------------------------------------------------
@@ -63,7 +65,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
 }
 // bounded wait (wall-clock, %globaltimer): returns false after BIGRU_WAIT_NS and records the site
 #ifndef BIGRU_WAIT_NS
-#define BIGRU_WAIT_NS 2000000000ull
+#define BIGRU_WAIT_NS 5000000000ull
 #endif
 __device__ __forceinline__ unsigned long long gtime_ns() {
     unsigned long long t;
@@ -89,6 +91,25 @@ __device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity
     }
     report_timeout(dbg, code, parity, 1);
     return false;
+}
+
+// ---- explicit shared-space accesses (32-bit shared addresses): pointers rebuilt through integer arithmetic lose their
+// address space and compile to generic LD.E / ST.E; these stay LDS / STS
+__device__ __forceinline__ void sts_f4(uint32_t addr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_bf16(uint32_t addr, __nv_bfloat16 v) {
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(__bfloat16_as_ushort(v)) : "memory");
 }
 
 // ---- proxies / fences ---------------------------------------------------------------------------

@@ -382,7 +382,7 @@ static inline int make_operand_map_mn(CUtensorMap* m, const void* base, uint64_t
 
 static inline cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p_in, cudaStream_t st,
                                  const CUtensorMap* tmAlo = nullptr, const CUtensorMap* tmBlo = nullptr) {
-    {   // the opt-in is per device: (re)apply it whenever the current device has not been seen (cheap, no process-wide flag)
+    {   // the shared-memory opt-in is per device: cache it per device ordinal, not process-wide
         static bool attr_set[64] = {};
         int dev = 0;
         cudaGetDevice(&dev);

@@ -495,12 +495,9 @@ static inline cudaError_t launch_fwd(const FwdParams& p_in, cudaStream_t st) {
     const size_t smem = fwd_smem_bytes(p.H, fx);
     void (*kern)(FwdParams) = p.H == 128 ? (fx ? gru_scan_fwd_kernel<128, true> : gru_scan_fwd_kernel<128, false>)
                                          : (fx ? gru_scan_fwd_kernel<256, true> : gru_scan_fwd_kernel<256, false>);
-    static bool attr[4] = {false, false, false, false};
-    const int ai = (CS - 1) * 2 + (fx ? 1 : 0);
-    if (!attr[ai]) {
+    {   // the shared-memory opt-in is per device (and cheap): set it on every launch rather than caching it process-wide
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr[ai] = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(p.D * (p.B / NB) * CS));
@@ -893,11 +890,9 @@ static inline cudaError_t launch_bwd(const BwdParams& p_in, cudaStream_t st) {
     if (p.H != 128 && p.H != 256) return cudaErrorInvalidValue;
     const size_t smem = bwd_smem_bytes(p.H);
     void (*kern)(BwdParams) = p.H == 128 ? gru_scan_bwd_kernel<128> : gru_scan_bwd_kernel<256>;
-    static bool attr[2] = {false, false};
-    if (!attr[CS - 1]) {
+    {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr[CS - 1] = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(p.D * (p.B / NB) * CS));

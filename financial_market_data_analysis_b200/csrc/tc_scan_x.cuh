@@ -92,7 +92,9 @@ struct FwdParams {
     const __nv_bfloat16* Wimg;    // [D][CS][128 rows: hi units, lo units][3][H]
     const float* giX;
     const float* b_hn;            // [D][H]
-    const float* h0;              // nullable [D][B][H]: initial hidden state of this layer
+    const float* h0;              // nullable [D][B][H]: initial hidden state of this layer ...
+    const float* gh0;             // ... and its recurrent product W_hh h0 [D][B][3H] (fp32, formed by the caller): step 0 reads it
+                                  // instead of a tensor-core product, so the scan itself always starts from step 1
     float* GX;
     float* YBX;
     float* hn_out;                // nullable [D][B][H]
@@ -144,13 +146,21 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_fwd_kernel(const __grid_
     const int cluster_id = blockIdx.x / CS;
     const int ntiles = B / NB;
     const int d = cluster_id / ntiles, tile = cluster_id % ntiles;
-    const bool has_h0 = p.h0 != nullptr;
+    const bool has_h0 = p.h0 != nullptr && p.gh0 != nullptr;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 8; ++i) tc::mbar_init(&h_full[i], 1);
         tc::mbar_init(mma_done, 1);
         tc::mbar_init(epi_done, EPI_WARPS);
         for (int i = 0; i < NSF; ++i) { tc::mbar_init(&in_full[i], 1); tc::mbar_init(&in_empty[i], EPI_WARPS); }
+        // first use of the per-source "peer chunk landed" barriers (h_s lands in buffer s & 1): armed here, before the
+        // cluster-wide sync below, so that a fast peer's st.async bytes can never reach a barrier that does not expect them
+        if (CS > 1)
+            for (uint32_t u = 0; u < (uint32_t)CS; ++u) {
+                if (u == c) continue;
+                if (T > 1) tc::mbar_arrive_expect_tx(&h_full[u], 2 * H_CHUNK);         // h_0
+                if (T > 2) tc::mbar_arrive_expect_tx(&h_full[4 + u], 2 * H_CHUNK);     // h_1
+            }
         tc::fence_mbar_init();
     }
     if (warp == EPI_WARPS) tc::tmem_alloc(tmem_slot, 512);
@@ -159,22 +169,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_fwd_kernel(const __grid_
     if (CS > 1) tc::cluster_sync_all();
     tc::tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
-    if (warp < EPI_WARPS) {
-        tcs::load_weights_to_tmem(p.Wimg + ((size_t)d * CS + c) * 128 * 3 * H, 3 * H, tmem, A_COL, warp, lane);
-        if (has_h0) {
-            // initial hidden state -> operand tile of step 0 (buffer 1: step s reads buffer (s-1)&1), all H columns locally
-            const int tid = threadIdx.x;
-            for (int e = tid; e < NB * H; e += EPI_WARPS * 32) {
-                const int row = e / H, k = e % H;
-                __nv_bfloat16 hi, lo;
-                split_bf16(p.h0[((int64_t)d * B + tile * NB + row) * H + k], hi, lo);
-                const uint32_t off = (uint32_t)(k >> 6) * H_CHUNK + tc::sw128_offset(row, k & 63);
-                *reinterpret_cast<__nv_bfloat16*>(sH + (size_t)2 * TILE_BYTES + off) = hi;
-                *reinterpret_cast<__nv_bfloat16*>(sH + (size_t)3 * TILE_BYTES + off) = lo;
-            }
-            tc::fence_proxy_async_smem();
-        }
-    }
+    if (warp < EPI_WARPS) tcs::load_weights_to_tmem(p.Wimg + ((size_t)d * CS + c) * 128 * 3 * H, 3 * H, tmem, A_COL, warp, lane);
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
@@ -197,8 +192,10 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_fwd_kernel(const __grid_
         // ---- control thread: issues the 24*KC MMAs of a step; K chunk u is ready when source CTA u's bytes have landed
         if (tc::elect_one()) {
             bool ok = true;
-            if (CS > 1 && T > 1)
-                for (uint32_t u = 0; u < (uint32_t)CS; ++u) if (u != c) tc::mbar_arrive_expect_tx(&h_full[u], 2 * H_CHUNK);
+            // h_s lands in buffer s & 1 and is multiplied at step s + 1 (step 0 has no product: h_-1 = 0, or the caller supplies
+            // W_hh h0).  The first use of every barrier was armed at initialisation, every later one right after the previous
+            // use was consumed; uses are counted, so the phase parities need no case analysis.
+            uint32_t epi_rounds = 0, hf_use0 = 0, hf_use1 = 0;
             auto store_tile = [&](int step) {             // this CTA's 64 columns of Y (hi, lo) for time step `step`
                 const int tt = d == 0 ? step : T - 1 - step;
                 const uint8_t* src = sH + (size_t)(step & 1) * 2 * TILE_BYTES + (size_t)c * H_CHUNK;
@@ -207,12 +204,11 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_fwd_kernel(const __grid_
                 tc::tma_store_commit();
             };
             const uint32_t hb0 = tc::smem_u32(sH);
-            for (int s = has_h0 ? 0 : 1; s < T; ++s) {
-                const int pb = (s - 1) & 1;               // s == 0 (initial state given): buffer 1
+            for (int s = 1; s < T; ++s) {
+                const int pb = (s - 1) & 1;
                 const uint32_t tb = hb0 + (uint32_t)pb * 2 * TILE_BYTES;
-                if (s > 0) {
-                    if (ok) ok = tc::mbar_wait(epi_done, (s - 1) & 1, p.dbg, 0x1400 + (s & 0xff));
-                }
+                if (ok) ok = tc::mbar_wait(epi_done, epi_rounds & 1, p.dbg, 0x1400 + (s & 0xff));
+                ++epi_rounds;
                 SCANX_TS(0);
                 tc::tcgen05_fence_after();
                 // own chunk first (it is local), then the peers' chunks in ring order as they land
@@ -221,20 +217,19 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_fwd_kernel(const __grid_
                 SCANX_TS(1);
                 for (uint32_t i = 1; i < (uint32_t)CS; ++i) {
                     const uint32_t u = (c + i) % CS;
-                    if (s > 0) {
-                        if (ok) ok = tc::mbar_wait(&h_full[pb * 4 + u], ((s - 1) >> 1) & 1, p.dbg, 0x1500 + (s & 0xff));
-                        if (s + 1 < T) tc::mbar_arrive_expect_tx(&h_full[(s & 1) * 4 + u], 2 * H_CHUNK);
-                        tc::tcgen05_fence_after();
-                    }
+                    if (ok) ok = tc::mbar_wait(&h_full[pb * 4 + u], (pb ? hf_use1 : hf_use0) & 1, p.dbg, 0x1500 + (s & 0xff));
+                    if (s + 2 < T) tc::mbar_arrive_expect_tx(&h_full[pb * 4 + u], 2 * H_CHUNK);      // h_{s+1} comes to this buffer
+                    tc::tcgen05_fence_after();
                     fwd_issue_chunk<H, false>(tmem, tmem + A_COL + u * 32, tc::umma_desc_k_sw128(tb + u * H_CHUNK),
                                               tc::umma_desc_k_sw128(tb + TILE_BYTES + u * H_CHUNK));
                 }
+                if (pb) ++hf_use1; else ++hf_use0;
                 tc::tma_store_wait_read();
                 tc::umma_commit(mma_done);
                 SCANX_TS(3);
-                if (s > 0) store_tile(s - 1);
+                store_tile(s - 1);
             }
-            if (ok) ok = tc::mbar_wait(epi_done, (T - 1) & 1, p.dbg, 0x1400);
+            if (ok) ok = tc::mbar_wait(epi_done, epi_rounds & 1, p.dbg, 0x1400);
             store_tile(T - 1);
             tc::tma_store_wait_all();
         }
@@ -255,11 +250,42 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_fwd_kernel(const __grid_
         for (int i = 0; i < 8; ++i) h_off[i] = c * H_CHUNK + tc::sw128_offset(c0 + i, j);
         // the 16-byte piece this lane forwards to the peers: 8 units of lane group lane/8, batch row c0 + lane%8
         const uint32_t fwd_off = c * H_CHUNK + tc::sw128_offset(c0 + (lane & 7), (q & 1) * 32 + (lane >> 3) * 8);
-        float4* xmine = reinterpret_cast<float4*>(sX) + (size_t)warp * 6 * 32 + lane;
-        const float4* xpeer = reinterpret_cast<const float4*>(sX) + (size_t)(warp ^ 2) * 6 * 32 + lane;
+        const uint32_t sIn_u = tc::smem_u32(sIn), sH_u = tc::smem_u32(sH);
+        const uint32_t xmine = tc::smem_u32(sX) + (uint32_t)((warp * 6 * 32 + lane) * 16);
+        const uint32_t xpeer = tc::smem_u32(sX) + (uint32_t)(((warp ^ 2) * 6 * 32 + lane) * 16);
         const int pair_id = 2 + (q & 1) + 2 * half;
         constexpr float L2E = 1.4426950408889634f;
         bool ok = true;
+        uint32_t mma_rounds = 0;
+        // publish this thread's 8 values of h (hi, lo) in operand buffer `buf`: own tile + every peer's (st.async on the
+        // source-indexed barrier), then one arrival per warp on epi_done
+        auto publish = [&](const float (&h8)[8], int buf, bool to_peers) {
+            const uint32_t hb = sH_u + (uint32_t)buf * 2 * TILE_BYTES;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                __nv_bfloat16 hi, lo;
+                split_bf16(h8[i], hi, lo);
+                tc::sts_bf16(hb + h_off[i], hi);
+                tc::sts_bf16(hb + TILE_BYTES + h_off[i], lo);
+            }
+            tc::tcgen05_fence_before();
+            if (CS > 1 && to_peers) {
+                __syncwarp();
+                const uint32_t a_hi = hb + fwd_off, a_lo = a_hi + TILE_BYTES, a_bar = tc::smem_u32(&h_full[buf * 4 + (int)c]);
+                const uint4 vh = tc::lds_u4(a_hi);
+                const uint4 vl = tc::lds_u4(a_lo);
+#pragma unroll
+                for (uint32_t i = 1; i < (uint32_t)CS; ++i) {
+                    const uint32_t pr = (c + i) % CS;
+                    const uint32_t rbar = tc::mapa_u32(a_bar, pr);
+                    tc::st_async_v4(tc::mapa_u32(a_hi, pr), vh, rbar);
+                    tc::st_async_v4(tc::mapa_u32(a_lo, pr), vl, rbar);
+                }
+            }
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(epi_done);
+        };
         for (int s = 0; s < T; ++s) {
             const int t = d == 0 ? s : T - 1 - s;
             const size_t blk = blk_index(d, tile, t, (int)c, ntiles, T, CS);
@@ -267,20 +293,20 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_fwd_kernel(const __grid_
             {
                 const int st = s % NSF;
                 if (ok) ok = tc::mbar_wait(&in_full[st], (s / NSF) & 1, p.dbg, 0x1200 + (s & 0xff));
-                const float4* gp = reinterpret_cast<const float4*>(sIn + (size_t)st * GI_BLOCK) + 2 * tid;
-                const float4 a0 = gp[0], a1 = gp[1], b0 = gp[512], b1 = gp[513], n0 = gp[1024], n1 = gp[1025];
+                const uint32_t gp = sIn_u + (uint32_t)st * GI_BLOCK + 32u * tid;
+                const float4 a0 = tc::lds_f4(gp), a1 = tc::lds_f4(gp + 16), b0 = tc::lds_f4(gp + 8192), b1 = tc::lds_f4(gp + 8192 + 16),
+                             n0 = tc::lds_f4(gp + 16384), n1 = tc::lds_f4(gp + 16384 + 16);
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&in_empty[st]);
                 gr[0] = a0.x; gr[1] = a0.y; gr[2] = a0.z; gr[3] = a0.w; gr[4] = a1.x; gr[5] = a1.y; gr[6] = a1.z; gr[7] = a1.w;
                 gz[0] = b0.x; gz[1] = b0.y; gz[2] = b0.z; gz[3] = b0.w; gz[4] = b1.x; gz[5] = b1.y; gz[6] = b1.z; gz[7] = b1.w;
                 gn[0] = n0.x; gn[1] = n0.y; gn[2] = n0.z; gn[3] = n0.w; gn[4] = n1.x; gn[5] = n1.y; gn[6] = n1.z; gn[7] = n1.w;
             }
-            const int buf = s & 1;
-            uint8_t* hb = sH + (size_t)buf * 2 * TILE_BYTES;
             float ar[8], az[8], an[8];
-            if (s > 0 || has_h0) {
+            if (s > 0) {
                 if (tid == 0) SCANX_TS(6);
-                if (ok) ok = tc::mbar_wait(mma_done, has_h0 ? (uint32_t)(s & 1) : (uint32_t)((s - 1) & 1), p.dbg, 0x1600 + (s & 0xff));
+                if (ok) ok = tc::mbar_wait(mma_done, mma_rounds & 1, p.dbg, 0x1600 + (s & 0xff));
+                ++mma_rounds;
                 if (tid == 0) SCANX_TS(7);
                 tc::tcgen05_fence_after();
                 float v[3][16];
@@ -291,14 +317,14 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_fwd_kernel(const __grid_
                 // hi rows keep columns [0, 8) of their half and hand [8, 16) to the lo rows' warp, and vice versa
 #pragma unroll
                 for (int g = 0; g < 3; ++g) {
-                    xmine[(g * 2 + 0) * 32] = make_float4(part ? v[g][0] : v[g][8], part ? v[g][1] : v[g][9], part ? v[g][2] : v[g][10], part ? v[g][3] : v[g][11]);
-                    xmine[(g * 2 + 1) * 32] = make_float4(part ? v[g][4] : v[g][12], part ? v[g][5] : v[g][13], part ? v[g][6] : v[g][14], part ? v[g][7] : v[g][15]);
+                    tc::sts_f4(xmine + (uint32_t)((g * 2 + 0) * 512), make_float4(part ? v[g][0] : v[g][8], part ? v[g][1] : v[g][9], part ? v[g][2] : v[g][10], part ? v[g][3] : v[g][11]));
+                    tc::sts_f4(xmine + (uint32_t)((g * 2 + 1) * 512), make_float4(part ? v[g][4] : v[g][12], part ? v[g][5] : v[g][13], part ? v[g][6] : v[g][14], part ? v[g][7] : v[g][15]));
                 }
                 pair_barrier(pair_id);
                 float o[3][8];
 #pragma unroll
                 for (int g = 0; g < 3; ++g) {
-                    const float4 x0 = xpeer[(g * 2 + 0) * 32], x1 = xpeer[(g * 2 + 1) * 32];
+                    const float4 x0 = tc::lds_f4(xpeer + (uint32_t)((g * 2 + 0) * 512)), x1 = tc::lds_f4(xpeer + (uint32_t)((g * 2 + 1) * 512));
                     o[g][0] = x0.x; o[g][1] = x0.y; o[g][2] = x0.z; o[g][3] = x0.w; o[g][4] = x1.x; o[g][5] = x1.y; o[g][6] = x1.z; o[g][7] = x1.w;
                 }
 #pragma unroll
@@ -308,12 +334,18 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_fwd_kernel(const __grid_
                     an[i] = (part ? v[2][8 + i] : v[2][i]) + o[2][i];
                 }
                 if (tid == 0) SCANX_TS(9);
+            } else if (has_h0) {
+                // step 0 with an initial state: W_hh h0 comes from the caller (fp32 FFMA GEMM, [D][B][3H])
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float* gp = p.gh0 + ((int64_t)d * B + tile * NB + c0 + i) * 3 * H + unit;
+                    ar[i] = gp[0]; az[i] = gp[H]; an[i] = gp[2 * H];
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { ar[i] = 0.f; az[i] = 0.f; an[i] = 0.f; }
             }
             float r8[8], z8[8], n8[8], hn8[8];
-            __nv_bfloat16 hhi[8], hlo[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 // r = 1/(1+ea), z = 1/(1+eb), n = tanh(cn) = 1 - 2/(1+et): three ex2, two reciprocals
@@ -327,31 +359,10 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_fwd_kernel(const __grid_
                 const float z = inv * (1.f + et);
                 const float n = fmaf(-2.f * inv, 1.f + eb, 1.f);
                 r8[i] = r; z8[i] = z; n8[i] = n;
-                const float h = fmaf(z, hprev[i] - n, n);
-                hprev[i] = h;
-                split_bf16(h, hhi[i], hlo[i]);
-                *reinterpret_cast<__nv_bfloat16*>(hb + h_off[i]) = hhi[i];
-                *reinterpret_cast<__nv_bfloat16*>(hb + TILE_BYTES + h_off[i]) = hlo[i];
+                hprev[i] = fmaf(z, hprev[i] - n, n);
             }
             if (tid == 0) SCANX_TS(10);
-            tc::tcgen05_fence_before();
-            if (CS > 1 && s + 1 < T) {
-                __syncwarp();
-                uint8_t* cp = hb + fwd_off;
-                const uint4 vh = *reinterpret_cast<const uint4*>(cp);
-                const uint4 vl = *reinterpret_cast<const uint4*>(cp + TILE_BYTES);
-                const uint32_t a_hi = tc::smem_u32(cp), a_lo = tc::smem_u32(cp + TILE_BYTES), a_bar = tc::smem_u32(&h_full[buf * 4 + (int)c]);
-#pragma unroll
-                for (uint32_t i = 1; i < (uint32_t)CS; ++i) {
-                    const uint32_t pr = (c + i) % CS;
-                    const uint32_t rbar = tc::mapa_u32(a_bar, pr);
-                    tc::st_async_v4(tc::mapa_u32(a_hi, pr), vh, rbar);
-                    tc::st_async_v4(tc::mapa_u32(a_lo, pr), vl, rbar);
-                }
-            }
-            tc::fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(epi_done);
+            publish(hprev, s & 1, s + 1 < T);
             if (tid == 0) SCANX_TS(11);
             {   // stash (off the chain)
                 float4* gs = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(p.GX) + blk * G_BLOCK) + 2 * tid;
@@ -608,12 +619,13 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_bwd_kernel(const __grid_
         for (int i = 0; i < 8; ++i) e_off[i] = tc::sw128_offset(c0 + i, j);
         // partial-sum destination inside a receive buffer: [src = c][cg = 4*half + i][jd] float4, jd = (q & 1)*32 + lane
         const uint32_t r_off = (((uint32_t)c * 8 + 4 * half) * 64 + (uint32_t)((q & 1) * 32 + lane)) * 16;
+        const uint32_t sIn_u = tc::smem_u32(sIn), sR_u = tc::smem_u32(sR), sD_u = tc::smem_u32(sD), sN_u = tc::smem_u32(sN);
         bool ok = true;
         // recurrent part of dh for this thread's (unit, 8 columns) at step s: every CTA's row blocks -> partial sums (hi + lo
         // blocks of one k share a lane) -> owner's receive buffer (st.async / local store) -> sum over the CS sources
         auto reduce_partials = [&](int s, float (&acc)[8]) {
             const int buf = s & 1;
-            uint8_t* rb_local = sR + (size_t)buf * RECV_BYTES;
+            const uint32_t rb_local = sR_u + (uint32_t)buf * RECV_BYTES;
             const uint32_t rbar_l = tc::smem_u32(&recv_full[buf]);
             auto route = [&](int kh) {
                 float vh[16], vl[16];
@@ -622,14 +634,14 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_bwd_kernel(const __grid_
                 tmem_ld16f(ta + (uint32_t)((1 * NKH + kh) * NB), vl);
                 tc::tmem_ld_wait();
                 const uint32_t dest = (uint32_t)(2 * kh + (q >> 1));
-                uint8_t* lp = rb_local + r_off;
+                const uint32_t lp = rb_local + r_off;
                 if (dest == c) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        *reinterpret_cast<float4*>(lp + (size_t)i * 64 * 16) =
-                            make_float4(vh[4 * i] + vl[4 * i], vh[4 * i + 1] + vl[4 * i + 1], vh[4 * i + 2] + vl[4 * i + 2], vh[4 * i + 3] + vl[4 * i + 3]);
+                        tc::sts_f4(lp + (uint32_t)(i * 64 * 16),
+                                   make_float4(vh[4 * i] + vl[4 * i], vh[4 * i + 1] + vl[4 * i + 1], vh[4 * i + 2] + vl[4 * i + 2], vh[4 * i + 3] + vl[4 * i + 3]));
                 } else {
-                    const uint32_t ra = tc::mapa_u32(tc::smem_u32(lp), dest), rb = tc::mapa_u32(rbar_l, dest);
+                    const uint32_t ra = tc::mapa_u32(lp, dest), rb = tc::mapa_u32(rbar_l, dest);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         uint4 u;
@@ -657,8 +669,8 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_bwd_kernel(const __grid_
             for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 #pragma unroll
             for (int src = 0; src < CS; ++src) {
-                const float4* rp = reinterpret_cast<const float4*>(rb_local) + ((size_t)src * 8 + 2 * (warp >> 1)) * 64 + j;
-                const float4 x0 = rp[0], x1 = rp[64];
+                const uint32_t rp = rb_local + (uint32_t)((((src * 8 + 2 * (warp >> 1)) * 64) + j) * 16);
+                const float4 x0 = tc::lds_f4(rp), x1 = tc::lds_f4(rp + 64 * 16);
                 acc[0] += x0.x; acc[1] += x0.y; acc[2] += x0.z; acc[3] += x0.w; acc[4] += x1.x; acc[5] += x1.y; acc[6] += x1.z; acc[7] += x1.w;
             }
         };
@@ -669,12 +681,12 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_bwd_kernel(const __grid_
             {
                 const int st = s % NSB;
                 if (ok) ok = tc::mbar_wait(&in_full[st], (s / NSB) & 1, p.dbg, 0x2200 + (s & 0xff));
-                const uint8_t* base = sIn + (size_t)st * BWD_STAGE;
-                const float4* gp = reinterpret_cast<const float4*>(base) + 2 * tid;
-                const float4 a0 = gp[0], a1 = gp[1], b0 = gp[512], b1 = gp[513], n0 = gp[1024], n1 = gp[1025], m0 = gp[1536], m1 = gp[1537];
+                const uint32_t gp = sIn_u + (uint32_t)st * BWD_STAGE + 32u * tid;
+                const float4 a0 = tc::lds_f4(gp), a1 = tc::lds_f4(gp + 16), b0 = tc::lds_f4(gp + 8192), b1 = tc::lds_f4(gp + 8192 + 16),
+                             n0 = tc::lds_f4(gp + 16384), n1 = tc::lds_f4(gp + 16384 + 16), m0 = tc::lds_f4(gp + 24576), m1 = tc::lds_f4(gp + 24576 + 16);
                 float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0, y0 = p0, y1 = p0;
-                if (!first) { const float4* hp = reinterpret_cast<const float4*>(base + G_BLOCK) + 2 * tid; p0 = hp[0]; p1 = hp[1]; }
-                if (!top) { const float4* yp = reinterpret_cast<const float4*>(base + G_BLOCK + YB_BLOCK) + 2 * tid; y0 = yp[0]; y1 = yp[1]; }
+                if (!first) { p0 = tc::lds_f4(gp + G_BLOCK); p1 = tc::lds_f4(gp + G_BLOCK + 16); }
+                if (!top) { y0 = tc::lds_f4(gp + G_BLOCK + YB_BLOCK); y1 = tc::lds_f4(gp + G_BLOCK + YB_BLOCK + 16); }
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&in_empty[st]);
                 vr[0] = a0.x; vr[1] = a0.y; vr[2] = a0.z; vr[3] = a0.w; vr[4] = a1.x; vr[5] = a1.y; vr[6] = a1.z; vr[7] = a1.w;
@@ -708,8 +720,8 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_bwd_kernel(const __grid_
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[i] = 0.f;
             }
-            uint8_t* tileb = sD + (size_t)buf * 2 * DT_BYTES;
-            uint8_t* nbuf = sN + (size_t)buf * 2 * H_CHUNK;
+            const uint32_t tileb = sD_u + (uint32_t)buf * 2 * DT_BYTES;
+            const uint32_t nbuf = sN_u + (uint32_t)buf * 2 * H_CHUNK;
             float dar[8], daz[8], dan[8], danr[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -721,14 +733,14 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_bwd_kernel(const __grid_
                 dhz[i] = dh * vz[i];
                 __nv_bfloat16 hi, lo;
                 split_bf16(dar[i], hi, lo);
-                *reinterpret_cast<__nv_bfloat16*>(tileb + e_off[i]) = hi;
-                *reinterpret_cast<__nv_bfloat16*>(tileb + DT_BYTES + e_off[i]) = lo;
+                tc::sts_bf16(tileb + e_off[i], hi);
+                tc::sts_bf16(tileb + DT_BYTES + e_off[i], lo);
                 split_bf16(daz[i], hi, lo);
-                *reinterpret_cast<__nv_bfloat16*>(tileb + H_CHUNK + e_off[i]) = hi;
-                *reinterpret_cast<__nv_bfloat16*>(tileb + DT_BYTES + H_CHUNK + e_off[i]) = lo;
+                tc::sts_bf16(tileb + H_CHUNK + e_off[i], hi);
+                tc::sts_bf16(tileb + DT_BYTES + H_CHUNK + e_off[i], lo);
                 split_bf16(danr[i], hi, lo);
-                *reinterpret_cast<__nv_bfloat16*>(tileb + 2 * H_CHUNK + e_off[i]) = hi;
-                *reinterpret_cast<__nv_bfloat16*>(tileb + DT_BYTES + 2 * H_CHUNK + e_off[i]) = lo;
+                tc::sts_bf16(tileb + 2 * H_CHUNK + e_off[i], hi);
+                tc::sts_bf16(tileb + DT_BYTES + 2 * H_CHUNK + e_off[i], lo);
             }
             if (tid == 0) SCANX_TS(9);
             tc::tcgen05_fence_before();
@@ -740,8 +752,8 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_bwd_kernel(const __grid_
             for (int i = 0; i < 8; ++i) {
                 __nv_bfloat16 hi, lo;
                 split_bf16(dan[i], hi, lo);
-                *reinterpret_cast<__nv_bfloat16*>(nbuf + e_off[i]) = hi;
-                *reinterpret_cast<__nv_bfloat16*>(nbuf + H_CHUNK + e_off[i]) = lo;
+                tc::sts_bf16(nbuf + e_off[i], hi);
+                tc::sts_bf16(nbuf + H_CHUNK + e_off[i], lo);
             }
             tc::fence_proxy_async_smem();
             __syncwarp();

@@ -16,7 +16,16 @@ from itertools import islice
 import torch
 from torch.utils.data import Dataset
 
-from . import _lib
+if __package__:
+    from . import _lib
+else:                                   # drop-in route: this directory is on sys.path (see biGRU_model.py)
+    import importlib as _importlib
+    import os as _os
+    import sys as _sys
+    _here = _os.path.dirname(_os.path.abspath(__file__))
+    if _os.path.dirname(_here) not in _sys.path:
+        _sys.path.insert(0, _os.path.dirname(_here))
+    _lib = _importlib.import_module(_os.path.basename(_here) + "._lib")
 
 try:                                    # the reference reads these from its config.py (:5)
     from config import ask_levels, bid_levels

@@ -65,6 +65,11 @@ int  bigru_param_offset(const bigru_plan* plan, int layer, int dir, int which,
 /* stash: activations kept from forward for backward; scratch: reusable temporary space */
 int  bigru_workspace_bytes(const bigru_plan* plan, size_t* stash_bytes, size_t* scratch_bytes);
 
+/* byte offset, inside the stash written by the last forward, of argmax_t of the max-pooled output (int32 [B][H],
+ * biGRU_model.py:125).  The max-pool's gradient routing is discontinuous where two time steps tie to within rounding;
+ * parity tests read the routing that was actually taken (tests/test_gpu_parity.py). */
+int  bigru_stash_argmax_offset(const bigru_plan* plan, size_t* byte_offset);
+
 /* --- BiGRU.forward (biGRU_model.py:63-138): dropout :87-94, nn.GRU :102, head :111-137.
  *  d_x[B,T,F]; d_h0 nullable [L*D,B,H] (the `hidden` argument); d_logits[B,C];
  *  d_hn nullable [L*D,B,H]; training!=0 applies dropout p (spatial!=0: per (b,f) channel over T,

@@ -68,6 +68,22 @@ class OracleBiGRU(nn.Module):
         return self.linear(torch.cat([last, mx, av], dim=1))     # :133-137
 
 
+def forward_routed(model: OracleBiGRU, x, hidden=None, idx=None):
+    """``OracleBiGRU.forward`` (eval / dropout-free) with the max-pool's gradient routing made explicit: with ``idx``
+    ([B, H] time indices) the pooled maximum is read at those steps (``gather``), otherwise at the arg-max.  The max-pool
+    (biGRU_model.py:125) is discontinuous where two steps tie to within rounding, so parity tests compare gradients under
+    the routing the kernel actually took and separately require every disagreement to be such a tie.
+    Returns (logits, s) with s[B, T, H] the direction-summed GRU output."""
+    B, T = x.size(0), x.size(1)
+    H = model.hidden_size
+    out, h_n = model.gru(x, hidden)
+    last = h_n.view(model.n_layers, model.n_directions, B, H)[-1].sum(0)
+    s = out[..., :H] + out[..., H:] if model.bidirectional else out
+    mx = s.max(dim=1).values if idx is None else s.gather(1, idx.unsqueeze(1)).squeeze(1)
+    av = s.sum(dim=1) / float(T)
+    return model.linear(torch.cat([last, mx, av], dim=1)), s
+
+
 def train_step(model: OracleBiGRU, optimizer, loss_fn, x, target):
     """Body of biGRU_model.py:198-210 (without the sklearn metrics)."""
     optimizer.zero_grad()

@@ -213,3 +213,20 @@ def test_next_row_entry_points_refuse_the_cpu(pkg):
     assert n_out.value == 9
     assert lib.bigru_window_features(None, None, None, None, None, 0, None, 9, None, 0, None, 0, 0, 2.0, 0, 1.5, 3.0, None, None,
                                      C.byref(n_out), None) == pkg._lib.ERR_ARG
+
+
+def test_drop_in_import_route(tmp_path):
+    """with the package directory itself on sys.path the reference's own import lines
+    (`from biGRU_model import BiGRU`, predict.py:16; `from sql_pytorch_dataloader import ...`, the notebook) resolve
+    to the B200 implementation - checked in a fresh interpreter started outside the repo."""
+    import subprocess
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from biGRU_model import BiGRU\n"
+        "from sql_pytorch_dataloader import MySQLBatchLoader, MySQLChunkLoader, TrainValTestSplit, window_indices\n"
+        "m = BiGRU(8, 108, 4, 1, 50, 0.2, False, True)\n"
+        "assert sorted(m.state_dict())[0] == 'gru.bias_hh_l0' and m.linear.weight.shape == (4, 24)\n"
+        "assert list(window_indices(range(4), 2)) == [(0, 1), (1, 2), (2, 3)]\n"
+        "print('ok')\n") % os.path.join(ROOT, "financial_market_data_analysis_b200")
+    r = subprocess.run([sys.executable, "-c", code], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]

@@ -67,6 +67,14 @@ static int run_case(int B, int T, int H, int D, int reps, int use_h0, int top) {
     }
     tcx::FwdParams p{};
     p.B = B; p.T = T; p.H = H; p.D = D; p.Wimg = d_f; p.giX = d_gi; p.b_hn = d_bhn; p.h0 = use_h0 ? d_h0 : nullptr;
+    std::vector<float> gh0((size_t)D * B * 3 * H, 0.f);
+    if (use_h0)
+        for (int d = 0; d < D; ++d) for (int b = 0; b < B; ++b) for (int q = 0; q < 3 * H; ++q) {
+            double a = 0; for (int k = 0; k < H; ++k) a += (double)whh[((size_t)d * 3 * H + q) * H + k] * h0[((size_t)d * B + b) * H + k];
+            gh0[((size_t)d * B + b) * 3 * H + q] = (float)a;
+        }
+    float* d_gh0 = dev(gh0);
+    p.gh0 = use_h0 ? d_gh0 : nullptr;
     p.GX = d_G; p.YBX = d_YB; p.hn_out = d_hn; p.Yhi = d_Yh; p.Ylo = d_Yl; p.dbg = dbg;
 #ifdef BIGRU_SCAN_TIMING
     unsigned long long* d_ts; CK(cudaMalloc(&d_ts, 8 * 16 * 8)); CK(cudaMemset(d_ts, 0, 8 * 16 * 8)); p.ts = d_ts;
@@ -91,6 +99,7 @@ static int run_case(int B, int T, int H, int D, int reps, int use_h0, int top) {
     // ---- CPU forward in double, full stash for the BPTT below (first rows of the batch only: they cover several tiles)
     const int bcheck = B > 40 ? 40 : B;
     double eY = 0, eG = 0, eHn = 0;
+    int nbad = 0; std::vector<int> bad_b(B, 0), bad_s(T, 0);
     // stash[d][b][s] -> r, z, n, hn, hprev per unit
     std::vector<double> sr((size_t)D * bcheck * T * H), sz(sr.size()), sn(sr.size()), shn(sr.size()), shp(sr.size());
     for (int d = 0; d < D; ++d)
@@ -124,11 +133,15 @@ static int run_case(int B, int T, int H, int D, int reps, int use_h0, int top) {
                 for (int j = 0; j < H; ++j) {
                     hs[j] = hnew[j];
                     const size_t yi = (size_t)row * D * H + d * H + j;
-                    eY = fmax(eY, fabs(hnew[j] - ((double)b2f(Yh[yi]) + (double)b2f(Yl[yi]))));
+                    const double ey = fabs(hnew[j] - ((double)b2f(Yh[yi]) + (double)b2f(Yl[yi])));
+                    if (ey > 1e-3 && nbad < 12) { ++nbad; printf("   bad Y d=%d b=%d t=%d (s=%d) unit=%d: got %.6f want %.6f\n", d, b, t, s, j, (double)b2f(Yh[yi]) + (double)b2f(Yl[yi]), hnew[j]); }
+                    if (ey > 1e-3) { bad_b[b]++; bad_s[s]++; }
+                    eY = fmax(eY, ey);
                 }
             }
             for (int j = 0; j < H; ++j) eHn = fmax(eHn, fabs(hs[j] - hn[((size_t)d * B + b) * H + j]));
         }
+    if (nbad) { printf("   bad per batch row:"); for (int b = 0; b < bcheck; ++b) printf(" %d", bad_b[b]); printf("\n   bad per step:"); for (int t = 0; t < T; ++t) printf(" %d", bad_s[t]); printf("\n"); }
     const bool fpass = hdbg[0] == 0 && eY < 2e-5 && eG < 2e-5 && eHn < 2e-5;
     printf("%s scanx_fwd B=%d T=%d H=%d D=%d h0=%d (cluster %d, grid %d): errY=%.2e errG=%.2e errHn=%.2e dbg=%x blk=%u thr=%u  %.3f ms (%.2f us/step)\n",
            fpass ? "PASS" : "FAIL", B, T, H, D, use_h0, CS, D * (B / 32) * CS, eY, eG, eHn, hdbg[0], hdbg[1], hdbg[2], ms, ms * 1e3 / T);
@@ -230,6 +243,22 @@ static int run_case(int B, int T, int H, int D, int reps, int use_h0, int top) {
 int main() {
     setvbuf(stdout, NULL, _IONBF, 0);
     int bad = 0;
+    if (getenv("SCANX_STRESS")) {
+        const int h0 = atoi(getenv("SCANX_STRESS"));
+        for (int i = 0; i < 25; ++i) bad += run_case(64, 11, 256, 2, 0, h0, 1);
+        for (int i = 0; i < 10; ++i) bad += run_case(128, 6, 256, 1, 0, h0, 0);
+        for (int i = 0; i < 10; ++i) bad += run_case(64, 7, 128, 2, 0, h0, 0);
+        printf("stress h0=%d: %d failures\n", h0, bad / 2);
+        return bad ? 1 : 0;
+    }
+    if (getenv("SCANX_H0")) {
+        for (int i = 0; i < 4; ++i) bad += run_case(64, 4, 256, 1, 0, 1, 0);
+        for (int i = 0; i < 2; ++i) bad += run_case(64, 11, 256, 2, 0, 1, 1);
+        for (int i = 0; i < 2; ++i) bad += run_case(128, 6, 256, 1, 0, 1, 0);
+        for (int i = 0; i < 2; ++i) bad += run_case(32, 4, 256, 1, 0, 1, 0);
+        printf(bad ? "SOME FAILED\n" : "ALL PASSED\n");
+        return bad ? 1 : 0;
+    }
     bad += run_case(32, 1, 128, 1, 0, 0, 0);
     bad += run_case(32, 3, 128, 1, 0, 0, 0);
     bad += run_case(64, 5, 128, 2, 0, 1, 1);
