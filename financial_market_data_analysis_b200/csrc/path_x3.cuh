@@ -8,6 +8,7 @@
 #pragma once
 #include "path_bf16.cuh"
 #include "tc_scan_x.cuh"
+#include <cstdlib>
 
 static int x3_plan_check(const bigru_plan& p) {
     if ((p.H != 128 && p.H != 256) || p.B % 32 != 0 || p.F % 8 != 0) {

@@ -107,16 +107,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 tc::mbar_arrive_expect_tx(&full[s], A_BYTES + B_BYTES);
                 const int combo = i % p.nsplit;                     // 0: hi x hi, 1: hi x lo, 2: lo x hi
                 const int k = (kb0 + i / p.nsplit) * BK;
-                const CUtensorMap* mA = combo == 2 ? &tmAlo : &tmA;
-                const CUtensorMap* mB = combo == 1 ? &tmBlo : &tmB;
+                // (each call names its tensor map directly: a run-time selected pointer makes the compiler copy the 128-byte
+                // descriptor to local memory)
+                const bool a_lo = combo == 2, b_lo = combo == 1;
+                uint8_t* da = sA + s * A_BYTES;
+                uint8_t* db = sB + s * B_BYTES;
+                const int ar = p.a_row_off[z] + m0, br = p.b_row_off[z] + n0, kb = k + p.b_k_off[z];
                 if (p.a_mn) {        // two boxes of 64 (MN) x 64 (K rows)
-                    tc::tma_load_2d(sA + s * A_BYTES, mA, &full[s], p.a_row_off[z] + m0, k);
-                    tc::tma_load_2d(sA + s * A_BYTES + A_BYTES / 2, mA, &full[s], p.a_row_off[z] + m0 + 64, k);
-                } else tc::tma_load_2d(sA + s * A_BYTES, mA, &full[s], k, p.a_row_off[z] + m0);
+                    if (a_lo) { tc::tma_load_2d(da, &tmAlo, &full[s], ar, k); tc::tma_load_2d(da + A_BYTES / 2, &tmAlo, &full[s], ar + 64, k); }
+                    else { tc::tma_load_2d(da, &tmA, &full[s], ar, k); tc::tma_load_2d(da + A_BYTES / 2, &tmA, &full[s], ar + 64, k); }
+                } else {
+                    if (a_lo) tc::tma_load_2d(da, &tmAlo, &full[s], k, ar);
+                    else tc::tma_load_2d(da, &tmA, &full[s], k, ar);
+                }
                 if (p.b_mn) {
-                    tc::tma_load_2d(sB + s * B_BYTES, mB, &full[s], p.b_row_off[z] + n0, k + p.b_k_off[z]);
-                    tc::tma_load_2d(sB + s * B_BYTES + B_BYTES / 2, mB, &full[s], p.b_row_off[z] + n0 + 64, k + p.b_k_off[z]);
-                } else tc::tma_load_2d(sB + s * B_BYTES, mB, &full[s], k + p.b_k_off[z], p.b_row_off[z] + n0);
+                    if (b_lo) { tc::tma_load_2d(db, &tmBlo, &full[s], br, kb); tc::tma_load_2d(db + B_BYTES / 2, &tmBlo, &full[s], br + 64, kb); }
+                    else { tc::tma_load_2d(db, &tmB, &full[s], br, kb); tc::tma_load_2d(db + B_BYTES / 2, &tmB, &full[s], br + 64, kb); }
+                } else {
+                    if (b_lo) tc::tma_load_2d(db, &tmBlo, &full[s], kb, br);
+                    else tc::tma_load_2d(db, &tmB, &full[s], kb, br);
+                }
             }
         }
     } else if (warp == 1) {
@@ -188,21 +198,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tc::fence_proxy_async_smem();
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (warp == 2 && tc::elect_one()) {
-                const int H = p.blk.H, G = p.blk.G, Bb = p.blk.B, Tt = p.blk.T, U = p.blk.U, NBt = p.blk.NB;
-                const int CSs = H / U, ntl = Bb / NBt;
+                const int H = p.blk.H, G = p.blk.G, Bb = p.blk.B, Tt = p.blk.T, U = p.blk.U;
+                const int sh = p.blk.NB == 32 ? 5 : 4;              // batch rows per tile: 16 or 32
+                const int CSs = H / U, ntl = Bb >> sh, nh = BM / U;
                 const size_t es = bf ? 2 : 4;
+                // the tile's 128 rows = BM/U runs of U units of one (d, gate, cta): their block coordinates are fixed for the tile
+                size_t row_part[2]; size_t gate_part[2];
+                for (int hh = 0; hh < nh; ++hh) {
+                    const int mr = m0 + hh * U;
+                    row_part[hh] = (size_t)(mr / (G * H)) * ntl;
+                    gate_part[hh] = (size_t)((mr % H) / U) * G + (size_t)((mr / H) % G);
+                }
+                int t_ = n0 / Bb, b = n0 % Bb;                      // advanced incrementally: 8 columns per run
                 for (int r = 0; r < BN / 8; ++r) {
-                    const int n = n0 + r * 8;
-                    if (n >= p.N) break;
-                    const int t_ = n / Bb, b = n % Bb;
-                    const int tile_ = b / NBt, cbg = (b % NBt) >> 3;
-                    for (int hh = 0; hh < BM / U; ++hh) {          // the tile's 128 rows = BM/U runs of U units of one (d, gate, cta)
-                        const int mr = m0 + hh * U;
-                        const int dd = mr / (G * H), gg = (mr / H) % G, cc = (mr % H) / U;
-                        const size_t e = ((((((size_t)dd * ntl + tile_) * Tt + t_) * CSs + cc) * G + gg) * 256 + (size_t)cbg * U) * 8;
+                    if (n0 + r * 8 >= p.N) break;
+                    const int tile_ = b >> sh, cbg = (b & ((1 << sh) - 1)) >> 3;
+                    for (int hh = 0; hh < nh; ++hh) {
+                        const size_t e = ((((row_part[hh] + tile_) * Tt + t_) * CSs * G + gate_part[hh]) * 256 + (size_t)cbg * U) * 8;
                         tc::bulk_s2g(reinterpret_cast<uint8_t*>(p.C) + e * es, smem + (size_t)r * run_bytes + (size_t)hh * U * 8 * es,
                                      (uint32_t)(U * 8 * es));
                     }
+                    b += 8;
+                    if (b >= Bb) { b -= Bb; ++t_; }
                 }
                 tc::tma_store_commit();
                 tc::tma_store_wait_read();     // smem may be released once it has been read; the writes complete on their own
@@ -257,13 +274,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tc::fence_proxy_async_smem();
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (warp == 2 && tc::elect_one()) {
-                const CUtensorMap* tmC = z == 0 ? &tmC0 : &tmC1;
                 const int nboxes = is_bf16 ? BN / 64 : BN / 32;
                 const int bw = is_bf16 ? 64 : 32;
                 for (int b = 0; b < nboxes; ++b) {
                     if (n0 + b * bw >= p.N) break;
-                    if (p.mode == OUT_ATOMIC_F32) tc::tma_reduce_add_2d(tmC, smem + (size_t)b * 16384, n0 + b * bw, m0);
-                    else tc::tma_store_2d(tmC, smem + (size_t)b * 16384, n0 + b * bw, m0);
+                    // (the map is named directly in each call: a run-time selected pointer costs a 128-byte local copy)
+                    if (p.mode == OUT_ATOMIC_F32) {
+                        if (z == 0) tc::tma_reduce_add_2d(&tmC0, smem + (size_t)b * 16384, n0 + b * bw, m0);
+                        else tc::tma_reduce_add_2d(&tmC1, smem + (size_t)b * 16384, n0 + b * bw, m0);
+                    } else {
+                        if (z == 0) tc::tma_store_2d(&tmC0, smem + (size_t)b * 16384, n0 + b * bw, m0);
+                        else tc::tma_store_2d(&tmC1, smem + (size_t)b * 16384, n0 + b * bw, m0);
+                    }
                 }
                 tc::tma_store_commit();
                 tc::tma_store_wait_read();     // smem may be released once it has been read; the writes complete on their own

@@ -204,6 +204,29 @@ class MySQLBatchLoader(Dataset):
         self.x = self._gather(0, 1, self.n_rows)[0] if self.n_rows else self.x_raw
         self.indices_gen = window_indices(range(len(indices)), window)
 
+    @classmethod
+    def from_tensors(cls, x_rows, y_rows, norm_params, window, device=None):
+        """The same dataset over a chunk that is already in memory (x_rows [N, F] raw features, y_rows [N, C] targets,
+        norm_params = (min [1, F], max [1, F]) as MySQLChunkLoader yields them) - no cursor, no SQL.  Used when the table
+        has been bulk-loaded (MySQLChunkLoader.from_table) and by the loader arm of bench.py."""
+        self = cls.__new__(cls)
+        Dataset.__init__(self)
+        if device is None:
+            device = x_rows.device if x_rows.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("MySQLBatchLoader (B200-native) keeps the chunk in HBM; there is no CPU fallback")
+        self.window = int(window)
+        self.x_raw = x_rows.to(self.device, torch.float32).contiguous()
+        self.y = y_rows.to(self.device, torch.float32).contiguous()
+        self.n_rows, self.n_features = self.x_raw.shape
+        self.n_targets = self.y.shape[1] if self.y.dim() == 2 else 0
+        self.x_min = norm_params[0][0].to(self.device, torch.float32).contiguous()
+        self.x_max = norm_params[1][0].to(self.device, torch.float32).contiguous()
+        self.x = None                                   # the normalised copy is formed on demand by collate()/the fused forward
+        self.indices_gen = window_indices(range(self.n_rows), window)
+        return self
+
     def _gather(self, start, count, width):
         out = torch.empty(count, width, self.n_features, device=self.device, dtype=torch.float32)
         _lib.check(_lib.load().bigru_window_gather_norm(
@@ -232,6 +255,8 @@ class MySQLBatchLoader(Dataset):
 
     def __getitem__(self, idx):
         w = next(self.indices_gen)          # sequential by construction, like the reference (idx is ignored)
+        if self.x is None:
+            self.x = self._gather(0, 1, self.n_rows)[0]
         return self.x[w[0]:w[-1] + 1], self.y[w[-1]:w[-1] + 1]
 
     def __len__(self):
