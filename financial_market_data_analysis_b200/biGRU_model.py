@@ -207,6 +207,9 @@ class BiGRU(nn.Module):
         self._dp_world = 1
         self._last_hidden = None
         self._last_plan_stash = None
+        self._last_seed = 0
+        self._graphs = {}
+        self.use_cuda_graph = os.environ.get("BIGRU_B200_CUDA_GRAPH", "1") != "0"
         self._loss_cache = {}
         self._flatten()
 
@@ -238,6 +241,7 @@ class BiGRU(nn.Module):
                 off += n
         self._flat, self._views = flat, views
         self._plans = {}
+        self._graphs = {}
         self._adam = None
 
     def _is_flat(self):
@@ -309,6 +313,7 @@ class BiGRU(nn.Module):
     def add_optimizer(self, optimizer):
         self.optimizer = optimizer
         self._adam = None
+        self._graphs = {}
 
     def add_device(self, device=torch.device("cpu")):
         self.device = device
@@ -370,20 +375,90 @@ class BiGRU(nn.Module):
 
     def _fused_state(self, dev):
         """Optimiser state of the fused step.  The flat gradient and the scalar loss share one buffer (``gext`` = P gradients
-        + 1 loss), so that data parallelism needs exactly one all-reduce per step."""
+        + 1 loss), so that data parallelism needs exactly one all-reduce per step.  ``step`` lives on the device too
+        (``dstep``), so that a captured CUDA graph of the step stays valid from one step to the next."""
         st = self._adam
         if st is None:
             P = self._flat.numel()
             gext = torch.empty(P + 1, device=dev, dtype=torch.float32)
             st = self._adam = {"m": torch.zeros_like(self._flat), "v": torch.zeros_like(self._flat), "step": 0,
+                               "dstep": torch.zeros(1, device=dev, dtype=torch.int32),
                                "gext": gext, "grad": gext[:P], "loss": gext[P:P + 1],
                                "scal": torch.zeros(2, device=dev, dtype=torch.float32)}
         return st
 
+    def _launch_fwd_loss_bwd(self, lib, plan, x, h0, tgt, kind, wv, pwv, denom, logits, dlogits, stash, args, st, s):
+        B, C = logits.shape
+        _lib.check(lib.bigru_forward(plan.handle, _lib.ptr(self._flat), _lib.ptr(x), _lib.ptr(h0), *args,
+                                     _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(logits), None, s), "bigru_forward")
+        _lib.check(lib.bigru_loss(kind, _lib.ptr(logits), _lib.ptr(tgt), _lib.ptr(wv), _lib.ptr(pwv), B, C, denom,
+                                  _lib.ptr(st["loss"]), _lib.ptr(dlogits), s), "bigru_loss")
+        _lib.check(lib.bigru_backward(plan.handle, _lib.ptr(self._flat), _lib.ptr(x), _lib.ptr(h0), *args,
+                                      _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(dlogits), _lib.ptr(st["grad"]),
+                                      None, None, s), "bigru_backward")
+
+    def _launch_update(self, lib, g, st, s):
+        """clip_grad_norm_(clip) + Adam on the flat buffers; the step counter is incremented on the device."""
+        sq = st["scal"][1:2]
+        _lib.check(lib.bigru_adam_tick(_lib.ptr(st["dstep"]), _lib.ptr(sq), s), "bigru_adam_tick")
+        _lib.check(lib.bigru_sqnorm(_lib.ptr(st["grad"]), st["grad"].numel(), _lib.ptr(sq), s), "bigru_sqnorm")
+        b1, b2 = g["betas"]
+        _lib.check(lib.bigru_clip_adam_step_dev(_lib.ptr(self._flat), _lib.ptr(st["grad"]), _lib.ptr(st["m"]),
+                                                _lib.ptr(st["v"]), self._flat.numel(), _lib.ptr(sq), float(self.clip),
+                                                float(g["lr"]), float(b1), float(b2), float(g["eps"]), _lib.ptr(st["dstep"]),
+                                                1.0, s), "bigru_clip_adam_step_dev")
+        st["step"] += 1
+
+    def _graph_for(self, key, x, tgt, kind, wv, pwv, denom, g):
+        """CUDA graph(s) of the train step for one (shape, loss) key: static input / output buffers, the
+        C-ABI calls captured once.  One graph at world size 1; with data parallelism two (forward+loss+backward | update) with
+        the gradient all-reduce issued between them."""
+        ent = self._graphs.get(key)
+        if ent is not None:
+            return ent
+        lib = _lib.load()
+        dev = x.device
+        plan = self._plan_for(x)
+        st = self._fused_state(dev)
+        B, C = x.shape[0], self.output_size
+        ent = {"x": torch.empty_like(x), "tgt": torch.empty_like(tgt), "logits": torch.empty(B, C, device=dev, dtype=torch.float32),
+               "dlogits": torch.empty(B, C, device=dev, dtype=torch.float32), "stash": plan.acquire_stash(), "plan": plan}
+        args = (float(self.dropout_p), int(bool(self.spatial_dropout)), 0, 0)
+        ent["x"].copy_(x); ent["tgt"].copy_(tgt)
+        # one eager pass on the static buffers first (first-use work such as shared-memory opt-ins happens outside the capture);
+        # its parameter update is real: it is the step the caller asked for
+        s = _stream_ptr(dev)
+        self._launch_fwd_loss_bwd(lib, plan, ent["x"], None, ent["tgt"], kind, wv, pwv, denom, ent["logits"], ent["dlogits"], ent["stash"], args, st, s)
+        if self._dp_world > 1:
+            allreduce_flat_(st["gext"], self._dp_group)
+        self._launch_update(lib, g, st, s)
+        torch.cuda.current_stream(dev).synchronize()
+        n0 = lib.bigru_launch_count()
+        ga = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ga, capture_error_mode="thread_local"):
+            s = _stream_ptr(dev)
+            self._launch_fwd_loss_bwd(lib, plan, ent["x"], None, ent["tgt"], kind, wv, pwv, denom, ent["logits"], ent["dlogits"], ent["stash"], args, st, s)
+            if self._dp_world == 1:
+                self._launch_update(lib, g, st, s)
+        gb = None
+        if self._dp_world > 1:
+            gb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gb, capture_error_mode="thread_local"):
+                self._launch_update(lib, g, st, _stream_ptr(dev))
+        st["step"] -= 1                                   # the capture ran the host-side bookkeeping once without stepping
+        ent["launches"] = int(lib.bigru_launch_count() - n0)
+        lib.bigru_launch_count_add(-ent["launches"])      # captured, not executed
+        ent["ga"], ent["gb"], ent["fresh"] = ga, gb, True
+        if len(self._graphs) > 4:
+            self._graphs.clear()
+        self._graphs[key] = ent
+        return ent
+
     def train_step(self, input_seq, target, hidden=None):
         """One optimisation step = the body of the reference loop (biGRU_model.py:198-210):
-        zero_grad, forward, loss, backward, clip_grad_norm_(clip), Adam step - as six C-ABI calls with
-        no autograd graph.  Returns (loss, logits) as device tensors (no host sync)."""
+        zero_grad, forward, loss, backward, clip_grad_norm_(clip), Adam step - C-ABI calls with no autograd graph, replayed
+        from a captured CUDA graph when the step is replayable (no dropout noise to draw, no initial state).
+        Returns (loss, logits) as device tensors (no host sync)."""
         spec, g = self._loss_spec(), self._adam_spec()
         if spec is None or g is None:
             raise RuntimeError("train_step needs add_loss_fn(CrossEntropyLoss | BCEWithLogitsLoss | "
@@ -403,36 +478,46 @@ class BiGRU(nn.Module):
             if tuple(tgt.shape) != (B, C):
                 raise ValueError(f"target must be [{B}, {C}]")
             denom = float(B * C * self._dp_world)
-        plan = self._plan_for(x)
-        st = self._fused_state(dev)
-        logits = torch.empty(B, C, device=dev, dtype=torch.float32)
-        dlogits = torch.empty_like(logits)
-        stash = plan.acquire_stash()
         training = bool(self.training and self.dropout_p > 0)
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
-        s = _stream_ptr()
-        args = (float(self.dropout_p), int(bool(self.spatial_dropout)), int(training), seed)
-        _lib.check(lib.bigru_forward(plan.handle, _lib.ptr(self._flat), _lib.ptr(x), _lib.ptr(h0), *args,
-                                     _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(logits), None, s), "bigru_forward")
-        loss, sq = st["loss"], st["scal"][1:2]
-        wv, pwv = self._loss_vec(w, C), self._loss_vec(pw, C)
-        _lib.check(lib.bigru_loss(kind, _lib.ptr(logits), _lib.ptr(tgt), _lib.ptr(wv), _lib.ptr(pwv), B, C, denom,
-                                  _lib.ptr(loss), _lib.ptr(dlogits), s), "bigru_loss")
-        _lib.check(lib.bigru_backward(plan.handle, _lib.ptr(self._flat), _lib.ptr(x), _lib.ptr(h0), *args,
-                                      _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(dlogits), _lib.ptr(st["grad"]),
-                                      None, None, s), "bigru_backward")
-        plan.release_stash(stash)
-        if self._dp_world > 1:
-            allreduce_flat_(st["gext"], self._dp_group)          # ONE all-reduce: shard gradients of the global-mean loss + the loss
-        sq.zero_()
-        _lib.check(lib.bigru_sqnorm(_lib.ptr(st["grad"]), st["grad"].numel(), _lib.ptr(sq), s), "bigru_sqnorm")
-        st["step"] += 1
-        b1, b2 = g["betas"]
-        _lib.check(lib.bigru_clip_adam_step(_lib.ptr(self._flat), _lib.ptr(st["grad"]), _lib.ptr(st["m"]),
-                                            _lib.ptr(st["v"]), self._flat.numel(), _lib.ptr(sq), float(self.clip),
-                                            float(g["lr"]), float(b1), float(b2), float(g["eps"]), st["step"], 1.0, s),
-                   "bigru_clip_adam_step")
-        return loss.clone(), logits
+        with torch.cuda.device(dev):
+            wv, pwv = self._loss_vec(w, C), self._loss_vec(pw, C)
+            st = self._fused_state(dev)
+            if self.use_cuda_graph and not training and h0 is None and not torch.cuda.is_current_stream_capturing():
+                key = (B, int(x.shape[1]), self.precision, kind, id(wv), id(pwv), denom, float(g["lr"]), tuple(g["betas"]),
+                       float(g["eps"]), float(self.clip), self._dp_world, dev.index)
+                try:
+                    ent = self._graph_for(key, x, tgt, kind, wv, pwv, denom, g)
+                except Exception as e:                        # capture is an optimisation: fall back to plain launches
+                    import warnings
+                    warnings.warn(f"BiGRU.train_step: CUDA-graph capture failed ({e}); using plain launches")
+                    self.use_cuda_graph = False
+                    ent = None
+                if ent is not None:
+                    if ent.pop("fresh", False):               # the warm-up pass inside _graph_for WAS this step
+                        return st["loss"].clone(), ent["logits"].clone()
+                    ent["x"].copy_(x, non_blocking=True)
+                    ent["tgt"].copy_(tgt, non_blocking=True)
+                    ent["ga"].replay()
+                    if ent["gb"] is not None:
+                        allreduce_flat_(st["gext"], self._dp_group)
+                        ent["gb"].replay()
+                    st["step"] += 1
+                    lib.bigru_launch_count_add(ent["launches"])
+                    return st["loss"].clone(), ent["logits"].clone()
+            plan = self._plan_for(x)
+            logits = torch.empty(B, C, device=dev, dtype=torch.float32)
+            dlogits = torch.empty_like(logits)
+            stash = plan.acquire_stash()
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
+            self._last_seed = seed
+            s = _stream_ptr(dev)
+            args = (float(self.dropout_p), int(bool(self.spatial_dropout)), int(training), seed)
+            self._launch_fwd_loss_bwd(lib, plan, x, h0, tgt, kind, wv, pwv, denom, logits, dlogits, stash, args, st, s)
+            plan.release_stash(stash)
+            if self._dp_world > 1:
+                allreduce_flat_(st["gext"], self._dp_group)          # ONE all-reduce: shard gradients of the global-mean loss + the loss
+            self._launch_update(lib, g, st, s)
+            return st["loss"].clone(), logits
 
     # ------------------------------------------------------------------ zero-copy windows
     def _window_args(self, dataset, start, count):
@@ -458,7 +543,7 @@ class BiGRU(nn.Module):
         _lib.check(lib.bigru_forward_windows(plan.handle, _lib.ptr(self._flat), _lib.ptr(dataset.x_raw), _lib.ptr(dataset.x_min),
                                              _lib.ptr(dataset.x_max), int(start), dataset.n_rows, float(self.dropout_p),
                                              int(bool(self.spatial_dropout)), int(training), seed, _lib.ptr(stash),
-                                             _lib.ptr(plan.scratch), _lib.ptr(logits), None, _stream_ptr()),
+                                             _lib.ptr(plan.scratch), _lib.ptr(logits), None, _stream_ptr(self._flat.device)),
                    "bigru_forward_windows")
         self._win_ctx = (plan, stash, training, seed)
         return logits
@@ -474,39 +559,32 @@ class BiGRU(nn.Module):
         logits = self.forward_windows(dataset, start, count)
         plan, stash, training, seed = self._win_ctx
         dev, B, C = logits.device, count, self.output_size
-        y = torch.empty(count, 1, dataset.n_targets, device=dev, dtype=torch.float32)
-        s = _stream_ptr()
-        _lib.check(lib.bigru_window_targets(_lib.ptr(dataset.y), int(start), dataset.n_rows, count, dataset.window,
-                                            dataset.n_targets, _lib.ptr(y), s), "bigru_window_targets")
-        if kind == _lib.LOSS_CE:
-            tgt = y.reshape(count, -1)[:, 0].to(torch.int64).contiguous()
-            denom = float(B * self._dp_world)
-        else:
-            tgt = y.reshape(count, C).contiguous()
-            denom = float(B * C * self._dp_world)
-        st = self._fused_state(dev)
-        dlogits = torch.empty_like(logits)
-        loss, sq = st["loss"], st["scal"][1:2]
-        wv, pwv = self._loss_vec(w, C), self._loss_vec(pw, C)
-        _lib.check(lib.bigru_loss(kind, _lib.ptr(logits), _lib.ptr(tgt), _lib.ptr(wv), _lib.ptr(pwv), B, C, denom,
-                                  _lib.ptr(loss), _lib.ptr(dlogits), s), "bigru_loss")
-        _lib.check(lib.bigru_backward(plan.handle, _lib.ptr(self._flat), None, None, float(self.dropout_p),
-                                      int(bool(self.spatial_dropout)), int(training), seed, _lib.ptr(stash),
-                                      _lib.ptr(plan.scratch), _lib.ptr(dlogits), _lib.ptr(st["grad"]), None, None, s),
-                   "bigru_backward")
-        plan.release_stash(stash)
-        self._win_ctx = None
-        if self._dp_world > 1:
-            allreduce_flat_(st["gext"], self._dp_group)
-        sq.zero_()
-        _lib.check(lib.bigru_sqnorm(_lib.ptr(st["grad"]), st["grad"].numel(), _lib.ptr(sq), s), "bigru_sqnorm")
-        st["step"] += 1
-        b1, b2 = g["betas"]
-        _lib.check(lib.bigru_clip_adam_step(_lib.ptr(self._flat), _lib.ptr(st["grad"]), _lib.ptr(st["m"]),
-                                            _lib.ptr(st["v"]), self._flat.numel(), _lib.ptr(sq), float(self.clip),
-                                            float(g["lr"]), float(b1), float(b2), float(g["eps"]), st["step"], 1.0, s),
-                   "bigru_clip_adam_step")
-        return loss.clone(), logits
+        with torch.cuda.device(dev):
+            y = torch.empty(count, 1, dataset.n_targets, device=dev, dtype=torch.float32)
+            s = _stream_ptr(dev)
+            _lib.check(lib.bigru_window_targets(_lib.ptr(dataset.y), int(start), dataset.n_rows, count, dataset.window,
+                                                dataset.n_targets, _lib.ptr(y), s), "bigru_window_targets")
+            if kind == _lib.LOSS_CE:
+                tgt = y.reshape(count, -1)[:, 0].to(torch.int64).contiguous()
+                denom = float(B * self._dp_world)
+            else:
+                tgt = y.reshape(count, C).contiguous()
+                denom = float(B * C * self._dp_world)
+            st = self._fused_state(dev)
+            dlogits = torch.empty_like(logits)
+            wv, pwv = self._loss_vec(w, C), self._loss_vec(pw, C)
+            _lib.check(lib.bigru_loss(kind, _lib.ptr(logits), _lib.ptr(tgt), _lib.ptr(wv), _lib.ptr(pwv), B, C, denom,
+                                      _lib.ptr(st["loss"]), _lib.ptr(dlogits), s), "bigru_loss")
+            _lib.check(lib.bigru_backward(plan.handle, _lib.ptr(self._flat), None, None, float(self.dropout_p),
+                                          int(bool(self.spatial_dropout)), int(training), seed, _lib.ptr(stash),
+                                          _lib.ptr(plan.scratch), _lib.ptr(dlogits), _lib.ptr(st["grad"]), None, None, s),
+                       "bigru_backward")
+            plan.release_stash(stash)
+            self._win_ctx = None
+            if self._dp_world > 1:
+                allreduce_flat_(st["gext"], self._dp_group)
+            self._launch_update(lib, g, st, s)
+            return st["loss"].clone(), logits
 
     def _generic_step(self, x, target):
         """Any loss / optimiser: autograd drives the same CUDA forward/backward kernels."""
@@ -516,10 +594,15 @@ class BiGRU(nn.Module):
             self.loss_fn.to(pred.device)                 # class weights follow the logits
         loss = self.loss_fn(pred, target.to(pred.device))
         loss.backward()
-        if self._dp_world > 1:
-            for p in self.parameters():
-                allreduce_flat_(p.grad, self._dp_group)
-                p.grad.div_(self._dp_world)
+        if self._dp_world > 1:                            # ONE all-reduce of all gradients (flattened), then scattered back
+            ps = [p for p in self.parameters() if p.grad is not None]
+            flat = torch.cat([p.grad.reshape(-1) for p in ps])
+            allreduce_flat_(flat, self._dp_group)
+            flat.div_(self._dp_world)
+            off = 0
+            for p in ps:
+                p.grad.copy_(flat[off:off + p.grad.numel()].view_as(p.grad))
+                off += p.grad.numel()
         nn.utils.clip_grad_norm_(self.parameters(), self.clip)
         self.optimizer.step()
         return loss.detach().reshape(1), pred.detach()
@@ -531,7 +614,7 @@ class BiGRU(nn.Module):
                              "(biGRU_model.py:213-221 feeds sigmoid(pred) > 0.5 to sklearn)")
         tgt = target.to(device=logits.device, dtype=torch.float32).contiguous()
         _lib.check(_lib.load().bigru_multilabel_counts(_lib.ptr(logits), _lib.ptr(tgt), logits.shape[0],
-                                                       logits.shape[1], _lib.ptr(counts_row), _stream_ptr()),
+                                                       logits.shape[1], _lib.ptr(counts_row), _stream_ptr(logits.device)),
                    "bigru_multilabel_counts")
 
     @staticmethod

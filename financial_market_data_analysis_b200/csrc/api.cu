@@ -492,6 +492,25 @@ extern "C" int bigru_clip_adam_step(float* d_params, float* d_grads, float* d_m,
     return BIGRU_OK;
 }
 
+extern "C" int bigru_adam_tick(int* d_step, float* d_sqnorm, void* stream) {
+    if (!d_step || !d_sqnorm) { bigru_set_error("adam_tick: null argument"); return BIGRU_ERR_ARG; }
+    KLAUNCH(KC_OPTIM, 0.0, 0.0, (cudaStream_t)stream, adam_tick_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_step, d_sqnorm));
+    return BIGRU_OK;
+}
+
+extern "C" int bigru_clip_adam_step_dev(float* d_params, float* d_grads, float* d_m, float* d_v, int64_t n,
+                                        const float* d_sqnorm, float clip, float lr, float b1, float b2, float eps,
+                                        const int* d_step, float grad_scale, void* stream) {
+    if (!d_params || !d_grads || !d_m || !d_v || !d_sqnorm || !d_step || n <= 0) {
+        bigru_set_error("clip_adam_step_dev: bad argument");
+        return BIGRU_ERR_ARG;
+    }
+    const unsigned blocks = (unsigned)min((int64_t)148 * 8, cdiv64(n, 256));
+    KLAUNCH(KC_OPTIM, 0.0, 0.0, (cudaStream_t)stream, clip_adam_dev_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_params, d_grads, d_m, d_v, n, d_sqnorm, clip,
+                                                                    lr, b1, b2, eps, d_step, grad_scale));
+    return BIGRU_OK;
+}
+
 extern "C" int bigru_window_gather_norm(const float* d_src, const float* d_xmin, const float* d_xmax, int64_t start,
                                         int64_t N, int B, int T, int F, float* d_out, void* stream) {
     if (B == 0 && T > 0 && F > 0 && start >= 0) return BIGRU_OK;          // empty batch: nothing to write
@@ -536,6 +555,8 @@ extern "C" int bigru_multilabel_counts(const float* d_logits, const float* d_tar
 // measurement hooks (bench.py): launch counter and per-kernel-class CUDA-event timing
 // ------------------------------------------------------------------------------------------
 extern "C" long long bigru_launch_count(void) { return profiler().launches.load(); }
+// kernels replayed through a captured CUDA graph do not pass the launch macros: the caller reports them (n per replay)
+extern "C" void bigru_launch_count_add(long long n) { profiler().launches.fetch_add(n, std::memory_order_relaxed); }
 
 extern "C" int bigru_prof_enable(int on) {
     Profiler& p = profiler();

@@ -345,6 +345,31 @@ __global__ void clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, f
     }
 }
 
+// device-resident step counter variant (CUDA-graph friendly: nothing about the step number is baked into the launch):
+// adam_tick increments *step and clears the squared-norm accumulator; the update kernel forms the bias corrections itself
+__global__ void adam_tick_kernel(int* __restrict__ step, float* __restrict__ sqnorm) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { *step += 1; *sqnorm = 0.f; }
+}
+__global__ void clip_adam_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                     float* __restrict__ v, int64_t n, const float* __restrict__ sqnorm, float clip,
+                                     float lr, float b1, float b2, float eps, const int* __restrict__ step_p, float gscale) {
+    const int step_i = *step_p;
+    const float bc1 = (float)(1.0 - pow((double)b1, (double)step_i));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, (double)step_i));
+    const float norm = sqrtf(*sqnorm) * gscale;
+    const float coef = fminf(1.f, clip / (norm + 1e-6f)) * gscale;
+    const float step = lr / bc1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gq = g[i] * coef;
+        g[i] = gq;
+        const float mi = m[i] + (gq - m[i]) * (1.f - b1);
+        const float vi = v[i] * b2 + (1.f - b2) * gq * gq;
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = p[i] - step * (mi / denom);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Window collation (sql_pytorch_dataloader.py:239-245): coalesced, float4 when F % 4 == 0
 // ------------------------------------------------------------------------------------------

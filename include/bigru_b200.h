@@ -104,6 +104,14 @@ int  bigru_clip_adam_step(float* d_params, float* d_grads, float* d_m, float* d_
                           const float* d_sqnorm, float clip, float lr, float b1, float b2, float eps,
                           int step, float grad_scale, void* stream);
 
+/* Device-resident step counter variant of the same update, for CUDA-graph capture of the train step:
+ *  bigru_adam_tick: *d_step += 1, *d_sqnorm = 0 (one tiny launch, before bigru_sqnorm);
+ *  bigru_clip_adam_step_dev: as bigru_clip_adam_step with the bias corrections formed on the device from *d_step. */
+int  bigru_adam_tick(int* d_step, float* d_sqnorm, void* stream);
+int  bigru_clip_adam_step_dev(float* d_params, float* d_grads, float* d_m, float* d_v, int64_t n,
+                              const float* d_sqnorm, float clip, float lr, float b1, float b2, float eps,
+                              const int* d_step, float grad_scale, void* stream);
+
 /* --- MySQLBatchLoader collation (sql_pytorch_dataloader.py:239-245 + default_collate):
  *  out[b,t,f] = (src[start+b+t, f] - xmin[f]) / (xmax[f] - xmin[f]);  src is [N,F], start+B+T-1 <= N.
  *  xmin/xmax nullable (then a plain gather).  targets: out[b,0,c] = y[start+b+T-1, c]. */
@@ -160,6 +168,7 @@ int  bigru_multilabel_counts(const float* d_logits, const float* d_target, int B
  *  kernel class (names via bigru_prof_class_name) since the last enable.  Timing adds event records
  *  to the stream, so bench.py enables it only for a separate, untimed-for-throughput pass. */
 long long   bigru_launch_count(void);
+void        bigru_launch_count_add(long long n);   /* launches replayed from a captured CUDA graph (not seen by the macros) */
 int         bigru_prof_enable(int on);
 int         bigru_prof_classes(void);
 const char* bigru_prof_class_name(int cls);
