@@ -124,6 +124,25 @@ __global__ void cast_x_kernel(const float* __restrict__ x, WindowSrc w, bf16_t* 
     }
 }
 
+// zero-copy windows: the chunk rows [start, start + rows) are normalised and cast ONCE ((B+T-1) x F
+// values instead of B*T*F); the kernels that consume the layer-0 input address them as windows (row b + t)
+__global__ void chunk_prep_kernel(WindowSrc w, bf16_t* __restrict__ hi, bf16_t* __restrict__ lo, int64_t rows, int F) {
+    const int64_t total = rows * F;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int f = (int)(i % F);
+        float v = w.src[(w.start + i / F) * F + f];
+        if (w.xmin) v = (v - w.xmin[f]) / (w.xmax[f] - w.xmin[f]);
+        const bf16_t h = __float2bfloat16(v);
+        hi[i] = h;
+        if (lo) lo[i] = __float2bfloat16(v - __bfloat162float(h));
+    }
+}
+// whether a windowed (never collated) layer-0 input is possible: no input dropout to apply, and every GEMM tile of 128
+// (64) logical rows stays inside one time step
+static inline bool windows_direct(const bigru_plan& p, bool have_windows, bool do_drop) {
+    return have_windows && !do_drop && p.B % 128 == 0;
+}
+
 // inter-layer dropout: Yrow -> Xrow (masked); rows x cols = R x DH
 __global__ void dropout_rows_kernel(const bf16_t* __restrict__ Y, bf16_t* __restrict__ Xrow, int64_t R, int cols, int B, int T,
                                     float pdrop, uint64_t seed, uint32_t stream) {
@@ -368,13 +387,13 @@ static int tc_gemm(const void* A, int64_t a_rows, int64_t lda, const void* Bm, i
     if (split) {
         const int e1 = p.a_mn ? tcg::make_operand_map_mn(&tAl, Alo, (uint64_t)p.K, (uint64_t)a_rows, (uint64_t)lda)
                               : tcg::make_operand_map(&tAl, Alo, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda);
-        const int e2 = p.b_mn ? tcg::make_operand_map_mn(&tBl, Blo, (uint64_t)p.K, (uint64_t)b_rows, (uint64_t)ldb)
+        const int e2 = p.b_mn ? tcg::make_operand_map_mn(&tBl, Blo, (uint64_t)(p.b_win ? p.b_win_rows : p.K), (uint64_t)b_rows, (uint64_t)ldb)
                               : tcg::make_operand_map(&tBl, Blo, (uint64_t)b_rows, (uint64_t)p.K, (uint64_t)ldb);
         if (e1 || e2) { bigru_set_error("cuTensorMapEncodeTiled failed (low operand parts)"); return BIGRU_ERR_CUDA; }
     }
     const int ea = p.a_mn ? tcg::make_operand_map_mn(&tA, A, (uint64_t)p.K, (uint64_t)a_rows, (uint64_t)lda)
                           : tcg::make_operand_map(&tA, A, (uint64_t)a_rows, (uint64_t)p.K, (uint64_t)lda);
-    const int eb = p.b_mn ? tcg::make_operand_map_mn(&tB, Bm, (uint64_t)p.K, (uint64_t)b_rows, (uint64_t)ldb)
+    const int eb = p.b_mn ? tcg::make_operand_map_mn(&tB, Bm, (uint64_t)(p.b_win ? p.b_win_rows : p.K), (uint64_t)b_rows, (uint64_t)ldb)
                           : tcg::make_operand_map(&tB, Bm, (uint64_t)b_rows, (uint64_t)p.K, (uint64_t)ldb);
     if (ea || eb) {
         bigru_set_error("cuTensorMapEncodeTiled failed (rows %lld/%lld K %d ld %lld/%lld)", (long long)a_rows,
@@ -419,9 +438,13 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
             }
         KLAUNCH(KC_PACK, 0.0, 0.0, st, pack_all_kernel<<<dim3(148, nj), 256, 0, st>>>(jobs, H, D));
     }
-    // 2. layer-0 input: cast to bf16, time-major rows (+ input dropout)
-    KLAUNCH(KC_PACK, 0.0, 6.0 * R * F, st, cast_x_kernel<<<148 * 8, 256, 0, st>>>(x, win, (bf16_t*)(S + L.Xrow[0]), nullptr, B, T, F,
-                                                                                   do_drop ? drop : 0.f, spatial, seed));
+    // 2. layer-0 input: cast to bf16, time-major rows (+ input dropout) - or, for windows of a chunk, only the chunk itself
+    const bool direct = windows_direct(p, win.src != nullptr, do_drop);
+    if (direct)
+        KLAUNCH(KC_PACK, 0.0, 6.0 * (B + T - 1) * F, st, chunk_prep_kernel<<<148, 256, 0, st>>>(win, (bf16_t*)(S + L.Xrow[0]), nullptr, (int64_t)B + T - 1, F));
+    else
+        KLAUNCH(KC_PACK, 0.0, 6.0 * R * F, st, cast_x_kernel<<<148 * 8, 256, 0, st>>>(x, win, (bf16_t*)(S + L.Xrow[0]), nullptr, B, T, F,
+                                                                                       do_drop ? drop : 0.f, spatial, seed));
     for (int l = 0; l < p.L; ++l) {
         const int I = (int)p.in_size(l);
         const bf16_t* Xrow = (const bf16_t*)(S + L.Xrow[l]);
@@ -443,7 +466,9 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
             g.M = D * 3 * H; g.N = (int)R; g.K = I; g.batch = 1; g.splitk = 1; g.mode = tcg::OUT_SCAN_BF16;
             g.blk = tcg::ScanBlk{T, B, H, 3}; g.m_fast = 1;      // the few weight m-tiles share each activation tile via L2
             g.C = W + L.gi; g.ldc = R; g.bias = (const float*)(S + L.bfold[l]); g.bias_per_row = 1; g.dbg = dbg;
-            TRY(tc_gemm(S + L.Wih[l], D * 3 * H, I, Xrow, R, I, g, st));
+            const bool wnd = direct && l == 0;
+            g.b_win = wnd ? B : 0;
+            TRY(tc_gemm(S + L.Wih[l], D * 3 * H, I, Xrow, wnd ? (int64_t)B + T - 1 : R, I, g, st));
         }
         // 4. recurrence
         tcs::FwdParams f{};
@@ -451,7 +476,7 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
         f.Wimg = (const bf16_t*)(S + L.Wimg[l]); f.giB = (const bf16_t*)(W + L.gi); f.b_hn = (const float*)(S + L.bhn[l]);
         f.Yrow = (bf16_t*)(S + L.Yrow[l]); f.G = (bf16_t*)(S + L.G[l]); f.YB = (bf16_t*)(S + L.YB[l]);
         f.hn_out = hn ? hn + (int64_t)l * D * B * H : nullptr; f.dbg = dbg;
-        f.fuse_x = fuse_x ? 1 : 0; f.Xrow = Xrow; f.Wih = (const bf16_t*)(S + L.Wih[l]); f.bfold = (const float*)(S + L.bfold[l]);
+        f.fuse_x = fuse_x ? 1 : 0; f.x_win = (direct && l == 0) ? 1 : 0; f.Xrow = Xrow; f.Wih = (const bf16_t*)(S + L.Wih[l]); f.bfold = (const float*)(S + L.bfold[l]);
         {
             ProfScope ps(KC_TC_SCAN_FWD, 2.0 * 3 * H * H * (double)R * D, 0.0, st);
             CUDA_TRY(tcs::launch_fwd(f, st));
@@ -474,7 +499,6 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
 static int backward_bf16(const bigru_plan& p, const float* params, const float* x, const float* h0, float drop,
                          int spatial, int training, uint64_t seed, const void* stash_v, void* scratch_v,
                          const float* dlogits, float* grads, float* dx, float* dh0, cudaStream_t st) {
-    (void)x;
     if (h0 || dh0) { bigru_set_error("BIGRU_PREC_BF16: initial hidden state / its gradient are not supported"); return BIGRU_ERR_UNSUPPORTED; }
     const Bf16Layout L = bf16_layout(p);
     const uint8_t* S = (const uint8_t*)stash_v;
@@ -519,6 +543,8 @@ static int backward_bf16(const bigru_plan& p, const float* params, const float* 
             g.C = grads + p.off_wih(l, 0); g.ldc = I; g.zC = p.ld_block(l);
             for (int d = 0; d < D; ++d) { g.a_row_off[d] = d * 3 * H; g.b_row_off[d] = 0; g.b_k_off[d] = 0; }
             g.dbg = dbg;
+            g.b_win = (l == 0 && windows_direct(p, x == nullptr, do_drop)) ? B : 0;      // forward_windows left only the chunk in the stash
+            g.b_win_rows = B + T - 1;
             TRY(tc_gemm(W + L.gi, (int64_t)D * 3 * H, (int64_t)D * 3 * H, Xin, I, I, g, st, KC_TC_GEMM_DWIH));
         }
         // 3. dW_hh[d] = dgh[d]^T H_prev  with H_prev(t) = Y(t-1) (dir 0) / Y(t+1) (dir 1): a shift of -+B ROWS of the

@@ -237,8 +237,13 @@ static int forward_x3(const bigru_plan& p, const float* params, const float* x, 
             }
         KLAUNCH(KC_PACK, 0.0, 0.0, st, x3_pack_all_kernel<<<dim3(148, nj), 256, 0, st>>>(jobs, H, D));
     }
-    KLAUNCH(KC_PACK, 0.0, 8.0 * R * F, st, cast_x_kernel<<<148 * 8, 256, 0, st>>>(x, win, (bf16_t*)(S + L.Xhi[0]), (bf16_t*)(S + L.Xlo[0]), B, T, F,
-                                                                                   do_drop ? drop : 0.f, spatial, seed));
+    const bool direct = windows_direct(p, win.src != nullptr, do_drop);      // zero-copy windows: only the chunk is normalised and split
+    if (direct)
+        KLAUNCH(KC_PACK, 0.0, 8.0 * (B + T - 1) * F, st, chunk_prep_kernel<<<148, 256, 0, st>>>(win, (bf16_t*)(S + L.Xhi[0]), (bf16_t*)(S + L.Xlo[0]),
+                                                                                                 (int64_t)B + T - 1, F));
+    else
+        KLAUNCH(KC_PACK, 0.0, 8.0 * R * F, st, cast_x_kernel<<<148 * 8, 256, 0, st>>>(x, win, (bf16_t*)(S + L.Xhi[0]), (bf16_t*)(S + L.Xlo[0]), B, T, F,
+                                                                                       do_drop ? drop : 0.f, spatial, seed));
     for (int l = 0; l < p.L; ++l) {
         const int I = (int)p.in_size(l);
         const bf16_t* Xhi = (const bf16_t*)(S + L.Xhi[l]);
@@ -257,7 +262,9 @@ static int forward_x3(const bigru_plan& p, const float* params, const float* x, 
             g.M = D * 3 * H; g.N = (int)R; g.K = I; g.batch = 1; g.splitk = 1; g.mode = tcg::OUT_SCAN_F32;
             g.blk = tcg::ScanBlk{T, B, H, 3, 64, 32}; g.m_fast = 1;
             g.C = W + L.gi; g.ldc = R; g.bias = (const float*)(S + L.bfold[l]); g.bias_per_row = 1; g.dbg = dbg;
-            TRY(tc_gemm(S + L.Wih_hi[l], D * 3 * H, I, Xhi, R, I, g, st, KC_TC_GEMM, S + L.Wih_lo[l], Xlo));
+            const bool wnd = direct && l == 0;
+            g.b_win = wnd ? B : 0;
+            TRY(tc_gemm(S + L.Wih_hi[l], D * 3 * H, I, Xhi, wnd ? (int64_t)B + T - 1 : R, I, g, st, KC_TC_GEMM, S + L.Wih_lo[l], Xlo));
         }
         if (h0) {   // recurrent product of the initial state, exact fp32 (tiny: B x 3H x H per direction); the scan starts at step 1
             GemmArgs r = gemm_args(h0 + (int64_t)l * D * B * H, params + p.off_whh(l, 0), (float*)(W + L.gh0), B, 3 * H, H, H, 1, H, 1, 3 * H);
@@ -293,7 +300,6 @@ static int forward_x3(const bigru_plan& p, const float* params, const float* x, 
 static int backward_x3(const bigru_plan& p, const float* params, const float* x, const float* h0, float drop,
                        int spatial, int training, uint64_t seed, const void* stash_v, void* scratch_v,
                        const float* dlogits, float* grads, float* dx, float* dh0, cudaStream_t st) {
-    (void)x;
     const X3Layout L = x3_layout(p);
     const uint8_t* S = (const uint8_t*)stash_v;
     uint8_t* W = (uint8_t*)scratch_v;
@@ -341,6 +347,8 @@ static int backward_x3(const bigru_plan& p, const float* params, const float* x,
             g.C = grads + p.off_wih(l, 0); g.ldc = I; g.zC = p.ld_block(l);
             for (int d = 0; d < D; ++d) { g.a_row_off[d] = d * 3 * H; g.b_row_off[d] = 0; g.b_k_off[d] = 0; }
             g.dbg = dbg;
+            g.b_win = (l == 0 && windows_direct(p, x == nullptr, do_drop)) ? B : 0;      // forward_windows left only the chunk in the stash
+            g.b_win_rows = B + T - 1;
             TRY(tc_gemm(dgi_hi, (int64_t)D * 3 * H, (int64_t)D * 3 * H, Xin_hi, I, I, g, st, KC_TC_GEMM_DWIH, dgi_lo, Xin_lo));
         }
         for (int part = 0; part < 2; ++part) {   // dW_hh[d] = dgh[d]^T H_prev (time-shifted Y, see path_bf16.cuh)

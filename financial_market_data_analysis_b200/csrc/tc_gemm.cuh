@@ -51,6 +51,11 @@ struct Params {
     int m_fast;               // rasterisation: 1 = consecutive CTAs walk m-tiles first (B tile shared through L2)
     int stages;               // smem ring depth (1..4), chosen per problem: shallow rings let 3-4 CTAs share an SM
     int tma_store;            // 1: epilogue stages the tile in smem and writes it with TMA (store / reduce-add)
+    int b_win;                // > 0: the B operand is a set of stride-1 sliding windows over a chunk [rows][F] (the collated batch
+                              //      x[b,t,:] = chunk[b + t,:] is never materialised): logical row r = t*b_win + b (K-major B: the
+                              //      N index, MN-major B: the K index) lives at chunk row r / b_win + r % b_win.  A tile's 128 (64)
+                              //      rows must share one t: b_win % 128 (64) == 0.
+    int b_win_rows;           // host side: rows of that chunk (extent of the tensor map of a windowed MN-major B operand)
     int nsplit;               // 1: plain bf16 product; 3: fp32-class product of split operands, A_hi B_hi + A_hi B_lo + A_lo B_hi
                               //    (second pair of tensor maps = the low parts; three ring slots per k-block)
     unsigned int* dbg;        // watchdog record (nullable)
@@ -112,7 +117,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const bool a_lo = combo == 2, b_lo = combo == 1;
                 uint8_t* da = sA + s * A_BYTES;
                 uint8_t* db = sB + s * B_BYTES;
-                const int ar = p.a_row_off[z] + m0, br = p.b_row_off[z] + n0, kb = k + p.b_k_off[z];
+                const int ar = p.a_row_off[z] + m0;
+                int br = p.b_row_off[z] + n0, kb = k + p.b_k_off[z];
+                if (p.b_win) { if (p.b_mn) kb = kb / p.b_win + kb % p.b_win; else br = p.b_row_off[z] + n0 / p.b_win + n0 % p.b_win; }
                 if (p.a_mn) {        // two boxes of 64 (MN) x 64 (K rows)
                     if (a_lo) { tc::tma_load_2d(da, &tmAlo, &full[s], ar, k); tc::tma_load_2d(da + A_BYTES / 2, &tmAlo, &full[s], ar + 64, k); }
                     else { tc::tma_load_2d(da, &tmA, &full[s], ar, k); tc::tma_load_2d(da + A_BYTES / 2, &tmA, &full[s], ar + 64, k); }

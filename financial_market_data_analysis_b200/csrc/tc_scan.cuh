@@ -133,6 +133,7 @@ struct FwdParams {
     // fused input projection (layer 0, n_features == 64): gi_t = W_ih x_t + b is formed by the same tensor pipe between
     // the recurrent products (it is idle while the epilogue works), giB is not read
     int fuse_x;
+    int x_win;                    // 1: Xrow is a chunk [B+T-1][64] and x_t of batch row b is chunk row b + t (zero-copy windows)
     const __nv_bfloat16* Xrow;    // [R][64] time-major input rows
     const __nv_bfloat16* Wih;     // [D*3H][64] (rows r|z|n of direction d at d*3H)
     const float* bfold;           // [D*3H]  b_ih (+ b_hh for r, z)
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_c
                 if (s >= NSX && ok) ok = tc::mbar_wait(&in_empty[st], ((s / NSX) - 1) & 1, p.dbg, 0x300 + (s & 0xff));
                 const int t = d == 0 ? s : T - 1 - s;
                 tc::mbar_arrive_expect_tx(&in_full[st], X_TILE);
-                tc::tma_load_2d(sIn + (size_t)st * X_TILE, &p.tmX, &in_full[st], 0, t * B + tile * NB);
+                tc::tma_load_2d(sIn + (size_t)st * X_TILE, &p.tmX, &in_full[st], 0, p.x_win ? t + tile * NB : t * B + tile * NB);
             }
         }
     } else if (warp == EPI_WARPS + 1) {
@@ -485,7 +486,7 @@ static inline cudaError_t launch_fwd(const FwdParams& p_in, cudaStream_t st) {
     if (p.H != 128 && p.H != 256) return cudaErrorInvalidValue;
     const bool fx = p.fuse_x != 0;
     if (fx) {
-        const uint64_t dx[2] = {64u, (uint64_t)p.T * p.B};
+        const uint64_t dx[2] = {64u, p.x_win ? (uint64_t)(p.T + p.B - 1) : (uint64_t)p.T * p.B};
         const uint64_t sx[1] = {64u * 2};
         const uint32_t bx[2] = {64u, (uint32_t)NB};
         const uint64_t dw[2] = {64u, (uint64_t)p.D * 3 * p.H};

@@ -774,3 +774,43 @@ def test_cuda_graph_step_matches_plain_launches():
         ltol, ptol = (1e-3, 1e-2) if precision == "bf16" else (1e-5, 1e-5)
         assert np.abs(out[True][0] - out[False][0]).max() < ltol, precision
         assert rel_l2(out[True][1], out[False][1]) < ptol, precision
+
+
+@pytest.mark.parametrize("F", [64, 24])
+def test_zero_copy_windows_against_loader_and_model_oracles(F):
+    """SURVEY.md 8(f) N1 against the ORACLES (not against the repo's own collation): windows of a chunk through
+    ``forward_windows`` / ``train_step_windows`` equal loader_oracle.normalise + collate (sql_pytorch_dataloader.py:239-245)
+    followed by the reference model (biGRU_model.py:63-138, :198-210).  B = 128 windows: the tensor-core paths then never
+    materialise x[B,T,F] (the chunk is normalised / cast once and addressed as windows by TMA); F = 64 takes the fused
+    layer-0 projection of the bf16 scan, F = 24 the projection GEMM."""
+    pkg = _pkg()
+    B, T, H, L, C = 128, 12, 128, 2, 4
+    g = torch.Generator().manual_seed(21)
+    n_rows = B + T - 1 + 9
+    x_raw = torch.rand(n_rows, F, generator=g) * 50 + 3
+    y = (torch.rand(n_rows, C, generator=g) < 0.3).float()
+    xmin, xmax = x_raw.min(0, keepdim=True).values - 1, x_raw.max(0, keepdim=True).values + 2
+    start = 4
+    xb, yb = lo.collate(lo.normalise(x_raw.numpy(), xmin.numpy()[0], xmax.numpy()[0]), y.numpy(), list(range(start, start + B)), T)
+    torch.manual_seed(0)
+    ref = bo.OracleBiGRU(H, F, C, L, 1.0, 0.0, False, True)
+    sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
+    ropt = torch.optim.Adam(ref.parameters(), lr=1e-2)
+    ref.train()
+    want_logits = ref(torch.from_numpy(xb)).detach().numpy()
+    bo.train_step(ref, ropt, nn.BCEWithLogitsLoss(), torch.from_numpy(xb), torch.from_numpy(yb[:, 0]))
+    want_upd = np.concatenate([(v - sd0[k]).numpy().ravel() for k, v in ref.state_dict().items()])
+    for precision in precisions():
+        if not supported(precision, B, F, H):
+            continue
+        tol = TOL[precision]
+        ds = pkg.MySQLBatchLoader.from_tensors(x_raw.cuda(), y.cuda(), (xmin, xmax), window=T)
+        m = pkg.BiGRU(H, F, C, L, 1.0, 0.0, False, True, precision=precision)
+        m.load_state_dict(sd0)
+        m = m.cuda()
+        m.add_loss_fn(nn.BCEWithLogitsLoss()); m.add_optimizer(torch.optim.Adam(m.parameters(), lr=1e-2)); m.train()
+        got = m.forward_windows(ds, start, B)
+        assert rel(got.cpu().numpy(), want_logits) < tol["logits"], (precision, rel(got.cpu().numpy(), want_logits))
+        m.train_step_windows(ds, start, B)
+        got_upd = np.concatenate([(v.cpu() - sd0[k]).numpy().ravel() for k, v in m.state_dict().items()])
+        assert rel_l2(got_upd, want_upd) < tol["update"], (precision, rel_l2(got_upd, want_upd))
