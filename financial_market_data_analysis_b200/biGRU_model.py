@@ -128,6 +128,7 @@ class _BiGRUFunction(torch.autograd.Function):
         stash = plan.acquire_stash()
         training = bool(model.training and model.dropout_p > 0)
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
+        model._last_seed = seed                       # the dropout masks are a pure function of (seed, element index)
         _lib.check(lib.bigru_forward(plan.handle, _lib.ptr(model._flat), _lib.ptr(x), _lib.ptr(h0),
                                      float(model.dropout_p), int(bool(model.spatial_dropout)), int(training), seed,
                                      _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(logits), _lib.ptr(hn),

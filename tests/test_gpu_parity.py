@@ -814,3 +814,58 @@ def test_zero_copy_windows_against_loader_and_model_oracles(F):
         m.train_step_windows(ds, start, B)
         got_upd = np.concatenate([(v.cpu() - sd0[k]).numpy().ravel() for k, v in m.state_dict().items()])
         assert rel_l2(got_upd, want_upd) < tol["update"], (precision, rel_l2(got_upd, want_upd))
+
+
+def _bigru_uniform(seed, stream, idx):
+    """common.cuh bigru_uniform restated: splitmix64 finaliser over (seed, stream, element index) -> [0, 1)."""
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+    idx = np.asarray(idx, np.uint64)
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * (idx + np.uint64(1)) + (np.uint64(stream) << np.uint64(40)) * np.uint64(0xD1B54A32D192ED03)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(40)).astype(np.float64) * (1.0 / 16777216.0)
+
+
+@pytest.mark.parametrize("spatial", [False, True])
+def test_dropout_mask_injection_parity(spatial):
+    """A6 by mask injection: the kernels' dropout masks are a pure function of (seed, element index), so the test rebuilds
+    them on the host, applies the SAME masks inside the reference computation (input dropout biGRU_model.py:87-94 -
+    elementwise or per (b, f) channel over T - and nn.GRU's inter-layer dropout :55) and compares logits and dx."""
+    p = 0.3
+    for precision in precisions():
+        B, T, F, H, L, C = (8, 6, 10, 16, 2, 3) if precision == "fp32" else (32, 6, 16, 128, 2, 3)
+        torch.manual_seed(12)
+        m = _pkg().BiGRU(H, F, C, L, 50, p, spatial, True, precision=precision).cuda()
+        m.train()
+        g = torch.Generator().manual_seed(3)
+        x = torch.randn(B, T, F, generator=g)
+        dl = torch.randn(B, C, generator=g)
+        xg = x.cuda().requires_grad_(True)
+        y = m(xg)
+        y.backward(dl.cuda())
+        seed = m._last_seed
+        bi, ti, fi = np.meshgrid(np.arange(B), np.arange(T), np.arange(F), indexing="ij")
+        key0 = bi * F + fi if spatial else (bi * T + ti) * F + fi
+        mask0 = torch.from_numpy((_bigru_uniform(seed, 0, key0) >= p).astype(np.float32) / (1 - p))
+        bi, ti, ci = np.meshgrid(np.arange(B), np.arange(T), np.arange(2 * H), indexing="ij")
+        mask1 = torch.from_numpy((_bigru_uniform(seed, 1, (bi * T + ti) * (2 * H) + ci) >= p).astype(np.float32) / (1 - p))
+        sd = {k: v.detach().cpu().double() for k, v in m.state_dict().items()}
+        layers = []
+        for l in range(L):
+            gl = nn.GRU(F if l == 0 else 2 * H, H, num_layers=1, batch_first=True, bidirectional=True).double()
+            gl.load_state_dict({k.replace(f"_l{l}", "_l0").replace("gru.", ""): v for k, v in sd.items() if f"_l{l}" in k})
+            layers.append(gl)
+        xr = x.double().requires_grad_(True)
+        out0, h0n = layers[0](xr * mask0.double())
+        out1, h1n = layers[1](out0 * mask1.double())
+        last = h1n.sum(0)
+        s = out1[..., :H] + out1[..., H:]
+        cat = torch.cat([last, s.max(dim=1).values, s.sum(dim=1) / T], dim=1)
+        want = cat @ sd["linear.weight"].t() + sd["linear.bias"]
+        want.backward(dl.double())
+        tol = TOL[precision]
+        assert rel(y.detach().cpu().numpy(), want.detach().numpy()) < tol["logits"], (precision, spatial)
+        assert rel_l2(xg.grad.cpu().numpy(), xr.grad.numpy()) < tol["grads"] * 5, (precision, spatial)
+        assert ((xg.grad.cpu() == 0) == (mask0 == 0)).all()                # dx is zero exactly where the input was dropped
