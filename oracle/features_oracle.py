@@ -9,9 +9,11 @@ Follows /root/reference/create_database.py:76-190 (the CREATE VIEW statements) a
   target                        :163-185  LEAD(close, 8 / 15) vs close +- n1 / n2 * ATR; a comparison with NULL is not true -> 0
 Frames at the head of the table are shorter (SQL window frames clip at the partition start).  NULL is NaN.
 
-PARITY UNPINNED by the reference itself: the views need a MariaDB server, which this container does not have, and the
-reference ships no expected outputs for them.  tests/test_oracle_cpu.py cross-checks this restatement against an
-independent implementation (pandas.rolling with min_periods=1, ddof=0) and against hand-computed rows."""
+PINNED to the reference's own SQL: tests/golden/make_features_golden.py imports the UNMODIFIED create_database.py with a
+`mysql.connector` stub that forwards its statements to sqlite3 (window functions; MariaDB's STD registered as a window
+aggregate), fills the table with a seed-fixed synthetic market and stores what the reference's views return in
+tests/golden/features.npz; tests/test_oracle_cpu.py checks this restatement against it (exact) and, independently,
+against pandas.rolling and hand-computed rows."""
 from __future__ import annotations
 
 import numpy as np

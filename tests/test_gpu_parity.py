@@ -649,6 +649,23 @@ def test_window_features_other_periods_match_oracle():
 
 
 @pytest.mark.gpu
+def test_window_features_match_reference_sql(golden_dir):
+    """SURVEY.md 8(f) N4 against the reference's own SQL (tests/golden/features.npz: create_database.py's views executed
+    unmodified through sqlite3): the kernel's features, NULL positions and target labels."""
+    from financial_market_data_analysis_b200.features import window_features
+    z = np.load(os.path.join(golden_dir, "features.npz"))
+    cols = [torch.from_numpy(z[k].astype(np.float32)).cuda() for k in ("close", "high", "low", "volume", "delta")]
+    got_f, got_t = window_features(*cols, volume_MA_periods=[int(v) for v in z["volume_MA_periods"]],
+                                   price_MA_periods=[int(v) for v in z["price_MA_periods"]], delta_MA_periods=[int(v) for v in z["delta_MA_periods"]],
+                                   bollinger_bands_period=int(z["bollinger_bands_period"]), bollinger_bands_std=float(z["bollinger_bands_std"]),
+                                   stochastic_oscillator=True)
+    g = got_f.cpu().numpy()
+    assert np.array_equal(np.isnan(g), np.isnan(z["features"]))
+    np.testing.assert_allclose(np.nan_to_num(g), np.nan_to_num(z["features"]), rtol=2e-6, atol=5e-4)
+    assert np.array_equal(got_t.cpu().numpy(), z["targets"])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n", [1, 7, 16, 500, 20000])
 def test_window_features_match_oracle(n):
     from oracle import features_oracle as fo

@@ -208,3 +208,19 @@ def test_features_oracle_hand_rows_and_shapes():
     np.testing.assert_allclose(feats[1:, 4], [1.0, 0.5, 1.0])                 # stoch over all rows so far
     f0, t0 = fo.window_features(np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0))
     assert f0.shape == (0, 9) and t0.shape == (0, 4)
+
+
+def test_features_oracle_against_reference_sql(golden_dir):
+    """SURVEY.md 8(f) N4, pinned: the restatement equals what the reference's own CREATE VIEW statements
+    (create_database.py:76-190, executed unmodified through the sqlite3 shim of tests/golden/make_features_golden.py)
+    return - every feature column, the SQL NULLs and the four target labels."""
+    from oracle import features_oracle as fo
+    z = np.load(os.path.join(golden_dir, "features.npz"))
+    cols = [z[k].astype(np.float64) for k in ("close", "high", "low", "volume", "delta")]
+    f, t = fo.window_features(*cols, volume_MA_periods=list(z["volume_MA_periods"]), price_MA_periods=list(z["price_MA_periods"]),
+                              delta_MA_periods=list(z["delta_MA_periods"]), bollinger_bands_period=int(z["bollinger_bands_period"]),
+                              bollinger_bands_std=float(z["bollinger_bands_std"]), stochastic_oscillator=True)
+    assert int(z["n_views"]) == 8 and f.shape == z["features"].shape
+    assert np.array_equal(np.isnan(f), np.isnan(z["features"]))
+    np.testing.assert_allclose(np.nan_to_num(f), np.nan_to_num(z["features"]), rtol=1e-12, atol=1e-9)
+    assert np.array_equal(t, z["targets"])
