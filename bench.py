@@ -334,9 +334,12 @@ def main():
             psteps = 3
             if rank == 0:
                 lib.bigru_prof_enable(1)
+            graphs_were = getattr(model, "use_cuda_graph", False)
+            model.use_cuda_graph = False            # the per-kernel events are recorded by the launch wrappers: plain launches here
             for i in range(psteps):                 # every rank steps (the step contains the gradient all-reduce)
                 step_resident(i)
             barrier()
+            model.use_cuda_graph = graphs_were
             if rank == 0:
                 rows = []
                 for k in range(lib.bigru_prof_classes()):

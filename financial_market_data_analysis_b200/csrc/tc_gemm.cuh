@@ -105,13 +105,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tc::tma_prefetch_desc(&tmB);
             if (p.nsplit > 1) { tc::tma_prefetch_desc(&tmAlo); tc::tma_prefetch_desc(&tmBlo); }
             const int nit = nkb * p.nsplit;
+            int combo = 0, kbi = kb0, s = 0;                        // advanced incrementally: no divisions on the issue path
+            uint32_t ph = 0;
             for (int i = 0; i < nit; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (i / STAGES) & 1;
                 if (!tc::mbar_wait(&empty[s], ph ^ 1, p.dbg, 0x100 + s)) break;
                 tc::mbar_arrive_expect_tx(&full[s], A_BYTES + B_BYTES);
-                const int combo = i % p.nsplit;                     // 0: hi x hi, 1: hi x lo, 2: lo x hi
-                const int k = (kb0 + i / p.nsplit) * BK;
+                // combo 0: hi x hi, 1: hi x lo, 2: lo x hi
+                const int k = kbi * BK;
                 // (each call names its tensor map directly: a run-time selected pointer makes the compiler copy the 128-byte
                 // descriptor to local memory)
                 const bool a_lo = combo == 2, b_lo = combo == 1;
@@ -134,15 +134,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     if (b_lo) tc::tma_load_2d(db, &tmBlo, &full[s], kb, br);
                     else tc::tma_load_2d(db, &tmB, &full[s], kb, br);
                 }
+                if (++combo == p.nsplit) { combo = 0; ++kbi; }
+                if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
         if (tc::elect_one()) {
             const uint32_t idesc = tc::umma_idesc_bf16(BM, BN, (uint32_t)p.a_mn, (uint32_t)p.b_mn);
             const int nit = nkb * p.nsplit;
-            for (int i = 0; i < nit; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (i / STAGES) & 1;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int i = 0; i < nit; ++i, s = (s + 1 == STAGES ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
                 if (!tc::mbar_wait(&full[s], ph, p.dbg, 0x200 + s)) break;
                 tc::tcgen05_fence_after();
                 const uint32_t aa = tc::smem_u32(sA + s * A_BYTES), ab = tc::smem_u32(sB + s * B_BYTES);
@@ -195,10 +197,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
                             w[j] = *reinterpret_cast<uint32_t*>(&h2);
                         }
-                        *reinterpret_cast<uint4*>(dst + ml * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                        tc::sts_u4(tc::smem_u32(dst) + ml * 16, make_uint4(w[0], w[1], w[2], w[3]));      // explicit st.shared (not generic)
                     } else {
-                        *reinterpret_cast<float4*>(dst + ml * 32) = make_float4(f[0], f[1], f[2], f[3]);
-                        *reinterpret_cast<float4*>(dst + ml * 32 + 16) = make_float4(f[4], f[5], f[6], f[7]);
+                        tc::sts_f4(tc::smem_u32(dst) + ml * 32, make_float4(f[0], f[1], f[2], f[3]));
+                        tc::sts_f4(tc::smem_u32(dst) + ml * 32 + 16, make_float4(f[4], f[5], f[6], f[7]));
                     }
                 }
             }
@@ -267,14 +269,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             w[j] = *reinterpret_cast<uint32_t*>(&h2);
                         }
                         const uint32_t chunk = ((uint32_t)((c & 1) * 4 + k4)) ^ sw;
-                        *reinterpret_cast<uint4*>(box + chunk * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                        tc::sts_u4(tc::smem_u32(box) + chunk * 16, make_uint4(w[0], w[1], w[2], w[3]));
                     }
                 } else {
                     uint8_t* box = smem + (size_t)c * 16384 + (size_t)ml * 128;
 #pragma unroll
                     for (int k4 = 0; k4 < 8; ++k4) {
                         const uint32_t chunk = ((uint32_t)k4) ^ sw;
-                        *reinterpret_cast<uint4*>(box + chunk * 16) = make_uint4(v[k4 * 4], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
+                        tc::sts_u4(tc::smem_u32(box) + chunk * 16, make_uint4(v[k4 * 4], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]));
                     }
                 }
             }

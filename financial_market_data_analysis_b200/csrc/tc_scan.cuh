@@ -370,8 +370,6 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_c
                 if (ok) ok = tc::mbar_wait(&in_full[st], (s / NSF) & 1, p.dbg, 0x200 + (s & 0xff));
                 const uint4* gp = reinterpret_cast<const uint4*>(sIn + (size_t)st * GI_BLOCK) + tid;
                 const uint4 u0 = gp[0], u1 = gp[256], u2 = gp[512];
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&in_empty[st]);
                 const __nv_bfloat16* t8 = reinterpret_cast<const __nv_bfloat16*>(&u0);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) gr[i] = __bfloat162float(t8[i]);
@@ -447,6 +445,10 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_fwd_kernel(const __grid_c
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(epi_done);
+            // the ring slot is released only HERE, after this step's results (which consume every value loaded from the slot)
+            // have been written: an arrive right behind the loads was seen to overtake them (the loads sat in the LSU queue behind
+            // the previous step's global stores), so the producer's next bulk copy replaced the slot before it had been read
+            if (!FX && lane == 0) tc::mbar_arrive(&in_empty[s % NSF]);
             if (tid == 0) SCAN_TS(10);
             if (tid == 224) SCAN_TS(13);
             {
@@ -763,8 +765,6 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
                     const float4* dyp = reinterpret_cast<const float4*>(base + G_BLOCK + YB_BLOCK) + 2 * tid;
                     a = dyp[0]; b = dyp[1];
                 }
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&in_empty[st]);
                 const __nv_bfloat16* t8 = reinterpret_cast<const __nv_bfloat16*>(&u0);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) vr[i] = __bfloat162float(t8[i]);
@@ -853,6 +853,10 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scan_bwd_kernel(const __grid_c
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(epi_done);
+            // the ring slot is released only HERE, after this step's results (which consume every value loaded from the slot)
+            // have been written: an arrive right behind the loads was seen to overtake them (the loads sat in the LSU queue behind
+            // the previous step's global stores), so the producer's next bulk copy replaced the slot before it had been read
+            if (lane == 0) tc::mbar_arrive(&in_empty[s % NSB]);
             if (tid == 0) SCAN_TS(10);
 #pragma unroll
             for (int i = 0; i < 8; ++i)

@@ -72,12 +72,23 @@ __device__ __forceinline__ void tmem_ld16f(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// the registers of a tcgen05.ld are defined only after tcgen05.wait::ld: tie them to the wait so that no consumer (not even a
+// register move) can be scheduled between the load and the wait
+__device__ __forceinline__ void tmem_ld_wait_pin(float (&a)[16], float (&b)[16], float (&c)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) asm volatile("" : "+f"(a[i]), "+f"(b[i]), "+f"(c[i]));
+}
+__device__ __forceinline__ void tmem_ld_wait_pin(float (&a)[16], float (&b)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) asm volatile("" : "+f"(a[i]), "+f"(b[i]));
+}
 
 __device__ __forceinline__ size_t blk_index(int d, int tile, int t, int c, int ntiles, int T, int CS) {
     return (((size_t)d * ntiles + tile) * T + t) * CS + c;
 }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
-__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 static inline size_t fwd_smem_bytes(int H) {
     const int KC = H / 64;
@@ -139,7 +150,8 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_fwd_kernel(const __grid_
     uint64_t* epi_done = bars + 9;
     uint64_t* in_full = bars + 10;           // [NSF]
     uint64_t* in_empty = bars + 10 + NSF;    // [NSF]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * NSF);
+    uint64_t* xch = bars + 10 + 2 * NSF;     // [8] per epilogue warp: "my half of the lane-half swap is in shared memory"
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18 + 2 * NSF);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t c = CS > 1 ? tc::cluster_ctarank() : 0u;
@@ -153,6 +165,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_fwd_kernel(const __grid_
         tc::mbar_init(mma_done, 1);
         tc::mbar_init(epi_done, EPI_WARPS);
         for (int i = 0; i < NSF; ++i) { tc::mbar_init(&in_full[i], 1); tc::mbar_init(&in_empty[i], EPI_WARPS); }
+        for (int i = 0; i < EPI_WARPS; ++i) tc::mbar_init(&xch[i], 1);
         // first use of the per-source "peer chunk landed" barriers (h_s lands in buffer s & 1): armed here, before the
         // cluster-wide sync below, so that a fast peer's st.async bytes can never reach a barrier that does not expect them
         if (CS > 1)
@@ -263,10 +276,9 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_fwd_kernel(const __grid_
         const uint32_t sIn_u = tc::smem_u32(sIn), sH_u = tc::smem_u32(sH);
         const uint32_t xmine = tc::smem_u32(sX) + (uint32_t)((warp * 6 * 32 + lane) * 16);
         const uint32_t xpeer = tc::smem_u32(sX) + (uint32_t)(((warp ^ 2) * 6 * 32 + lane) * 16);
-        const int pair_id = 2 + (q & 1) + 2 * half;
         constexpr float L2E = 1.4426950408889634f;
         bool ok = true;
-        uint32_t mma_rounds = 0;
+        uint32_t mma_rounds = 0, xch_rounds = 0;
         // publish this thread's 8 values of h (hi, lo) in this CTA's chunk of operand buffer `buf`, then one arrival per
         // warp on epi_done; the control thread forwards the finished chunk to the peers
         auto publish = [&](const float (&h8)[8], int buf) {
@@ -293,8 +305,6 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_fwd_kernel(const __grid_
                 const uint32_t gp = sIn_u + (uint32_t)st * GI_BLOCK + 32u * tid;
                 const float4 a0 = tc::lds_f4(gp), a1 = tc::lds_f4(gp + 16), b0 = tc::lds_f4(gp + 8192), b1 = tc::lds_f4(gp + 8192 + 16),
                              n0 = tc::lds_f4(gp + 16384), n1 = tc::lds_f4(gp + 16384 + 16);
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&in_empty[st]);
                 gr[0] = a0.x; gr[1] = a0.y; gr[2] = a0.z; gr[3] = a0.w; gr[4] = a1.x; gr[5] = a1.y; gr[6] = a1.z; gr[7] = a1.w;
                 gz[0] = b0.x; gz[1] = b0.y; gz[2] = b0.z; gz[3] = b0.w; gz[4] = b1.x; gz[5] = b1.y; gz[6] = b1.z; gz[7] = b1.w;
                 gn[0] = n0.x; gn[1] = n0.y; gn[2] = n0.z; gn[3] = n0.w; gn[4] = n1.x; gn[5] = n1.y; gn[6] = n1.z; gn[7] = n1.w;
@@ -309,7 +319,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_fwd_kernel(const __grid_
                 float v[3][16];
                 const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(16 * half);
                 tmem_ld16f(ta, v[0]); tmem_ld16f(ta + NB, v[1]); tmem_ld16f(ta + 2 * NB, v[2]);
-                tc::tmem_ld_wait();
+                tmem_ld_wait_pin(v[0], v[1], v[2]);
                 if (tid == 0) SCANX_TS(8);
                 // hi rows keep columns [0, 8) of their half and hand [8, 16) to the lo rows' warp, and vice versa
 #pragma unroll
@@ -317,7 +327,12 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_fwd_kernel(const __grid_
                     tc::sts_f4(xmine + (uint32_t)((g * 2 + 0) * 512), make_float4(part ? v[g][0] : v[g][8], part ? v[g][1] : v[g][9], part ? v[g][2] : v[g][10], part ? v[g][3] : v[g][11]));
                     tc::sts_f4(xmine + (uint32_t)((g * 2 + 1) * 512), make_float4(part ? v[g][4] : v[g][12], part ? v[g][5] : v[g][13], part ? v[g][6] : v[g][14], part ? v[g][7] : v[g][15]));
                 }
-                pair_barrier(pair_id);
+                // hand-over through mbarriers (release / acquire at CTA scope): this warp's half is written -> arrive on its own
+                // barrier, then wait for the partner's
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&xch[warp]);
+                if (ok) ok = tc::mbar_wait(&xch[warp ^ 2], xch_rounds & 1, p.dbg, 0x1900 + (s & 0xff));
+                ++xch_rounds;
                 float o[3][8];
 #pragma unroll
                 for (int g = 0; g < 3; ++g) {
@@ -360,6 +375,10 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_fwd_kernel(const __grid_
             }
             if (tid == 0) SCANX_TS(10);
             publish(hprev, s & 1);
+            // the ring slot is released only HERE, after this step's results (which consume every value loaded from the slot)
+            // have been written: an arrive right behind the loads was seen to overtake them (the loads sat in the LSU queue behind
+            // the previous step's global stores), so the producer's next bulk copy replaced the slot before it had been read
+            if (lane == 0) tc::mbar_arrive(&in_empty[s % NSF]);
             if (tid == 0) SCANX_TS(11);
             {   // stash (off the chain)
                 float4* gs = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(p.GX) + blk * G_BLOCK) + 2 * tid;
@@ -630,7 +649,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_bwd_kernel(const __grid_
                 const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(16 * half);
                 tmem_ld16f(ta + (uint32_t)((0 * NKH + kh) * NB), vh);
                 tmem_ld16f(ta + (uint32_t)((1 * NKH + kh) * NB), vl);
-                tc::tmem_ld_wait();
+                tmem_ld_wait_pin(vh, vl);
                 const uint32_t dest = (uint32_t)(2 * kh + (q >> 1));
                 const uint32_t lp = rb_local + r_off;
                 if (dest == c) {
@@ -685,8 +704,6 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_bwd_kernel(const __grid_
                 float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0, y0 = p0, y1 = p0;
                 if (!first) { p0 = tc::lds_f4(gp + G_BLOCK); p1 = tc::lds_f4(gp + G_BLOCK + 16); }
                 if (!top) { y0 = tc::lds_f4(gp + G_BLOCK + YB_BLOCK); y1 = tc::lds_f4(gp + G_BLOCK + YB_BLOCK + 16); }
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&in_empty[st]);
                 vr[0] = a0.x; vr[1] = a0.y; vr[2] = a0.z; vr[3] = a0.w; vr[4] = a1.x; vr[5] = a1.y; vr[6] = a1.z; vr[7] = a1.w;
                 vz[0] = b0.x; vz[1] = b0.y; vz[2] = b0.z; vz[3] = b0.w; vz[4] = b1.x; vz[5] = b1.y; vz[6] = b1.z; vz[7] = b1.w;
                 vn[0] = n0.x; vn[1] = n0.y; vn[2] = n0.z; vn[3] = n0.w; vn[4] = n1.x; vn[5] = n1.y; vn[6] = n1.z; vn[7] = n1.w;
@@ -745,6 +762,10 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_bwd_kernel(const __grid_
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(epi_done);
+            // the ring slot is released only HERE, after this step's results (which consume every value loaded from the slot)
+            // have been written: an arrive right behind the loads was seen to overtake them (the loads sat in the LSU queue behind
+            // the previous step's global stores), so the producer's next bulk copy replaced the slot before it had been read
+            if (lane == 0) tc::mbar_arrive(&in_empty[s % NSB]);
             if (tid == 0) SCANX_TS(10);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {

@@ -97,13 +97,18 @@ static int run_case(int B, int T, int H, int D, int reps, int use_h0, int top) {
     CK(cudaMemcpy(G.data(), d_G, G.size() * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(hn.data(), d_hn, hn.size() * 4, cudaMemcpyDeviceToHost));
     // ---- CPU forward in double, full stash for the BPTT below (first rows of the batch only: they cover several tiles)
-    const int bcheck = B > 40 ? 40 : B;
+    // rows checked: the first 40 (several tiles) and, with SCANX_ALLTILES, one row of every 5 across the whole batch
+    std::vector<int> rows_chk;
+    for (int b = 0; b < (B > 40 ? 40 : B); ++b) rows_chk.push_back(b);
+    if (getenv("SCANX_ALLTILES")) for (int b = 40; b < B; b += 5) rows_chk.push_back(b);
+    const int bcheck = (int)rows_chk.size();
     double eY = 0, eG = 0, eHn = 0;
     int nbad = 0; std::vector<int> bad_b(B, 0), bad_s(T, 0);
     // stash[d][b][s] -> r, z, n, hn, hprev per unit
     std::vector<double> sr((size_t)D * bcheck * T * H), sz(sr.size()), sn(sr.size()), shn(sr.size()), shp(sr.size());
     for (int d = 0; d < D; ++d)
-        for (int b = 0; b < bcheck; ++b) {
+        for (int bi = 0; bi < bcheck; ++bi) {
+            const int b = rows_chk[bi];
             std::vector<double> hs(H, 0.0), hnew(H);
             if (use_h0) for (int j = 0; j < H; ++j) hs[j] = h0[((size_t)d * B + b) * H + j];
             for (int s = 0; s < T; ++s) {
@@ -123,7 +128,7 @@ static int run_case(int B, int T, int H, int D, int reps, int use_h0, int top) {
                     const double hnv = a[2] + bhn[d * H + j];
                     const double n = tanh(gp[2 * H + j] + r * hnv);
                     hnew[j] = n + z * (hs[j] - n);
-                    const size_t si = (((size_t)d * bcheck + b) * T + t) * H + j;
+                    const size_t si = (((size_t)d * bcheck + bi) * T + t) * H + j;
                     sr[si] = r; sz[si] = z; sn[si] = n; shn[si] = hnv; shp[si] = hs[j];
                     eG = fmax(eG, fabs(r - G[bidx(d, b, t, j, 0, 4, B, T, H)]));
                     eG = fmax(eG, fabs(z - G[bidx(d, b, t, j, 1, 4, B, T, H)]));
@@ -141,7 +146,7 @@ static int run_case(int B, int T, int H, int D, int reps, int use_h0, int top) {
             }
             for (int j = 0; j < H; ++j) eHn = fmax(eHn, fabs(hs[j] - hn[((size_t)d * B + b) * H + j]));
         }
-    if (nbad) { printf("   bad per batch row:"); for (int b = 0; b < bcheck; ++b) printf(" %d", bad_b[b]); printf("\n   bad per step:"); for (int t = 0; t < T; ++t) printf(" %d", bad_s[t]); printf("\n"); }
+    if (nbad) { printf("   bad per batch row:"); for (int b = 0; b < B; ++b) if (bad_b[b]) printf(" %d:%d", b, bad_b[b]); printf("\n   bad per step:"); for (int t = 0; t < T; ++t) printf(" %d", bad_s[t]); printf("\n"); }
     const bool fpass = hdbg[0] == 0 && eY < 2e-5 && eG < 2e-5 && eHn < 2e-5;
     printf("%s scanx_fwd B=%d T=%d H=%d D=%d h0=%d (cluster %d, grid %d): errY=%.2e errG=%.2e errHn=%.2e dbg=%x blk=%u thr=%u  %.3f ms (%.2f us/step)\n",
            fpass ? "PASS" : "FAIL", B, T, H, D, use_h0, CS, D * (B / 32) * CS, eY, eG, eHn, hdbg[0], hdbg[1], hdbg[2], ms, ms * 1e3 / T);
@@ -185,7 +190,8 @@ static int run_case(int B, int T, int H, int D, int reps, int use_h0, int top) {
     CK(cudaMemcpy(dh0.data(), d_dh0, dh0.size() * 4, cudaMemcpyDeviceToHost));
     double eD = 0, eH0 = 0, mD = 0;
     for (int d = 0; d < D; ++d)
-        for (int b = 0; b < bcheck; ++b) {
+        for (int bi = 0; bi < bcheck; ++bi) {
+            const int b = rows_chk[bi];
             std::vector<double> carry(H, 0.0), rec(H, 0.0), dgh(3 * H);
             if (top)
                 for (int j = 0; j < H; ++j) { double dl = 0; for (int c = 0; c < C; ++c) dl += (double)dlog[(size_t)b * C + c] * linw[(size_t)c * 3 * H + j]; carry[j] = dl; }
@@ -193,7 +199,7 @@ static int run_case(int B, int T, int H, int D, int reps, int use_h0, int top) {
                 const int t = d == 0 ? T - 1 - s : s;
                 const long row = (long)t * B + b;
                 for (int j = 0; j < H; ++j) {
-                    const size_t si = (((size_t)d * bcheck + b) * T + t) * H + j;
+                    const size_t si = (((size_t)d * bcheck + bi) * T + t) * H + j;
                     double dy;
                     if (top) {
                         double dm = 0, da = 0;
@@ -243,6 +249,12 @@ static int run_case(int B, int T, int H, int D, int reps, int use_h0, int top) {
 int main() {
     setvbuf(stdout, NULL, _IONBF, 0);
     int bad = 0;
+    if (getenv("SCANX_BIG")) {
+        const int n = atoi(getenv("SCANX_BIG"));
+        for (int i = 0; i < n; ++i) bad += run_case(512, 128, 256, 2, 0, 0, 1);
+        printf("big: %d failures of %d\n", bad / 2, n);
+        return bad ? 1 : 0;
+    }
     if (getenv("SCANX_STRESS")) {
         const int h0 = atoi(getenv("SCANX_STRESS"));
         for (int i = 0; i < 25; ++i) bad += run_case(64, 11, 256, 2, 0, h0, 1);
