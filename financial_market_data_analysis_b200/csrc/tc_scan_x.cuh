@@ -224,18 +224,6 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_fwd_kernel(const __grid_
                 ++epi_rounds;
                 SCANX_TS(0);
                 tc::tcgen05_fence_after();
-                // this CTA's chunk of h_{s-1} (hi, lo: 4 KB each, contiguous in the tile) goes to every peer's tile as two bulk
-                // DSMEM copies that complete on the peer's source-indexed barrier: the copy engine moves the 24 KB while the
-                // tensor pipe works on the local chunk, and the epilogue warps do not spend ~1500 cycles issuing st.async
-                if (CS > 1) {
-                    uint8_t* own = sH + (size_t)pb * 2 * TILE_BYTES + (size_t)c * H_CHUNK;
-#pragma unroll
-                    for (uint32_t i = 1; i < (uint32_t)CS; ++i) {
-                        const uint32_t pr = (c + i) % CS;
-                        tc::bulk_s2cluster(own, own, H_CHUNK, &h_full[pb * 4 + (int)c], pr);
-                        tc::bulk_s2cluster(own + TILE_BYTES, own + TILE_BYTES, H_CHUNK, &h_full[pb * 4 + (int)c], pr);
-                    }
-                }
                 // own chunk first (it is local), then the peers' chunks in ring order as they land
                 fwd_issue_chunk<H, true>(tmem, tmem + A_COL + c * 32, tc::umma_desc_k_sw128(tb + c * H_CHUNK),
                                          tc::umma_desc_k_sw128(tb + TILE_BYTES + c * H_CHUNK));
@@ -273,15 +261,18 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_fwd_kernel(const __grid_
         uint32_t h_off[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) h_off[i] = c * H_CHUNK + tc::sw128_offset(c0 + i, j);
+        // the 16-byte piece this lane forwards to the peers: 8 units of lane group lane/8, batch row c0 + lane%8
+        const uint32_t fwd_off = c * H_CHUNK + tc::sw128_offset(c0 + (lane & 7), (q & 1) * 32 + (lane >> 3) * 8);
         const uint32_t sIn_u = tc::smem_u32(sIn), sH_u = tc::smem_u32(sH);
         const uint32_t xmine = tc::smem_u32(sX) + (uint32_t)((warp * 6 * 32 + lane) * 16);
         const uint32_t xpeer = tc::smem_u32(sX) + (uint32_t)(((warp ^ 2) * 6 * 32 + lane) * 16);
         constexpr float L2E = 1.4426950408889634f;
         bool ok = true;
         uint32_t mma_rounds = 0, xch_rounds = 0;
-        // publish this thread's 8 values of h (hi, lo) in this CTA's chunk of operand buffer `buf`, then one arrival per
-        // warp on epi_done; the control thread forwards the finished chunk to the peers
-        auto publish = [&](const float (&h8)[8], int buf) {
+        // publish this thread's 8 values of h (hi, lo) in operand buffer `buf`: own tile + every peer's (st.async on the
+        // source-indexed barrier: the bytes travel while the other warps still compute; a bulk DSMEM copy issued by the
+        // control thread after epi_done was measured slower, 0.48 vs 0.41 ms per launch), then one arrival per warp on epi_done
+        auto publish = [&](const float (&h8)[8], int buf, bool to_peers) {
             const uint32_t hb = sH_u + (uint32_t)buf * 2 * TILE_BYTES;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -291,6 +282,19 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_fwd_kernel(const __grid_
                 tc::sts_bf16(hb + TILE_BYTES + h_off[i], lo);
             }
             tc::tcgen05_fence_before();
+            if (CS > 1 && to_peers) {
+                __syncwarp();
+                const uint32_t a_hi = hb + fwd_off, a_lo = a_hi + TILE_BYTES, a_bar = tc::smem_u32(&h_full[buf * 4 + (int)c]);
+                const uint4 vh = tc::lds_u4(a_hi);
+                const uint4 vl = tc::lds_u4(a_lo);
+#pragma unroll
+                for (uint32_t i = 1; i < (uint32_t)CS; ++i) {
+                    const uint32_t pr = (c + i) % CS;
+                    const uint32_t rbar = tc::mapa_u32(a_bar, pr);
+                    tc::st_async_v4(tc::mapa_u32(a_hi, pr), vh, rbar);
+                    tc::st_async_v4(tc::mapa_u32(a_lo, pr), vl, rbar);
+                }
+            }
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(epi_done);
@@ -374,7 +378,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_fwd_kernel(const __grid_
                 hprev[i] = fmaf(z, hprev[i] - n, n);
             }
             if (tid == 0) SCANX_TS(10);
-            publish(hprev, s & 1);
+            publish(hprev, s & 1, s + 1 < T);
             // the ring slot is released only HERE, after this step's results (which consume every value loaded from the slot)
             // have been written: an arrive right behind the loads was seen to overtake them (the loads sat in the LSU queue behind
             // the previous step's global stores), so the producer's next bulk copy replaced the slot before it had been read
