@@ -79,7 +79,7 @@ class _Plan:
                    "bigru_device_check")
         h = _lib.C.c_void_p()
         _lib.check(lib.bigru_plan_create(B, T, model.n_features, model.hidden_size, model.n_layers, model.output_size,
-                                         int(model.bidirectional), _PRECISIONS[model.precision], _lib.C.byref(h)),
+                                         int(model.bidirectional), _PRECISIONS[model.resolved_precision(B)], _lib.C.byref(h)),
                    "bigru_plan_create")
         self.handle, self.B, self.T, self.device = h, B, T, device
         a, b = _lib.C.c_size_t(), _lib.C.c_size_t()
@@ -169,8 +169,13 @@ class BiGRU(nn.Module):
 
     Parameters (same order and defaults as the reference, :32-33): hidden_size, n_features,
     output_size, n_layers=1, clip=50, dropout=0.2, spatial_dropout=True, bidirectional=True.
-    Extra keyword ``precision``: "fp32" (FFMA kernels; the parity path) or "bf16" (bf16 operands
-    on tcgen05 tensor cores, fp32 accumulation and state).  Default: $BIGRU_B200_PRECISION or "fp32".
+    Extra keyword ``precision``:
+      "fp32"    FFMA kernels, exact transcendental functions; any shape (the exact path),
+      "bf16x3"  fp32-class on tcgen05 tensor cores (every operand a (hi, lo) bf16 pair, fp32 accumulation / state /
+                gradients): meets the reference's 1e-4 logits tolerance; H in {128, 256}, batch % 32 == 0, features % 8 == 0,
+      "bf16"    single bf16 operands on tcgen05, fp32 accumulation and state (fastest, ~3e-3 on logits),
+      "auto"    "bf16x3" for every batch shape it takes, "fp32" otherwise (decided per batch shape).
+    Default: $BIGRU_B200_PRECISION or "fp32".
     """
 
     def __init__(self, hidden_size, n_features, output_size, n_layers=1, clip=50, dropout=0.2,
@@ -186,8 +191,8 @@ class BiGRU(nn.Module):
         self.bidirectional = bidirectional
         self.n_directions = 2 if bidirectional else 1
         self.precision = precision or os.environ.get("BIGRU_B200_PRECISION", "fp32")
-        if self.precision not in _PRECISIONS:
-            raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+        if self.precision != "auto" and self.precision not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_PRECISIONS) + ['auto']}")
 
         # same submodule names and construction order as the reference (:50-60) so that a given
         # torch.manual_seed produces the same initial weights and state_dict keys
@@ -266,8 +271,15 @@ class BiGRU(nn.Module):
         return self._flat
 
     # ------------------------------------------------------------------ plans
+    def resolved_precision(self, batch: int) -> str:
+        """The precision a batch of this size runs at ("auto": the fp32-class tensor-core path wherever it applies)."""
+        if self.precision != "auto":
+            return self.precision
+        ok = self.hidden_size in (128, 256) and batch % 32 == 0 and self.n_features % 8 == 0
+        return "bf16x3" if ok else "fp32"
+
     def _plan_for(self, x) -> _Plan:
-        key = (int(x.shape[0]), int(x.shape[1]), self.precision, x.device.index)
+        key = (int(x.shape[0]), int(x.shape[1]), self.resolved_precision(int(x.shape[0])), x.device.index)
         plan = self._plans.get(key)
         if plan is None:
             if len(self._plans) > 8:

@@ -477,6 +477,25 @@ def test_error_conventions():
         pkg.BiGRU(8, 4, 2, 1)(torch.zeros(2, 3, 4))    # parameters on CPU: no CPU path
 
 
+def test_auto_precision_picks_the_path_per_batch_shape():
+    """precision="auto": batches the fp32-class tensor-core path takes run there, others on the exact FFMA path; both
+    within the reference tolerance of the oracle (logits <= 1e-4 rel)."""
+    pkg = _pkg()
+    B, T, F, H, L, C = 64, 12, 16, 128, 2, 3
+    torch.manual_seed(3)
+    ref = bo.OracleBiGRU(H, F, C, L, 50, 0.0, False, True).eval()
+    m = pkg.BiGRU(H, F, C, L, 50, 0.0, False, True, precision="auto")
+    m.load_state_dict(ref.state_dict())
+    m = m.cuda().eval()
+    for b in (B, B - 3):                                   # 64 -> bf16x3, 61 -> fp32
+        x = torch.randn(b, T, F, generator=torch.Generator().manual_seed(b))
+        with torch.no_grad():
+            want = ref(x)
+            got = m(x.cuda()).cpu()
+        assert m.resolved_precision(b) == ("bf16x3" if b % 32 == 0 else "fp32")
+        assert float((got - want).abs().max() / want.abs().max()) <= 1e-4
+
+
 def test_long_sequence_config_reduced():
     """BASELINE config 4 (B256,T1024,F128,H512,L2) at reduced batch/length: H=512 runs on the fp32 path (the
     tensor-core path covers H in {128, 256} and must refuse loudly); logits <= 1e-4 rel of the torch.nn.GRU CPU path."""

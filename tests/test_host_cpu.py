@@ -85,6 +85,13 @@ def test_model_surface_and_state_dict(pkg, golden_dir):
     assert mine.can_fuse_step()
     mine.add_loss_fn(nn.CrossEntropyLoss(label_smoothing=0.1))
     assert not mine.can_fuse_step()
+    # precision="auto": the fp32-class tensor-core path for every batch shape it takes, the exact FFMA path otherwise
+    auto = pkg.BiGRU(256, 64, 3, 2, precision="auto")
+    assert auto.resolved_precision(512) == "bf16x3" and auto.resolved_precision(500) == "fp32"
+    assert pkg.BiGRU(8, 108, 4, 1, precision="auto").resolved_precision(64) == "fp32"
+    assert pkg.BiGRU(256, 64, 3, 2, precision="bf16").resolved_precision(7) == "bf16"
+    with pytest.raises(ValueError):
+        pkg.BiGRU(8, 4, 2, 1, precision="fp64")
 
 
 def test_chunk_loader_host_logic(pkg, golden_dir, tmp_path):
