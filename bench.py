@@ -159,7 +159,7 @@ def run_reference(args):
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 CONFIG_OF = {"bf16x3": "configs[1] (fused-gate tensor-core kernels at fp32 tolerance: split bf16x3 operands, fp32 accumulate)",
@@ -500,10 +500,26 @@ def main():
                 "config": workload_config(world, precision), "clocks": head.get("clocks"), "e2e": head.get("e2e"),
                 "gpu_launches": head["gpu_launches"], "roofline": head.get("roofline"), "cpu_baseline": cpu,
                 "e2e_windows": e2e_windows, "variants": variants, "parity": parity, "cudnn_comparator": cudnn}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(obj):
+    """The ONE JSON line goes to the process's real stdout; everything libraries print meanwhile (NCCL's version banner
+    lands on fd 1) was redirected to stderr by _guard_stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+def _guard_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
+    _guard_stdout()
     main()
