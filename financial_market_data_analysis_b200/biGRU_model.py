@@ -111,12 +111,27 @@ class _BiGRUFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, x, h0, *params):
         lib = _lib.load()
-        plan = model._plan_for(x)
         B = x.shape[0]
+        Bp = model._padded_batch(B)
+        if Bp != B:                                       # whole batch tiles on the tensor-core paths: zero rows appended
+            xp = x.new_zeros((Bp,) + tuple(x.shape[1:]))
+            xp[:B] = x
+            x = xp
+            if h0 is not None:
+                hp = h0.new_zeros(h0.shape[0], Bp, h0.shape[2])
+                hp[:, :B] = h0
+                h0 = hp
+        plan = model._plan_for(x)
         ctx.dev_guard = torch.cuda.device(x.device)      # the C ABI launches on the CURRENT device: make it the model's
         ctx.dev_guard.__enter__()
         try:
-            return _BiGRUFunction._forward(ctx, lib, plan, model, x, h0, B)
+            out = _BiGRUFunction._forward(ctx, lib, plan, model, x, h0, Bp)
+            ctx.real_batch = B
+            model._last_batch = B
+            if Bp != B:
+                model._last_hidden = model._last_hidden[:, :B]
+                out = out[:B]
+            return out
         finally:
             ctx.dev_guard.__exit__(None, None, None)
 
@@ -150,6 +165,11 @@ class _BiGRUFunction(torch.autograd.Function):
         x, h0 = ctx.saved_tensors
         h0 = h0 if ctx.has_h0 else None
         dlogits = dlogits.contiguous().float()
+        B, Bp = ctx.real_batch, x.shape[0]
+        if Bp != B:                                       # padded rows: zero upstream gradient
+            dl = dlogits.new_zeros(Bp, dlogits.shape[1])
+            dl[:B] = dlogits
+            dlogits = dl
         grads = torch.empty_like(model._flat)
         dx = torch.empty_like(x) if ctx.needs_input_grad[1] else None
         dh0 = torch.empty_like(h0) if (h0 is not None and ctx.needs_input_grad[2]) else None
@@ -160,6 +180,9 @@ class _BiGRUFunction(torch.autograd.Function):
                                           _lib.ptr(grads), _lib.ptr(dx), _lib.ptr(dh0), _stream_ptr(x.device)), "bigru_backward")
         plan.release_stash(ctx.stash)
         ctx.stash = None
+        if Bp != B:
+            dx = dx[:B] if dx is not None else None
+            dh0 = dh0[:, :B] if dh0 is not None else None
         pg = tuple(grads[o:o + n].view(shape) for (o, n, shape) in model._views)
         return (None, dx, dh0) + pg
 
@@ -172,7 +195,8 @@ class BiGRU(nn.Module):
     Extra keyword ``precision``:
       "fp32"    FFMA kernels, exact transcendental functions; any shape (the exact path),
       "bf16x3"  fp32-class on tcgen05 tensor cores (every operand a (hi, lo) bf16 pair, fp32 accumulation / state /
-                gradients): meets the reference's 1e-4 logits tolerance; H in {128, 256}, batch % 32 == 0, features % 8 == 0,
+                gradients): meets the reference's 1e-4 logits tolerance; H in {128, 256} (other batch sizes than whole 32-row tiles
+                run zero-padded, any feature count),
       "bf16"    single bf16 operands on tcgen05, fp32 accumulation and state (fastest, ~3e-3 on logits),
       "auto"    "bf16x3" for every batch shape it takes, "fp32" otherwise (decided per batch shape).
     Default: $BIGRU_B200_PRECISION or "fp32".
@@ -271,12 +295,19 @@ class BiGRU(nn.Module):
         return self._flat
 
     # ------------------------------------------------------------------ plans
-    def resolved_precision(self, batch: int) -> str:
-        """The precision a batch of this size runs at ("auto": the fp32-class tensor-core path wherever it applies)."""
+    def resolved_precision(self, batch: int = 0) -> str:
+        """The precision a batch runs at ("auto": the fp32-class tensor-core path wherever it applies)."""
         if self.precision != "auto":
             return self.precision
-        ok = self.hidden_size in (128, 256) and batch % 32 == 0 and self.n_features % 8 == 0
+        ok = self.hidden_size in (128, 256)
         return "bf16x3" if ok else "fp32"
+
+    def _padded_batch(self, batch: int) -> int:
+        """The tensor-core paths work on whole batch tiles (32 rows at bf16x3, 16 at bf16): other batch sizes run zero-padded
+        to the next multiple.  Batch rows are independent and the padded rows receive a zero upstream gradient, so logits,
+        loss and every gradient of the real rows are unchanged."""
+        mult = {"bf16x3": 32, "bf16": 16}.get(self.resolved_precision(batch), 1)
+        return (batch + mult - 1) // mult * mult
 
     def _plan_for(self, x) -> _Plan:
         key = (int(x.shape[0]), int(x.shape[1]), self.resolved_precision(int(x.shape[0])), x.device.index)
@@ -311,7 +342,7 @@ class BiGRU(nn.Module):
         off = _lib.C.c_size_t()
         _lib.check(_lib.load().bigru_stash_argmax_offset(plan.handle, _lib.C.byref(off)), "bigru_stash_argmax_offset")
         n = plan.B * self.hidden_size * 4
-        return stash[off.value:off.value + n].view(torch.int32).view(plan.B, self.hidden_size).clone()
+        return stash[off.value:off.value + n].view(torch.int32).view(plan.B, self.hidden_size)[:getattr(self, "_last_batch", plan.B)].clone()
 
     # ------------------------------------------------------------------ reference surface
     def forward(self, input_seq, hidden=None):
@@ -401,7 +432,8 @@ class BiGRU(nn.Module):
         return st
 
     def _launch_fwd_loss_bwd(self, lib, plan, x, h0, tgt, kind, wv, pwv, denom, logits, dlogits, stash, args, st, s):
-        B, C = logits.shape
+        # the loss sees the REAL batch rows (tgt's); logits / dlogits may carry zero-padded rows behind them (whole batch tiles)
+        B, C = tgt.shape[0], logits.shape[1]
         _lib.check(lib.bigru_forward(plan.handle, _lib.ptr(self._flat), _lib.ptr(x), _lib.ptr(h0), *args,
                                      _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(logits), None, s), "bigru_forward")
         _lib.check(lib.bigru_loss(kind, _lib.ptr(logits), _lib.ptr(tgt), _lib.ptr(wv), _lib.ptr(pwv), B, C, denom,
@@ -433,9 +465,9 @@ class BiGRU(nn.Module):
         dev = x.device
         plan = self._plan_for(x)
         st = self._fused_state(dev)
-        B, C = x.shape[0], self.output_size
-        ent = {"x": torch.empty_like(x), "tgt": torch.empty_like(tgt), "logits": torch.empty(B, C, device=dev, dtype=torch.float32),
-               "dlogits": torch.empty(B, C, device=dev, dtype=torch.float32), "stash": plan.acquire_stash(), "plan": plan}
+        B, C = x.shape[0], self.output_size               # x arrives padded to whole batch tiles; tgt has the real rows
+        ent = {"x": torch.zeros_like(x), "tgt": torch.empty_like(tgt), "logits": torch.empty(B, C, device=dev, dtype=torch.float32),
+               "dlogits": torch.zeros(B, C, device=dev, dtype=torch.float32), "stash": plan.acquire_stash(), "plan": plan}
         args = (float(self.dropout_p), int(bool(self.spatial_dropout)), 0, 0)
         ent["x"].copy_(x); ent["tgt"].copy_(tgt)
         # one eager pass on the static buffers first (first-use work such as shared-memory opt-ins happens outside the capture);
@@ -492,14 +524,30 @@ class BiGRU(nn.Module):
                 raise ValueError(f"target must be [{B}, {C}]")
             denom = float(B * C * self._dp_world)
         training = bool(self.training and self.dropout_p > 0)
+        Bp = self._padded_batch(B)
         with torch.cuda.device(dev):
             wv, pwv = self._loss_vec(w, C), self._loss_vec(pw, C)
             st = self._fused_state(dev)
+            x_real = x
+
+            def padded(x, h0):                                # whole batch tiles on the tensor-core paths (see _padded_batch)
+                if Bp == B:
+                    return x, h0
+                xp = x.new_zeros(Bp, x.shape[1], x.shape[2])
+                xp[:B] = x
+                if h0 is not None:
+                    hp = h0.new_zeros(h0.shape[0], Bp, h0.shape[2])
+                    hp[:, :B] = h0
+                    h0 = hp
+                return xp, h0
+            self._last_batch = B
             if self.use_cuda_graph and not training and h0 is None and not torch.cuda.is_current_stream_capturing():
                 key = (B, int(x.shape[1]), self.precision, kind, id(wv), id(pwv), denom, float(g["lr"]), tuple(g["betas"]),
                        float(g["eps"]), float(self.clip), self._dp_world, dev.index)
                 try:
-                    ent = self._graph_for(key, x, tgt, kind, wv, pwv, denom, g)
+                    ent = self._graphs.get(key)
+                    if ent is None:
+                        ent = self._graph_for(key, padded(x, None)[0], tgt, kind, wv, pwv, denom, g)
                 except Exception as e:                        # capture is an optimisation: fall back to plain launches
                     import warnings
                     warnings.warn(f"BiGRU.train_step: CUDA-graph capture failed ({e}); using plain launches")
@@ -507,8 +555,8 @@ class BiGRU(nn.Module):
                     ent = None
                 if ent is not None:
                     if ent.pop("fresh", False):               # the warm-up pass inside _graph_for WAS this step
-                        return st["loss"].clone(), ent["logits"].clone()
-                    ent["x"].copy_(x, non_blocking=True)
+                        return st["loss"].clone(), ent["logits"][:B].clone()
+                    ent["x"][:B].copy_(x_real, non_blocking=True)      # rows >= B of the static buffer stay zero
                     ent["tgt"].copy_(tgt, non_blocking=True)
                     ent["ga"].replay()
                     if ent["gb"] is not None:
@@ -516,10 +564,11 @@ class BiGRU(nn.Module):
                         ent["gb"].replay()
                     st["step"] += 1
                     lib.bigru_launch_count_add(ent["launches"])
-                    return st["loss"].clone(), ent["logits"].clone()
+                    return st["loss"].clone(), ent["logits"][:B].clone()
+            x, h0 = padded(x, h0)
             plan = self._plan_for(x)
-            logits = torch.empty(B, C, device=dev, dtype=torch.float32)
-            dlogits = torch.empty_like(logits)
+            logits = torch.empty(Bp, C, device=dev, dtype=torch.float32)
+            dlogits = torch.zeros_like(logits) if Bp != B else torch.empty_like(logits)
             stash = plan.acquire_stash()
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
             self._last_seed = seed
@@ -530,7 +579,7 @@ class BiGRU(nn.Module):
             if self._dp_world > 1:
                 allreduce_flat_(st["gext"], self._dp_group)          # ONE all-reduce: shard gradients of the global-mean loss + the loss
             self._launch_update(lib, g, st, s)
-            return st["loss"].clone(), logits
+            return st["loss"].clone(), (logits[:B] if Bp != B else logits)
 
     # ------------------------------------------------------------------ zero-copy windows
     def _window_args(self, dataset, start, count):
@@ -548,6 +597,9 @@ class BiGRU(nn.Module):
             self._flatten()
         lib = _lib.load()
         self._window_args(dataset, start, count)
+        if self._padded_batch(count) != count:                # not whole batch tiles: collate on the device, then the padded path
+            self._win_ctx = None
+            return self.forward(dataset.collate(start, count)[0])
         plan = self._plan_for(torch.empty(count, dataset.window, 0, device=self._flat.device))     # keyed by (B, T)
         logits = torch.empty(count, self.output_size, device=self._flat.device, dtype=torch.float32)
         stash = plan.acquire_stash()
@@ -569,6 +621,11 @@ class BiGRU(nn.Module):
             raise RuntimeError("train_step_windows needs a fusable loss and torch.optim.Adam (see train_step)")
         lib = _lib.load()
         kind, w, pw = spec
+        if self._padded_batch(count) != count:                # not whole batch tiles: collate on the device, then train_step
+            self._window_args(dataset, start, count)
+            x, y = dataset.collate(start, count)
+            tgt = y.reshape(count, -1)[:, 0].to(torch.int64) if kind == _lib.LOSS_CE else y.reshape(count, self.output_size)
+            return self.train_step(x, tgt)
         logits = self.forward_windows(dataset, start, count)
         plan, stash, training, seed = self._win_ctx
         dev, B, C = logits.device, count, self.output_size

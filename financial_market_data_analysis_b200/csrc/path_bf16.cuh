@@ -15,9 +15,9 @@
 typedef __nv_bfloat16 bf16_t;
 
 static int bf16_plan_check(const bigru_plan& p) {
-    if ((p.H != 128 && p.H != 256) || p.B % 16 != 0 || p.F % 8 != 0) {
-        bigru_set_error("BIGRU_PREC_BF16 supports hidden_size 128 or 256, batch %% 16 == 0, n_features %% 8 == 0 "
-                        "(got H=%d B=%d F=%d); use BIGRU_PREC_FP32 for other shapes", p.H, p.B, p.F);
+    if ((p.H != 128 && p.H != 256) || p.B % 16 != 0) {
+        bigru_set_error("BIGRU_PREC_BF16 supports hidden_size 128 or 256 and batch %% 16 == 0 (got H=%d B=%d; the Python mirror pads "
+                        "other batch sizes with zero rows); use BIGRU_PREC_FP32 for other shapes", p.H, p.B);
         return BIGRU_ERR_UNSUPPORTED;
     }
     return BIGRU_OK;
@@ -30,17 +30,20 @@ struct Bf16Layout {            // byte offsets, 1024-aligned
     size_t gi, dghn, dYa, dYb, dcat, dhinit, scratch_total;
 };
 static inline size_t al(size_t x) { return (x + 1023) & ~(size_t)1023; }
+// Layer-0 operands (X rows and W_ih rows) are stored with their K extent (n_features) padded to a multiple of 8 with zeros: a
+// TMA row pitch must be a multiple of 16 bytes.  The padding never leaves the packed images (gradients keep n_features columns).
+static inline int pad8(int64_t v) { return (int)((v + 7) & ~(int64_t)7); }
 static Bf16Layout bf16_layout(const bigru_plan& p) {
     Bf16Layout L{};
     const size_t R = (size_t)p.B * p.T, DH = (size_t)p.D * p.H, H = p.H, D = p.D;
     size_t o = 0;
     for (int l = 0; l < p.L; ++l) {
-        const size_t I = p.in_size(l);
+        const size_t I = p.in_size(l), Ip = (size_t)pad8((int64_t)I);
         L.Yrow[l] = o; o = al(o + R * DH * 2);
         L.YB[l] = o; o = al(o + R * DH * 2);
         L.G[l] = o; o = al(o + R * D * 4 * H * 2);
-        L.Xrow[l] = o; o = al(o + R * I * 2);
-        L.Wih[l] = o; o = al(o + D * 3 * H * I * 2);
+        L.Xrow[l] = o; o = al(o + R * Ip * 2);
+        L.Wih[l] = o; o = al(o + D * 3 * H * Ip * 2);
         L.WihT[l] = o; o = al(o + D * 3 * H * I * 2);
         L.Wimg[l] = o; o = al(o + D * 3 * H * H * 2);
         L.WTimg[l] = o; o = al(o + D * 3 * H * H * 2);
@@ -124,6 +127,34 @@ __global__ void cast_x_kernel(const float* __restrict__ x, WindowSrc w, bf16_t* 
     }
 }
 
+// the same for n_features % 8 != 0: element-wise, rows written with the padded pitch Fp = pad8(F) (zero columns behind F)
+__global__ void cast_x_pad_kernel(const float* __restrict__ x, WindowSrc w, bf16_t* __restrict__ Xrow, bf16_t* __restrict__ Xlo, int B, int T, int F,
+                                  int Fp, float pdrop, int spatial, uint64_t seed) {
+    const float scale = pdrop > 0.f ? 1.f / (1.f - pdrop) : 1.f;
+    const int64_t total = (int64_t)B * T * Fp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int f = (int)(i % Fp);
+        const int64_t r = i / Fp;
+        const int64_t b = r % B, t = r / B;
+        float v = 0.f;
+        if (f < F) {
+            if (w.src) {
+                v = w.src[(w.start + b + t) * F + f];
+                if (w.xmin) v = (v - w.xmin[f]) / (w.xmax[f] - w.xmin[f]);
+            } else {
+                v = x[(b * T + t) * F + f];
+            }
+            if (pdrop > 0.f) {
+                const uint64_t key = spatial ? (uint64_t)b * F + f : ((uint64_t)b * T + t) * F + f;
+                v = bigru_uniform(seed, 0u, key) < pdrop ? 0.f : v * scale;
+            }
+        }
+        const bf16_t h = __float2bfloat16(v);
+        Xrow[i] = h;
+        if (Xlo) Xlo[i] = __float2bfloat16(v - __bfloat162float(h));
+    }
+}
+
 // zero-copy windows: the chunk rows [start, start + rows) are normalised and cast ONCE ((B+T-1) x F
 // values instead of B*T*F); the kernels that consume the layer-0 input address them as windows (row b + t)
 __global__ void chunk_prep_kernel(WindowSrc w, bf16_t* __restrict__ hi, bf16_t* __restrict__ lo, int64_t rows, int F) {
@@ -140,7 +171,7 @@ __global__ void chunk_prep_kernel(WindowSrc w, bf16_t* __restrict__ hi, bf16_t* 
 // whether a windowed (never collated) layer-0 input is possible: no input dropout to apply, and every GEMM tile of 128
 // (64) logical rows stays inside one time step
 static inline bool windows_direct(const bigru_plan& p, bool have_windows, bool do_drop) {
-    return have_windows && !do_drop && p.B % 128 == 0;
+    return have_windows && !do_drop && p.B % 128 == 0 && p.F % 8 == 0;
 }
 
 // inter-layer dropout: Yrow -> Xrow (masked); rows x cols = R x DH
@@ -200,7 +231,7 @@ __global__ void pack_bias_kernel(const float* __restrict__ b_ih, const float* __
 
 // All weight packing of a forward call in ONE launch: blockIdx.y enumerates (layer, direction).
 struct PackJob { const float* w_ih; const float* w_hh; const float* b_ih; const float* b_hh;
-                 bf16_t* Wih; bf16_t* WihT; bf16_t* Wimg; bf16_t* WTimg; float* bfold; float* bhn; int I; int d; };
+                 bf16_t* Wih; bf16_t* WihT; bf16_t* Wimg; bf16_t* WTimg; float* bfold; float* bhn; int I; int d; };   // Wih rows hold pad8(I) columns
 struct PackJobs { PackJob j[32]; };
 // dst_rm[r][c] = dst_t[c][r] = bf16(src[r][c]) for a [rows][cols] fp32 matrix (cols % 32 == 0, rows % 32 == 0): 32 x 32 tiles
 // through shared memory so that the row-major AND the transposed image are both written coalesced.  ld_rm / ld_t are the
@@ -231,12 +262,13 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackJobs jobs, int 
         // W_ih [3H][I] -> rows d*3H.. of Wih [D*3H][I] and columns d*3H.. of WihT [I][D*3H]
         pack_tile_pair(J.w_ih, H3, I, J.Wih + (int64_t)d * H3 * I, I, J.WihT + (int64_t)d * H3, (int64_t)D * H3, blockIdx.x, gridDim.x, tile);
     } else {
-        const int64_t n_ih = (int64_t)H3 * I;
+        const int Ip = (I + 7) & ~7;                           // zero columns up to the padded row pitch
+        const int64_t n_ih = (int64_t)H3 * Ip;
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ih; i += (int64_t)gridDim.x * blockDim.x) {
-            const int k = i % I, q = i / I;
-            const bf16_t v = __float2bfloat16(J.w_ih[i]);
-            J.Wih[((int64_t)d * H3 + q) * I + k] = v;
-            J.WihT[(int64_t)k * D * H3 + (int64_t)d * H3 + q] = v;
+            const int k = i % Ip, q = i / Ip;
+            const bf16_t v = __float2bfloat16(k < I ? J.w_ih[(int64_t)q * I + k] : 0.f);
+            J.Wih[((int64_t)d * H3 + q) * Ip + k] = v;
+            if (k < I) J.WihT[(int64_t)k * D * H3 + (int64_t)d * H3 + q] = v;
         }
     }
     // W_hh [3H][H]: gate g of unit u -> Wimg [unit][g][H] (row g*H+u of W_hh is row u*3+g of the image) and W_hh^T
@@ -442,9 +474,12 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
     const bool direct = windows_direct(p, win.src != nullptr, do_drop);
     if (direct)
         KLAUNCH(KC_PACK, 0.0, 6.0 * (B + T - 1) * F, st, chunk_prep_kernel<<<148, 256, 0, st>>>(win, (bf16_t*)(S + L.Xrow[0]), nullptr, (int64_t)B + T - 1, F));
-    else
+    else if (F % 8 == 0)
         KLAUNCH(KC_PACK, 0.0, 6.0 * R * F, st, cast_x_kernel<<<148 * 8, 256, 0, st>>>(x, win, (bf16_t*)(S + L.Xrow[0]), nullptr, B, T, F,
                                                                                        do_drop ? drop : 0.f, spatial, seed));
+    else
+        KLAUNCH(KC_PACK, 0.0, 6.0 * R * F, st, cast_x_pad_kernel<<<148 * 8, 256, 0, st>>>(x, win, (bf16_t*)(S + L.Xrow[0]), nullptr, B, T, F, pad8(F),
+                                                                                           do_drop ? drop : 0.f, spatial, seed));
     for (int l = 0; l < p.L; ++l) {
         const int I = (int)p.in_size(l);
         const bf16_t* Xrow = (const bf16_t*)(S + L.Xrow[l]);
@@ -463,12 +498,13 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
         const bool fuse_x = (I == 64);
         if (!fuse_x) {
             tcg::Params g{};
-            g.M = D * 3 * H; g.N = (int)R; g.K = I; g.batch = 1; g.splitk = 1; g.mode = tcg::OUT_SCAN_BF16;
+            const int Ip = pad8(I);                                                     // zero-padded K extent (layer 0, n_features % 8 != 0)
+            g.M = D * 3 * H; g.N = (int)R; g.K = Ip; g.batch = 1; g.splitk = 1; g.mode = tcg::OUT_SCAN_BF16;
             g.blk = tcg::ScanBlk{T, B, H, 3}; g.m_fast = 1;      // the few weight m-tiles share each activation tile via L2
             g.C = W + L.gi; g.ldc = R; g.bias = (const float*)(S + L.bfold[l]); g.bias_per_row = 1; g.dbg = dbg;
             const bool wnd = direct && l == 0;
             g.b_win = wnd ? B : 0;
-            TRY(tc_gemm(S + L.Wih[l], D * 3 * H, I, Xrow, wnd ? (int64_t)B + T - 1 : R, I, g, st));
+            TRY(tc_gemm(S + L.Wih[l], D * 3 * H, Ip, Xrow, wnd ? (int64_t)B + T - 1 : R, Ip, g, st));
         }
         // 4. recurrence
         tcs::FwdParams f{};
@@ -545,7 +581,7 @@ static int backward_bf16(const bigru_plan& p, const float* params, const float* 
             g.dbg = dbg;
             g.b_win = (l == 0 && windows_direct(p, x == nullptr, do_drop)) ? B : 0;      // forward_windows left only the chunk in the stash
             g.b_win_rows = B + T - 1;
-            TRY(tc_gemm(W + L.gi, (int64_t)D * 3 * H, (int64_t)D * 3 * H, Xin, I, I, g, st, KC_TC_GEMM_DWIH));
+            TRY(tc_gemm(W + L.gi, (int64_t)D * 3 * H, (int64_t)D * 3 * H, Xin, I, pad8(I), g, st, KC_TC_GEMM_DWIH));   // I columns, padded row pitch
         }
         // 3. dW_hh[d] = dgh[d]^T H_prev  with H_prev(t) = Y(t-1) (dir 0) / Y(t+1) (dir 1): a shift of -+B ROWS of the
         //    time-major output; rows outside [0, R) read as zero through TMA (h_prev = 0 at the first step).

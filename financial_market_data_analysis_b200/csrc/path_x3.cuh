@@ -11,9 +11,9 @@
 #include <cstdlib>
 
 static int x3_plan_check(const bigru_plan& p) {
-    if ((p.H != 128 && p.H != 256) || p.B % 32 != 0 || p.F % 8 != 0) {
-        bigru_set_error("BIGRU_PREC_BF16X3 supports hidden_size 128 or 256, batch %% 32 == 0, n_features %% 8 == 0 "
-                        "(got H=%d B=%d F=%d); use BIGRU_PREC_FP32 for other shapes", p.H, p.B, p.F);
+    if ((p.H != 128 && p.H != 256) || p.B % 32 != 0) {
+        bigru_set_error("BIGRU_PREC_BF16X3 supports hidden_size 128 or 256 and batch %% 32 == 0 (got H=%d B=%d; the Python mirror pads "
+                        "other batch sizes with zero rows); use BIGRU_PREC_FP32 for other shapes", p.H, p.B);
         return BIGRU_ERR_UNSUPPORTED;
     }
     return BIGRU_OK;
@@ -30,15 +30,15 @@ static X3Layout x3_layout(const bigru_plan& p) {
     const size_t R = (size_t)p.B * p.T, DH = (size_t)p.D * p.H, H = p.H, D = p.D;
     size_t o = 0;
     for (int l = 0; l < p.L; ++l) {
-        const size_t I = p.in_size(l);
+        const size_t I = p.in_size(l), Ip = (size_t)pad8((int64_t)I);      // layer-0 K extent padded to 8 (see path_bf16.cuh)
         L.Yhi[l] = o; o = al(o + R * DH * 2);
         L.Ylo[l] = o; o = al(o + R * DH * 2);
         L.YB[l] = o; o = al(o + R * DH * 4);
         L.G[l] = o; o = al(o + R * D * 4 * H * 4);
-        L.Xhi[l] = o; o = al(o + R * I * 2);
-        L.Xlo[l] = o; o = al(o + R * I * 2);
-        L.Wih_hi[l] = o; o = al(o + D * 3 * H * I * 2);
-        L.Wih_lo[l] = o; o = al(o + D * 3 * H * I * 2);
+        L.Xhi[l] = o; o = al(o + R * Ip * 2);
+        L.Xlo[l] = o; o = al(o + R * Ip * 2);
+        L.Wih_hi[l] = o; o = al(o + D * 3 * H * Ip * 2);
+        L.Wih_lo[l] = o; o = al(o + D * 3 * H * Ip * 2);
         L.WihT_hi[l] = o; o = al(o + D * 3 * H * I * 2);
         L.WihT_lo[l] = o; o = al(o + D * 3 * H * I * 2);
         L.Wimg[l] = o; o = al(o + D * 2 * 3 * H * H * 2);        // stacked hi | lo rows
@@ -145,13 +145,15 @@ __global__ void __launch_bounds__(256) x3_pack_all_kernel(const X3PackJobs jobs,
             __syncthreads();
         }
     } else {
-        const int64_t n_ih = (int64_t)H3 * I;
+        const int Ip = (I + 7) & ~7;                           // zero columns up to the padded row pitch
+        const int64_t n_ih = (int64_t)H3 * Ip;
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ih; i += (int64_t)gridDim.x * blockDim.x) {
-            const int k = i % I, q = i / I;
+            const int k = i % Ip, q = i / Ip;
             bf16_t hi, lo;
-            x3_split(J.w_ih[i], hi, lo);
-            const int64_t o1 = ((int64_t)d * H3 + q) * I + k, o2 = (int64_t)k * D * H3 + (int64_t)d * H3 + q;
-            J.Wih_hi[o1] = hi; J.Wih_lo[o1] = lo; J.WihT_hi[o2] = hi; J.WihT_lo[o2] = lo;
+            x3_split(k < I ? J.w_ih[(int64_t)q * I + k] : 0.f, hi, lo);
+            const int64_t o1 = ((int64_t)d * H3 + q) * Ip + k, o2 = (int64_t)k * D * H3 + (int64_t)d * H3 + q;
+            J.Wih_hi[o1] = hi; J.Wih_lo[o1] = lo;
+            if (k < I) { J.WihT_hi[o2] = hi; J.WihT_lo[o2] = lo; }
         }
     }
     // W_hh -> the forward (stacked hi | lo rows) and backward (own-gate rows x all k) tensor-memory images of tc_scan_x.cuh
@@ -241,9 +243,12 @@ static int forward_x3(const bigru_plan& p, const float* params, const float* x, 
     if (direct)
         KLAUNCH(KC_PACK, 0.0, 8.0 * (B + T - 1) * F, st, chunk_prep_kernel<<<148, 256, 0, st>>>(win, (bf16_t*)(S + L.Xhi[0]), (bf16_t*)(S + L.Xlo[0]),
                                                                                                  (int64_t)B + T - 1, F));
-    else
+    else if (F % 8 == 0)
         KLAUNCH(KC_PACK, 0.0, 8.0 * R * F, st, cast_x_kernel<<<148 * 8, 256, 0, st>>>(x, win, (bf16_t*)(S + L.Xhi[0]), (bf16_t*)(S + L.Xlo[0]), B, T, F,
                                                                                        do_drop ? drop : 0.f, spatial, seed));
+    else
+        KLAUNCH(KC_PACK, 0.0, 8.0 * R * F, st, cast_x_pad_kernel<<<148 * 8, 256, 0, st>>>(x, win, (bf16_t*)(S + L.Xhi[0]), (bf16_t*)(S + L.Xlo[0]), B, T, F,
+                                                                                           pad8(F), do_drop ? drop : 0.f, spatial, seed));
     for (int l = 0; l < p.L; ++l) {
         const int I = (int)p.in_size(l);
         const bf16_t* Xhi = (const bf16_t*)(S + L.Xhi[l]);
@@ -259,12 +264,13 @@ static int forward_x3(const bigru_plan& p, const float* params, const float* x, 
         }
         {   // input projection for all t, both directions: W_ih X^T + bias(row) in the scan kernel's blocked fp32 layout
             tcg::Params g{};
-            g.M = D * 3 * H; g.N = (int)R; g.K = I; g.batch = 1; g.splitk = 1; g.mode = tcg::OUT_SCAN_F32;
+            const int Ip = pad8(I);                                                     // zero-padded K extent (layer 0, n_features % 8 != 0)
+            g.M = D * 3 * H; g.N = (int)R; g.K = Ip; g.batch = 1; g.splitk = 1; g.mode = tcg::OUT_SCAN_F32;
             g.blk = tcg::ScanBlk{T, B, H, 3, 64, 32}; g.m_fast = 1;
             g.C = W + L.gi; g.ldc = R; g.bias = (const float*)(S + L.bfold[l]); g.bias_per_row = 1; g.dbg = dbg;
             const bool wnd = direct && l == 0;
             g.b_win = wnd ? B : 0;
-            TRY(tc_gemm(S + L.Wih_hi[l], D * 3 * H, I, Xhi, wnd ? (int64_t)B + T - 1 : R, I, g, st, KC_TC_GEMM, S + L.Wih_lo[l], Xlo));
+            TRY(tc_gemm(S + L.Wih_hi[l], D * 3 * H, Ip, Xhi, wnd ? (int64_t)B + T - 1 : R, Ip, g, st, KC_TC_GEMM, S + L.Wih_lo[l], Xlo));
         }
         if (h0) {   // recurrent product of the initial state, exact fp32 (tiny: B x 3H x H per direction); the scan starts at step 1
             GemmArgs r = gemm_args(h0 + (int64_t)l * D * B * H, params + p.off_whh(l, 0), (float*)(W + L.gh0), B, 3 * H, H, H, 1, H, 1, 3 * H);
@@ -349,7 +355,7 @@ static int backward_x3(const bigru_plan& p, const float* params, const float* x,
             g.dbg = dbg;
             g.b_win = (l == 0 && windows_direct(p, x == nullptr, do_drop)) ? B : 0;      // forward_windows left only the chunk in the stash
             g.b_win_rows = B + T - 1;
-            TRY(tc_gemm(dgi_hi, (int64_t)D * 3 * H, (int64_t)D * 3 * H, Xin_hi, I, I, g, st, KC_TC_GEMM_DWIH, dgi_lo, Xin_lo));
+            TRY(tc_gemm(dgi_hi, (int64_t)D * 3 * H, (int64_t)D * 3 * H, Xin_hi, I, pad8(I), g, st, KC_TC_GEMM_DWIH, dgi_lo, Xin_lo));   // I columns, padded pitch
         }
         for (int part = 0; part < 2; ++part) {   // dW_hh[d] = dgh[d]^T H_prev (time-shifted Y, see path_bf16.cuh)
             tcg::Params g{};

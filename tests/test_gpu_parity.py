@@ -46,13 +46,13 @@ def precisions():
 
 
 def supported(precision, B, F, H, h0=False):
-    """BIGRU_PREC_BF16 covers H in {128, 256}, B % 16 == 0, F % 8 == 0, no initial hidden state;
-    BIGRU_PREC_BF16X3 covers H in {128, 256}, B % 32 == 0, F % 8 == 0, with or without an initial hidden state."""
+    """Through the Python mirror the tensor-core paths take any batch size (zero-padded to whole batch tiles) and any feature
+    count (layer-0 K extent padded to 8 inside the plan) for H in {128, 256}; BIGRU_PREC_BF16 has no initial hidden state."""
     if precision == "fp32":
         return True
     if precision == "bf16x3":
-        return H in (128, 256) and B % 32 == 0 and F % 8 == 0
-    return H in (128, 256) and B % 16 == 0 and F % 8 == 0 and not h0
+        return H in (128, 256)
+    return H in (128, 256) and not h0
 
 
 def rel(a, b):
@@ -186,6 +186,9 @@ SWEEP = [  # B, T, F, H, L, C, bidir, h0
     (32, 6, 16, 128, 2, 3, True, True),       # initial hidden state on the x3 tensor-core path (2-CTA clusters)
     (64, 11, 24, 256, 2, 4, True, True),      # ... and with 4-CTA clusters, two batch tiles
     (96, 3, 8, 256, 1, 2, False, False),
+    (19, 6, 13, 128, 2, 3, True, True),       # batch not a whole tile (zero-padded rows), n_features % 8 != 0 (padded K extent), h0
+    (40, 5, 108, 256, 1, 4, True, False),     # the reference's own feature count (108) at a tensor-core hidden size
+    (3, 4, 5, 128, 2, 2, False, False),
 ]
 
 
@@ -477,23 +480,46 @@ def test_error_conventions():
         pkg.BiGRU(8, 4, 2, 1)(torch.zeros(2, 3, 4))    # parameters on CPU: no CPU path
 
 
-def test_auto_precision_picks_the_path_per_batch_shape():
-    """precision="auto": batches the fp32-class tensor-core path takes run there, others on the exact FFMA path; both
-    within the reference tolerance of the oracle (logits <= 1e-4 rel)."""
+def test_auto_precision_and_batch_padding():
+    """precision="auto" runs the fp32-class tensor-core path for H in {128, 256}; batch sizes that are not whole batch tiles
+    run zero-padded (the padded rows get a zero upstream gradient).  Logits, loss, input gradient and every parameter gradient
+    of an odd batch must match the oracle like a whole-tile batch does; the fused train step (plain and CUDA graph) too."""
     pkg = _pkg()
-    B, T, F, H, L, C = 64, 12, 16, 128, 2, 3
-    torch.manual_seed(3)
-    ref = bo.OracleBiGRU(H, F, C, L, 50, 0.0, False, True).eval()
-    m = pkg.BiGRU(H, F, C, L, 50, 0.0, False, True, precision="auto")
-    m.load_state_dict(ref.state_dict())
-    m = m.cuda().eval()
-    for b in (B, B - 3):                                   # 64 -> bf16x3, 61 -> fp32
-        x = torch.randn(b, T, F, generator=torch.Generator().manual_seed(b))
+    T, F, H, L, C = 12, 16, 128, 2, 3
+    for prec, b in (("auto", 64), ("auto", 61), ("bf16", 19), ("auto", 1)):
+        torch.manual_seed(3)
+        ref = bo.OracleBiGRU(H, F, C, L, 50, 0.0, False, True)
+        m = pkg.BiGRU(H, F, C, L, 50, 0.0, False, True, precision=prec)
+        m.load_state_dict(ref.state_dict())
+        m = m.cuda()
+        tol_l, tol_g = ((1e-4, 1e-3) if prec == "auto" else (3e-2, 6e-2))
+        assert m.resolved_precision(b) == ("bf16x3" if prec == "auto" else "bf16")
+        g = torch.Generator().manual_seed(b)
+        x = torch.randn(b, T, F, generator=g)
+        y = torch.randint(0, C, (b,), generator=g)
+        xr = x.clone().requires_grad_(True)
+        lr_ = nn.functional.cross_entropy(ref(xr), y)
+        lr_.backward()
+        xg = x.cuda().requires_grad_(True)
+        out = m(xg)
+        assert out.shape == (b, C)
+        lg = nn.functional.cross_entropy(out, y.cuda())
+        lg.backward()
         with torch.no_grad():
             want = ref(x)
-            got = m(x.cuda()).cpu()
-        assert m.resolved_precision(b) == ("bf16x3" if b % 32 == 0 else "fp32")
-        assert float((got - want).abs().max() / want.abs().max()) <= 1e-4
+        assert float((out.detach().cpu() - want).abs().max() / want.abs().max()) <= tol_l
+        assert abs(float(lg.detach()) - float(lr_.detach())) <= tol_l * max(1.0, abs(float(lr_.detach())))
+        assert rel_l2(xg.grad.cpu().numpy(), xr.grad.numpy()) <= tol_g
+        for (k, p_ref), (_, p_gpu) in zip(ref.named_parameters(), m.named_parameters()):
+            assert rel_l2(p_gpu.grad.cpu().numpy(), p_ref.grad.numpy()) <= tol_g * 3, k
+        assert m.pooled_argmax().shape == (b, H)
+        # fused step on the odd batch: loss and logits of the real rows, plain launches and graph replay
+        m.add_loss_fn(nn.CrossEntropyLoss()); m.add_optimizer(torch.optim.Adam(m.parameters(), lr=1e-3))
+        for it in range(3):
+            loss, logits = m.train_step(x.cuda(), y.cuda())
+            assert logits.shape == (b, C) and bool(torch.isfinite(loss).all())
+            if it == 0:
+                assert abs(float(loss) - float(lr_.detach())) <= tol_l * max(1.0, abs(float(lr_.detach())))
 
 
 def test_long_sequence_config_reduced():

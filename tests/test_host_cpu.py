@@ -87,7 +87,11 @@ def test_model_surface_and_state_dict(pkg, golden_dir):
     assert not mine.can_fuse_step()
     # precision="auto": the fp32-class tensor-core path for every batch shape it takes, the exact FFMA path otherwise
     auto = pkg.BiGRU(256, 64, 3, 2, precision="auto")
-    assert auto.resolved_precision(512) == "bf16x3" and auto.resolved_precision(500) == "fp32"
+    assert auto.resolved_precision(512) == "bf16x3" and auto.resolved_precision(500) == "bf16x3"
+    assert auto._padded_batch(512) == 512 and auto._padded_batch(500) == 512 and auto._padded_batch(1) == 32
+    assert pkg.BiGRU(256, 64, 3, 2, precision="bf16")._padded_batch(500) == 512 - 0 and pkg.BiGRU(256, 64, 3, 2, precision="bf16")._padded_batch(17) == 32
+    assert pkg.BiGRU(256, 64, 3, 2, precision="fp32")._padded_batch(500) == 500
+    assert pkg.BiGRU(256, 108, 3, 2, precision="auto").resolved_precision(512) == "bf16x3"     # any feature count (padded K extent)
     assert pkg.BiGRU(8, 108, 4, 1, precision="auto").resolved_precision(64) == "fp32"
     assert pkg.BiGRU(256, 64, 3, 2, precision="bf16").resolved_precision(7) == "bf16"
     with pytest.raises(ValueError):
