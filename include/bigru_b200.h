@@ -37,10 +37,17 @@ extern "C" {
 #define BIGRU_ERR_DEVICE      -3   /* no sm_100-class device */
 #define BIGRU_ERR_UNSUPPORTED -4   /* shape not supported by the requested precision path */
 
-#define BIGRU_PREC_FP32 0          /* fp32 FFMA path: the parity reference (<=1e-4 rel on logits) */
-#define BIGRU_PREC_BF16 1          /* bf16 operands on tcgen05 tensor cores, fp32 accumulate/state */
+#define BIGRU_PREC_FP32 0          /* fp32 FFMA path: exact, any shape (<=1e-4 rel on logits) */
+#define BIGRU_PREC_BF16 1          /* bf16 operands on tcgen05 tensor cores, fp32 accumulate/state.
+                                      hidden_size 128 or 256, batch % 16 == 0, no initial hidden state */
 #define BIGRU_PREC_BF16X3 2        /* fp32-class on tensor cores: (hi, lo) bf16 operand pairs, 3-4 products per term,
-                                      fp32 accumulate / gate math / stash; meets the 1e-4 logit tolerance at tensor-core speed */
+                                      fp32 accumulate / gate math / stash; meets the 1e-4 logit tolerance at tensor-core speed.
+                                      hidden_size 128 or 256, batch % 32 == 0.
+                                      Both tensor-core paths take any n_features (the layer-0 operands are stored with the
+                                      feature extent zero-padded to a multiple of 8 inside the plan's workspaces).  Other
+                                      batch sizes: append zero rows to x (and zero rows to d_logits) up to the next multiple -
+                                      batch rows are independent; the Python mirror does exactly that.  Anything else returns
+                                      BIGRU_ERR_UNSUPPORTED. */
 
 #define BIGRU_LOSS_CE   0          /* torch.nn.CrossEntropyLoss (BASELINE.json configs) */
 #define BIGRU_LOSS_BCE  1          /* torch.nn.BCEWithLogitsLoss(weight,pos_weight) notebook raw :1192 */
