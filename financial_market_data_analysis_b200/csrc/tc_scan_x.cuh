@@ -79,6 +79,11 @@ __device__ __forceinline__ void tmem_ld_wait_pin(float (&a)[16], float (&b)[16],
 #pragma unroll
     for (int i = 0; i < 16; ++i) asm volatile("" : "+f"(a[i]), "+f"(b[i]), "+f"(c[i]));
 }
+__device__ __forceinline__ void tmem_ld_wait_pin(float (&a)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) asm volatile("" : "+f"(a[i]));
+}
 __device__ __forceinline__ void tmem_ld_wait_pin(float (&a)[16], float (&b)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
