@@ -197,7 +197,7 @@ class BiGRU(nn.Module):
       "bf16x3"  fp32-class on tcgen05 tensor cores (every operand a (hi, lo) bf16 pair, fp32 accumulation / state /
                 gradients): meets the reference's 1e-4 logits tolerance; H in {128, 256} (other batch sizes than whole 32-row tiles
                 run zero-padded, any feature count),
-      "bf16"    single bf16 operands on tcgen05, fp32 accumulation and state (fastest, ~3e-3 on logits),
+      "bf16"    single bf16 operands on tcgen05, fp32 accumulation and state (fastest, ~3e-3 on logits); H in {128, 256, 512},
       "auto"    "bf16x3" for every batch shape it takes, "fp32" otherwise (decided per batch shape).
     Default: $BIGRU_B200_PRECISION or "fp32".
     """
@@ -306,7 +306,8 @@ class BiGRU(nn.Module):
         """The tensor-core paths work on whole batch tiles (32 rows at bf16x3, 16 at bf16): other batch sizes run zero-padded
         to the next multiple.  Batch rows are independent and the padded rows receive a zero upstream gradient, so logits,
         loss and every gradient of the real rows are unchanged."""
-        mult = {"bf16x3": 32, "bf16": 16}.get(self.resolved_precision(batch), 1)
+        prec = self.resolved_precision(batch)
+        mult = 32 if (prec == "bf16x3" or (prec == "bf16" and self.hidden_size == 512)) else (16 if prec == "bf16" else 1)
         return (batch + mult - 1) // mult * mult
 
     def _plan_for(self, x) -> _Plan:

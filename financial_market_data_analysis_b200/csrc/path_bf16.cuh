@@ -10,14 +10,18 @@
 #include "kernels_f32.cuh"
 #include "tc_gemm.cuh"
 #include "tc_scan.cuh"
+#include "tc_scan_w.cuh"
 #include <algorithm>
 
 typedef __nv_bfloat16 bf16_t;
 
+// hidden size 512 runs on the 8-CTA-cluster kernels of tc_scan_w.cuh (64-unit slices, 32-row batch tiles)
+static inline bool bf16_wide(const bigru_plan& p) { return p.H == 512; }
 static int bf16_plan_check(const bigru_plan& p) {
-    if ((p.H != 128 && p.H != 256) || p.B % 16 != 0) {
-        bigru_set_error("BIGRU_PREC_BF16 supports hidden_size 128 or 256 and batch %% 16 == 0 (got H=%d B=%d; the Python mirror pads "
-                        "other batch sizes with zero rows); use BIGRU_PREC_FP32 for other shapes", p.H, p.B);
+    const bool ok = ((p.H == 128 || p.H == 256) && p.B % 16 == 0) || (p.H == 512 && p.B % 32 == 0);
+    if (!ok) {
+        bigru_set_error("BIGRU_PREC_BF16 supports hidden_size 128 or 256 with batch %% 16 == 0 and hidden_size 512 with batch %% 32 == 0 "
+                        "(got H=%d B=%d; the Python mirror pads other batch sizes with zero rows); use BIGRU_PREC_FP32 for other shapes", p.H, p.B);
         return BIGRU_ERR_UNSUPPORTED;
     }
     return BIGRU_OK;
@@ -45,7 +49,7 @@ static Bf16Layout bf16_layout(const bigru_plan& p) {
         L.Xrow[l] = o; o = al(o + R * Ip * 2);
         L.Wih[l] = o; o = al(o + D * 3 * H * Ip * 2);
         L.WihT[l] = o; o = al(o + D * 3 * H * I * 2);
-        L.Wimg[l] = o; o = al(o + D * 3 * H * H * 2);
+        L.Wimg[l] = o; o = al(o + D * (bf16_wide(p) ? 4 : 3) * H * H * 2);     // wide: [CS][128][H + 384] TMEM image + [CS][2][128][64] tail
         L.WTimg[l] = o; o = al(o + D * 3 * H * H * 2);
         L.bfold[l] = o; o = al(o + D * 3 * H * 4);
         L.bhn[l] = o; o = al(o + D * H * 4);
@@ -190,10 +194,11 @@ __global__ void dropout_rows_kernel(const bf16_t* __restrict__ Y, bf16_t* __rest
 }
 // gradient of the same dropout, in place on the BLOCKED fp32 gradient [d][tile][t][cta][thread][8] (see tc_gemm.cuh)
 __global__ void dropout_grad_rows_kernel(float* __restrict__ dYB, int64_t R, int cols, int B, int T, int H, float pdrop,
-                                         uint64_t seed, uint32_t stream) {
+                                         uint64_t seed, uint32_t stream, int wide) {
     const float scale = 1.f / (1.f - pdrop);
     const int64_t total = R * cols;
-    const int CS = H / 128, ntl = B / 16;
+    const int U = wide ? 64 : 128, NBt = wide ? 32 : 16;          // units per CTA, batch rows per tile (tc_scan.cuh / tc_scan_w.cuh)
+    const int CS = H / U, ntl = B / NBt;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int i8 = i & 7;
         int64_t e = i >> 3;
@@ -202,8 +207,8 @@ __global__ void dropout_grad_rows_kernel(float* __restrict__ dYB, int64_t R, int
         const int t = e % T; e /= T;
         const int tile = e % ntl;
         const int d = e / ntl;
-        const int unit = c * 128 + ((tid >> 5) & 3) * 32 + (tid & 31);
-        const int64_t b = tile * 16 + (tid >> 7) * 8 + i8;
+        const int unit = wide ? c * 64 + (tid & 63) : c * 128 + ((tid >> 5) & 3) * 32 + (tid & 31);
+        const int64_t b = wide ? tile * 32 + (tid >> 6) * 8 + i8 : tile * 16 + (tid >> 7) * 8 + i8;
         const uint64_t key = ((uint64_t)b * T + t) * cols + (uint64_t)(d * H + unit);
         dYB[i] = bigru_uniform(seed, stream, key) < pdrop ? 0.f : dYB[i] * scale;
     }
@@ -273,9 +278,10 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackJobs jobs, int 
     }
     // W_hh [3H][H]: gate g of unit u -> Wimg [unit][g][H] (row g*H+u of W_hh is row u*3+g of the image) and W_hh^T
     // -> WTimg [H][3H]; one gate block ([H][H]) at a time so that the row-major image is a plain strided copy
-    for (int g = 0; g < 3; ++g)
-        pack_tile_pair(J.w_hh + (int64_t)g * H * H, H, H, J.Wimg + (int64_t)g * H, (int64_t)3 * H, J.WTimg + (int64_t)g * H, H3,
-                       blockIdx.x, gridDim.x, tile);
+    if (H <= 256)                                           // H = 512: pack_wide_images_kernel (tc_scan_w.cuh) writes the images
+        for (int g = 0; g < 3; ++g)
+            pack_tile_pair(J.w_hh + (int64_t)g * H * H, H, H, J.Wimg + (int64_t)g * H, (int64_t)3 * H, J.WTimg + (int64_t)g * H, H3,
+                           blockIdx.x, gridDim.x, tile);
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < H3; q += (int64_t)gridDim.x * blockDim.x) {
         J.bfold[d * H3 + q] = J.b_ih[q] + (q < 2 * H ? J.b_hh[q] : 0.f);
         if (q >= 2 * H) J.bhn[d * H + q - 2 * H] = J.b_hh[q];
@@ -326,11 +332,14 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const bf16_t* __restrict_
         for (int i = 0; i < 8; ++i) { s_max[grp * H + u0 + i] = mx[i]; s_sum[grp * H + u0 + i] = sm[i]; s_arg[grp * H + u0 + i] = am[i]; }
     }
     __syncthreads();
-    const int j = tid;
-    float last = 0.f, m = -INFINITY, sum = 0.f;
-    int a_t = 0;
-    if (j < H) {
-        last = __bfloat162float(Y[((int64_t)(T - 1) * B + b) * ld + j]);
+    // second phase: thread -> units tid, tid + 256 (H <= 512)
+    float last2[2] = {0.f, 0.f}, m2[2] = {0.f, 0.f}, avg2[2] = {0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int j = tid + 256 * k;
+        if (j >= H) continue;
+        float last = __bfloat162float(Y[((int64_t)(T - 1) * B + b) * ld + j]), m = -INFINITY, sum = 0.f;
+        int a_t = 0;
         if (Ylo) last += __bfloat162float(Ylo[((int64_t)(T - 1) * B + b) * ld + j]);
         if (D == 2) {
             float lr = __bfloat162float(Y[(int64_t)b * ld + H + j]);
@@ -345,13 +354,16 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const bf16_t* __restrict_
         float* c = cat + (int64_t)b * 3 * H;
         c[j] = last; c[H + j] = m; c[2 * H + j] = sum / (float)T;
         arg[(int64_t)b * H + j] = a_t;
+        last2[k] = last; m2[k] = m; avg2[k] = sum / (float)T;
     }
-    const float avg = sum / (float)T;
+    const int j = tid;
     for (int cc = 0; cc < C; ++cc) {
         float v = 0.f;
-        if (j < H) {
-            const float* w = lin_w + (int64_t)cc * 3 * H;
-            v = last * w[j] + m * w[H + j] + avg * w[2 * H + j];
+        const float* w = lin_w + (int64_t)cc * 3 * H;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int jj = tid + 256 * k;
+            if (jj < H) v += last2[k] * w[jj] + m2[k] * w[H + jj] + avg2[k] * w[2 * H + jj];
         }
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if ((j & 31) == 0) red[cc * 8 + (j >> 5)] = v;
@@ -447,6 +459,7 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
                         float* hn, cudaStream_t st, WindowSrc win = WindowSrc{nullptr, nullptr, nullptr, 0}) {
     if (h0) { bigru_set_error("BIGRU_PREC_BF16: an initial hidden state is not supported; use BIGRU_PREC_FP32"); return BIGRU_ERR_UNSUPPORTED; }
     const Bf16Layout L = bf16_layout(p);
+    const bool wide = bf16_wide(p);
     uint8_t* S = (uint8_t*)stash_v;
     uint8_t* W = (uint8_t*)scratch_v;
     const int B = p.B, T = p.T, H = p.H, D = p.D, F = p.F;
@@ -469,6 +482,15 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
                 J.bfold = (float*)(S + L.bfold[l]); J.bhn = (float*)(S + L.bhn[l]); J.I = (int)p.in_size(l); J.d = d;
             }
         KLAUNCH(KC_PACK, 0.0, 0.0, st, pack_all_kernel<<<dim3(148, nj), 256, 0, st>>>(jobs, H, D));
+        if (wide) {
+            using WG = tcw::Geo<512>;
+            const size_t fimg = (size_t)WG::CS * 128 * WG::ROW_ELEMS, ftail = (size_t)WG::CS * WG::NTAIL * 128 * 64, bimg = (size_t)WG::CS * 128 * WG::NRB * 192;
+            for (int l = 0; l < p.L; ++l)
+                for (int d = 0; d < D; ++d)
+                    KLAUNCH(KC_PACK, 0.0, 0.0, st, tcw::pack_wide_images_kernel<512><<<148 * 2, 256, 0, st>>>(
+                                params + p.off_whh(l, d), (bf16_t*)(S + L.Wimg[l]) + d * fimg, (bf16_t*)(S + L.Wimg[l]) + D * fimg + d * ftail,
+                                (bf16_t*)(S + L.WTimg[l]) + d * bimg));
+        }
     }
     // 2. layer-0 input: cast to bf16, time-major rows (+ input dropout) - or, for windows of a chunk, only the chunk itself
     const bool direct = windows_direct(p, win.src != nullptr, do_drop);
@@ -495,18 +517,30 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
         // 3. input projection for all t, both directions, written in the scan kernel's blocked layout:  W_ih X^T + bias(row).
         //    With 64 input features (layer 0 of the reference configurations) the projection is formed inside the scan
         //    kernel instead (tc_scan.cuh, fuse_x): no gi round trip through HBM and no GEMM launch.
-        const bool fuse_x = (I == 64);
+        const bool fuse_x = (I == 64) && !wide;
         if (!fuse_x) {
             tcg::Params g{};
             const int Ip = pad8(I);                                                     // zero-padded K extent (layer 0, n_features % 8 != 0)
             g.M = D * 3 * H; g.N = (int)R; g.K = Ip; g.batch = 1; g.splitk = 1; g.mode = tcg::OUT_SCAN_BF16;
-            g.blk = tcg::ScanBlk{T, B, H, 3}; g.m_fast = 1;      // the few weight m-tiles share each activation tile via L2
+            g.blk = wide ? tcg::ScanBlk{T, B, H, 3, 64, 32} : tcg::ScanBlk{T, B, H, 3}; g.m_fast = 1;      // the few weight m-tiles share each activation tile via L2
             g.C = W + L.gi; g.ldc = R; g.bias = (const float*)(S + L.bfold[l]); g.bias_per_row = 1; g.dbg = dbg;
             const bool wnd = direct && l == 0;
             g.b_win = wnd ? B : 0;
             TRY(tc_gemm(S + L.Wih[l], D * 3 * H, Ip, Xrow, wnd ? (int64_t)B + T - 1 : R, Ip, g, st));
         }
         // 4. recurrence
+        if (wide) {
+            using WG = tcw::Geo<512>;
+            tcw::FwdParams f{};
+            f.B = B; f.T = T; f.H = H; f.D = D;
+            f.Wimg = (const bf16_t*)(S + L.Wimg[l]); f.Wtail = f.Wimg + (size_t)D * WG::CS * 128 * WG::ROW_ELEMS;
+            f.giW = (const bf16_t*)(W + L.gi); f.b_hn = (const float*)(S + L.bhn[l]);
+            f.Yrow = (bf16_t*)(S + L.Yrow[l]); f.GW = (bf16_t*)(S + L.G[l]); f.YBW = (bf16_t*)(S + L.YB[l]);
+            f.hn_out = hn ? hn + (int64_t)l * D * B * H : nullptr; f.dbg = dbg;
+            ProfScope ps(KC_TC_SCAN_FWD, 2.0 * 3 * H * H * (double)R * D, 0.0, st);
+            CUDA_TRY(tcw::launch_fwd(f, st));
+            continue;
+        }
         tcs::FwdParams f{};
         f.B = B; f.T = T; f.H = H; f.D = D;
         f.Wimg = (const bf16_t*)(S + L.Wimg[l]); f.giB = (const bf16_t*)(W + L.gi); f.b_hn = (const float*)(S + L.bhn[l]);
@@ -537,6 +571,7 @@ static int backward_bf16(const bigru_plan& p, const float* params, const float* 
                          const float* dlogits, float* grads, float* dx, float* dh0, cudaStream_t st) {
     if (h0 || dh0) { bigru_set_error("BIGRU_PREC_BF16: initial hidden state / its gradient are not supported"); return BIGRU_ERR_UNSUPPORTED; }
     const Bf16Layout L = bf16_layout(p);
+    const bool wide = bf16_wide(p);
     const uint8_t* S = (const uint8_t*)stash_v;
     uint8_t* W = (uint8_t*)scratch_v;
     const int B = p.B, T = p.T, H = p.H, D = p.D, C = p.C;
@@ -555,14 +590,24 @@ static int backward_bf16(const bigru_plan& p, const float* params, const float* 
     for (int l = p.L - 1; l >= 0; --l) {
         const int I = (int)p.in_size(l);
         // 1. BPTT scan
-        tcs::BwdParams b{};
-        b.B = B; b.T = T; b.H = H; b.D = D;
-        b.WTimg = (const bf16_t*)(S + L.WTimg[l]); b.G = (const bf16_t*)(S + L.G[l]); b.YB = (const bf16_t*)(S + L.YB[l]);
-        b.dYB = dY;
-        if (l == p.L - 1) { b.dlogits = dlogits; b.lin_w = params + p.off_linw(); b.arg = (const int*)(S + L.arg); b.C = C; }
-        b.dgi_row = (bf16_t*)(W + L.gi); b.dghn_row = (bf16_t*)(W + L.dghn);
-        b.db_ih = grads + p.off_bih(l, 0); b.db_hh = grads + p.off_bhh(l, 0); b.dir_stride = p.ld_block(l); b.dbg = dbg;
-        {
+        if (wide) {
+            tcw::BwdParams b{};
+            b.B = B; b.T = T; b.H = H; b.D = D;
+            b.WTimg = (const bf16_t*)(S + L.WTimg[l]); b.GW = (const bf16_t*)(S + L.G[l]); b.YBW = (const bf16_t*)(S + L.YB[l]);
+            b.dYBW = dY;
+            if (l == p.L - 1) { b.dlogits = dlogits; b.lin_w = params + p.off_linw(); b.arg = (const int*)(S + L.arg); b.C = C; }
+            b.dgi_row = (bf16_t*)(W + L.gi); b.dghn_row = (bf16_t*)(W + L.dghn);
+            b.db_ih = grads + p.off_bih(l, 0); b.db_hh = grads + p.off_bhh(l, 0); b.dir_stride = p.ld_block(l); b.dbg = dbg;
+            ProfScope ps(KC_TC_SCAN_BWD, 2.0 * 3 * H * H * (double)R * D, 0.0, st);
+            CUDA_TRY(tcw::launch_bwd(b, st));
+        } else {
+            tcs::BwdParams b{};
+            b.B = B; b.T = T; b.H = H; b.D = D;
+            b.WTimg = (const bf16_t*)(S + L.WTimg[l]); b.G = (const bf16_t*)(S + L.G[l]); b.YB = (const bf16_t*)(S + L.YB[l]);
+            b.dYB = dY;
+            if (l == p.L - 1) { b.dlogits = dlogits; b.lin_w = params + p.off_linw(); b.arg = (const int*)(S + L.arg); b.C = C; }
+            b.dgi_row = (bf16_t*)(W + L.gi); b.dghn_row = (bf16_t*)(W + L.dghn);
+            b.db_ih = grads + p.off_bih(l, 0); b.db_hh = grads + p.off_bhh(l, 0); b.dir_stride = p.ld_block(l); b.dbg = dbg;
             ProfScope ps(KC_TC_SCAN_BWD, 2.0 * 3 * H * H * (double)R * D, 0.0, st);
             CUDA_TRY(tcs::launch_bwd(b, st));
         }
@@ -607,11 +652,11 @@ static int backward_bf16(const bigru_plan& p, const float* params, const float* 
             tcg::Params g{};
             g.M = I; g.N = (int)R; g.K = D * 3 * H; g.batch = 1; g.splitk = 1;
             g.mode = l > 0 ? tcg::OUT_SCAN_F32 : tcg::OUT_F32;
-            g.blk = tcg::ScanBlk{T, B, H, 1}; g.m_fast = 1;
+            g.blk = wide ? tcg::ScanBlk{T, B, H, 1, 64, 32} : tcg::ScanBlk{T, B, H, 1}; g.m_fast = 1;
             g.C = dYnext; g.ldc = R; g.dbg = dbg;
             TRY(tc_gemm(S + L.WihT[l], I, (int64_t)D * 3 * H, W + L.gi, R, (int64_t)D * 3 * H, g, st, KC_TC_GEMM_DX));
             if (l > 0 && dropped)
-                KLAUNCH(KC_MISC, 0.0, 0.0, st, dropout_grad_rows_kernel<<<148 * 8, 256, 0, st>>>(dYnext, R, I, B, T, H, drop, seed, (uint32_t)l));
+                KLAUNCH(KC_MISC, 0.0, 0.0, st, dropout_grad_rows_kernel<<<148 * 8, 256, 0, st>>>(dYnext, R, I, B, T, H, drop, seed, (uint32_t)l, wide ? 1 : 0));
             if (l == 0) {
                 dim3 grid((I + 31) / 32, (B + 31) / 32, T);
                 KLAUNCH(KC_MISC, 0.0, 0.0, st, dx_to_batch_major_kernel<<<grid, dim3(32, 8), 0, st>>>(dYnext, dx, B, T, I,

@@ -1,5 +1,6 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden fixtures.
 Run on the B200 box:  python -m pytest tests -m gpu -x -q"""
+import json
 import os
 
 import numpy as np
@@ -52,7 +53,7 @@ def supported(precision, B, F, H, h0=False):
         return True
     if precision == "bf16x3":
         return H in (128, 256)
-    return H in (128, 256) and not h0
+    return H in (128, 256, 512) and not h0          # H = 512: the 8-CTA-cluster kernels of tc_scan_w.cuh
 
 
 def rel(a, b):
@@ -189,6 +190,8 @@ SWEEP = [  # B, T, F, H, L, C, bidir, h0
     (19, 6, 13, 128, 2, 3, True, True),       # batch not a whole tile (zero-padded rows), n_features % 8 != 0 (padded K extent), h0
     (40, 5, 108, 256, 1, 4, True, False),     # the reference's own feature count (108) at a tensor-core hidden size
     (3, 4, 5, 128, 2, 2, False, False),
+    (64, 6, 24, 512, 2, 3, True, False),      # hidden 512 (bf16 path: 8-CTA clusters, tc_scan_w.cuh), two batch tiles
+    (40, 3, 128, 512, 1, 2, False, False),
 ]
 
 
@@ -523,8 +526,8 @@ def test_auto_precision_and_batch_padding():
 
 
 def test_long_sequence_config_reduced():
-    """BASELINE config 4 (B256,T1024,F128,H512,L2) at reduced batch/length: H=512 runs on the fp32 path (the
-    tensor-core path covers H in {128, 256} and must refuse loudly); logits <= 1e-4 rel of the torch.nn.GRU CPU path."""
+    """BASELINE config 4 (B256,T1024,F128,H512,L2) at reduced batch/length on the exact FFMA path (logits <= 1e-4 rel of the
+    torch.nn.GRU CPU path); the bf16x3 path must refuse H = 512 loudly (its split weights do not fit tensor memory)."""
     B, T, F, H, L, C = 16, 256, 128, 512, 2, 3
     torch.manual_seed(0)
     ref = bo.OracleBiGRU(H, F, C, L, 50, 0.0, False, True)
@@ -539,10 +542,49 @@ def test_long_sequence_config_reduced():
     with torch.no_grad():
         got = m(x.cuda()).cpu().numpy()
     assert rel(got, want) < 1e-4
-    if "bf16" in precisions():
-        mb = _pkg().BiGRU(H, F, C, L, 50, 0.0, False, True, precision="bf16").cuda()
+    if "bf16x3" in precisions():
+        mb = _pkg().BiGRU(H, F, C, L, 50, 0.0, False, True, precision="bf16x3").cuda()
         with pytest.raises(ValueError, match="hidden_size 128 or 256"):
             mb(x.cuda())
+
+
+def test_long_sequence_config_on_tensor_cores():
+    """BASELINE configs[4] at its FULL sequence length, feature count and hidden size (T1024, F128, H512, L2, bidirectional) on the
+    persistent 8-CTA-cluster tensor-core kernels (precision="bf16", tc_scan_w.cuh), batch 64 so that the torch.nn.GRU CPU
+    oracle (forward + autograd) finishes in about a minute: logits and every gradient against the oracle at the bf16 path's
+    tolerances, the training step against the exact FFMA path's loss."""
+    if "bf16" not in precisions():
+        pytest.skip("tensor-core path not built")
+    B, T, F, H, L, C = 64, 1024, 128, 512, 2, 3
+    tol = TOL["bf16"]
+    torch.manual_seed(0)
+    ref = bo.OracleBiGRU(H, F, C, L, 50, 0.0, False, True)
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn(B, T, F, generator=g)
+    y = torch.randint(0, C, (B,), generator=g)
+    ref.train()
+    out_ref = ref(x)
+    loss_ref = nn.functional.cross_entropy(out_ref, y)
+    loss_ref.backward()
+    m = _pkg().BiGRU(H, F, C, L, 50, 0.0, False, True, precision="bf16")
+    m.load_state_dict(ref.state_dict())
+    m = m.cuda().train()
+    out = m(x.cuda())
+    loss = nn.functional.cross_entropy(out, y.cuda())
+    loss.backward()
+    e_log = rel(out.detach().cpu().numpy(), out_ref.detach().numpy())
+    got = torch.cat([p.grad.reshape(-1) for p in m._ordered_params()]).cpu().numpy()
+    want = torch.cat([p.grad.reshape(-1) for p in ref.parameters()]).numpy()
+    e_g = rel_l2(got, want)
+    print(f"configs[4] (B{B}) bf16 tensor-core path: logits rel {e_log:.3e}, gradient flat rel-L2 {e_g:.3e}")
+    path = os.environ.get("BIGRU_PARITY_REPORT_C4")
+    if path:
+        with open(path, "w") as f:
+            json.dump({"shape": dict(B=B, T=T, F=F, H=H, L=L, C=C), "precision": "bf16", "logits_rel": e_log, "grad_flat_rel_l2": e_g,
+                       "loss": float(loss.detach()), "loss_reference": float(loss_ref.detach())}, f, indent=1)
+    assert e_log < tol["logits"], e_log
+    assert e_g < tol["gflat"], e_g
+    assert abs(float(loss.detach()) - float(loss_ref.detach())) < 3e-2
 
 
 def test_training_trajectories_agree():
