@@ -29,6 +29,9 @@ if ROOT not in sys.path:
 
 METRIC = "sequences/sec (train step) biGRU h=256 seq=128 feat=64"
 WORK = dict(per_gpu_batch=512, seq_len=128, n_features=64, hidden=256, layers=2, classes=3)
+# --config c4: BASELINE.json configs[4] (long-sequence stress: persistent-kernel residency) - not the headline metric
+WORK_C4 = dict(per_gpu_batch=256, seq_len=1024, n_features=128, hidden=512, layers=2, classes=3)
+METRIC_C4 = "sequences/sec (train step) biGRU h=512 seq=1024 feat=128"
 
 
 def flops_train_per_seq(T, F, H, L, C, D=2):
@@ -164,19 +167,23 @@ def run_reference(args):
 
 CONFIG_OF = {"bf16x3": "configs[1] (fused-gate tensor-core kernels at fp32 tolerance: split bf16x3 operands, fp32 accumulate)",
              "fp32": "configs[1] (fp32 FFMA parity path)", "bf16": "configs[2] (bf16 tcgen05 gate GEMM)"}
+CONFIG_OF_C4 = {"bf16": "configs[4] (long sequence, hidden 512: 8-CTA-cluster persistent scans, bf16 tcgen05)",
+                "fp32": "configs[4] (long sequence, hidden 512, fp32 FFMA path)"}
 
 
 def workload_config(n_gpus, precision, cpu=False, batch=None):
     W = WORK
     b = batch or W["per_gpu_batch"]
-    which = "configs[0]/[1] shape on the host CPU (reference arm)" if cpu else CONFIG_OF.get(precision, "configs[1]")
-    return {"workload": f"BASELINE.json {which}: biGRU train step, batch 512/GPU x seq 128 x feat 64, hidden 256, "
-                        "2 layers, bidirectional, 3-class cross-entropy, clip 50, Adam 1e-3",
+    c4 = W["hidden"] == 512
+    which = ("configs[4] shape" if c4 else "configs[0]/[1] shape") + " on the host CPU (reference arm)" if cpu else \
+        (CONFIG_OF_C4 if c4 else CONFIG_OF).get(precision, "configs[4]" if c4 else "configs[1]")
+    return {"workload": f"BASELINE.json {which}: biGRU train step, batch {W['per_gpu_batch']}/GPU x seq {W['seq_len']} x feat {W['n_features']}, "
+                        f"hidden {W['hidden']}, {W['layers']} layers, bidirectional, 3-class cross-entropy, clip 50, Adam 1e-3",
             "global_batch": b * (1 if cpu else n_gpus), "per_gpu_batch": b, "seq_len": W["seq_len"],
             "n_features": W["n_features"], "hidden": W["hidden"], "layers": W["layers"], "bidirectional": True,
             "classes": W["classes"], "loss": "CrossEntropyLoss", "optimizer": "Adam(lr=1e-3)+clip_grad_norm_(50)",
             "parallelism": "cpu" if cpu else f"dp{n_gpus}", "precision": precision,
-            "l2": "8 rotating input batches + >1 GB of activation traffic per step (>> 126 MB L2)"}
+            "l2": "rotating input batches + >1 GB of activation traffic per step (>> 126 MB L2)"}
 
 
 def main():
@@ -188,7 +195,12 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("BIGRU_B200_PRECISION", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the secondary precision (bf16) measurement")
+    ap.add_argument("--config", default="c1", choices=["c1", "c4"],
+                    help="c1: BASELINE.json configs[1] (the headline metric); c4: configs[4] long sequence (B256 T1024 F128 H512)")
     args = ap.parse_args()
+    global WORK, METRIC
+    if args.config == "c4":
+        WORK, METRIC = WORK_C4, METRIC_C4
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
@@ -230,7 +242,7 @@ def main():
     if precision == "auto":          # the path that meets the stated tolerance first
         precision = "bf16x3" if plan_ok(pkg._lib.PREC_BF16X3) else ("bf16" if plan_ok(pkg._lib.PREC_BF16) else "fp32")
 
-    NBUF = 8
+    NBUF = 8 if args.config == "c1" else 2                    # c4: 134 MB per batch
     host = [synthetic(B, T, F, C, 1234 + rank + 97 * i) for i in range(NBUF)]
     host = [(x.pin_memory(), t.pin_memory()) for x, t in host]
     resident = [(x.to(dev), t.to(dev)) for x, t in host]
@@ -272,7 +284,7 @@ def main():
         """value (device-resident inputs), e2e (pinned host inputs, H2D + loss D2H inside the timed region) and the live
         per-kernel-class roofline of one precision."""
         model = make_model(prec)
-        out = {"precision": prec, "workload": CONFIG_OF.get(prec)}
+        out = {"precision": prec, "workload": (CONFIG_OF_C4 if args.config == "c4" else CONFIG_OF).get(prec)}
 
         def step_resident(i):
             x, t = resident[i % NBUF]
@@ -287,6 +299,18 @@ def main():
             out["clocks"] = sampler.stop() if rank == 0 else None
         ms_step = ms / steps
         out.update(value=B * world / (ms_step * 1e-3), ms_per_step=ms_step, gpu_launches=int(launches))
+        if world > 1:
+            # exposed communication: the same step with the gradient all-reduce switched off (replicas diverge harmlessly
+            # for these few steps; a fresh model follows for every later arm)
+            dpw = model._dp_world
+            model._dp_world = 1
+            ms0, _ = timed(step_resident, max(5, steps // 2), warmup)
+            model._dp_world = dpw
+            ms0 /= max(5, steps // 2)
+            out["comm"] = {"ms_per_step_with_allreduce": ms_step, "ms_per_step_without": ms0,
+                           "exposed_frac": max(0.0, 1.0 - ms0 / ms_step), "bytes_per_step": 4 * (model.flat_parameters().numel() + 1),
+                           "collective": "one NCCL all_reduce(SUM) of the flat gradient + loss per step"}
+            model = make_model(prec)
 
         if with_e2e:
             # Every step's inputs start in pinned host memory and are copied to the GPU inside the timed region
@@ -442,12 +466,13 @@ def main():
             torch.manual_seed(0)
             ref = OracleBiGRU(H, F, C, L, 50, 0.0, False, True)
             ref.eval()
-            xs = host[0][0][:64].contiguous()
+            xs = host[0][0][:(64 if args.config == "c1" else 16)].contiguous()
             with torch.no_grad():
                 want = ref(xs)
-            parity = {"what": "max |logit - oracle logit| / max |oracle logit| on 64 sequences of the benchmark shape (eval mode); "
-                              "the full-batch figures with gradients are in profiles/r02_parity_c1.json (tests/test_gpu_parity.py)",
-                      "tolerance": 1e-4}
+            parity = {"what": "max |logit - oracle logit| / max |oracle logit| on %d sequences of the benchmark shape (eval mode); "
+                              "the full-batch figures with gradients are in profiles/r02_parity_c%s.json (tests/test_gpu_parity.py)"
+                              % (xs.shape[0], "1" if args.config == "c1" else "4"),
+                      "tolerance": 1e-4 if args.config == "c1" else 3e-2}
             for prec in [precision] + list(variants):
                 m2 = pkg.BiGRU(H, F, C, L, 50, 0.0, False, True, precision=prec)
                 m2.load_state_dict(ref.state_dict())
@@ -499,7 +524,7 @@ def main():
                 "vs_baseline": None, "dtype": dt, "data": "synthetic",
                 "config": workload_config(world, precision), "clocks": head.get("clocks"), "e2e": head.get("e2e"),
                 "gpu_launches": head["gpu_launches"], "roofline": head.get("roofline"), "cpu_baseline": cpu,
-                "e2e_windows": e2e_windows, "variants": variants, "parity": parity, "cudnn_comparator": cudnn}
+                "e2e_windows": e2e_windows, "variants": variants, "parity": parity, "cudnn_comparator": cudnn, "comm": head.get("comm")}
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
