@@ -29,10 +29,12 @@ def main():
     B, T, F, H, L, C = 512, 128, 64, 256, 2, 3
     prec = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+    if len(sys.argv) > 3:                                   # B,T,F,H   e.g. 256,256,128,512 (the hidden-512 kernels, precision bf16)
+        B, T, F, H = (int(v) for v in sys.argv[3].split(","))
     torch.manual_seed(0)
     m = pkg.BiGRU(H, F, C, L, 50, 0.0, False, True, precision=prec).cuda().eval()
     x = torch.randn(B, T, F, generator=torch.Generator().manual_seed(1234)).cuda()
-    lay = layout(B, T, F, H, L)
+    lay = layout(B, T, F, H, L) if prec == "bf16x3" else [("stash", 0, None)]
     ref = None
     for it in range(n):
         with torch.no_grad():
@@ -45,6 +47,7 @@ def main():
             continue
         msgs = []
         for name, off, nb in lay:
+            nb = ref.numel() if nb is None else nb
             a, b = ref[off:off + nb], snap[off:off + nb]
             if not torch.equal(a, b):
                 nd = int((a != b).sum())
