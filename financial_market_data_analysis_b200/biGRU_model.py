@@ -269,10 +269,17 @@ class BiGRU(nn.Module):
                 p.data = flat[off:off + n].view(p.shape)
                 views.append((off, n, tuple(p.shape)))
                 off += n
+        old = getattr(self, "_adam", None)
         self._flat, self._views = flat, views
         self._plans = {}
         self._graphs = {}
         self._adam = None
+        if old is not None and old["m"].numel() == total:        # keep the Adam moments across a re-flatten (.to() / .cuda())
+            st = self._fused_state(dev)
+            st["m"].copy_(old["m"].to(dev)); st["v"].copy_(old["v"].to(dev))
+            st["step"] = old["step"]
+            st["dstep"].fill_(old["step"])
+            self._mirror_optimizer_state()
 
     def _is_flat(self):
         f = self._flat
@@ -378,7 +385,8 @@ class BiGRU(nn.Module):
                     and fn.ignore_index == -100:
                 return _lib.LOSS_CE, None, None
         elif isinstance(fn, nn.BCEWithLogitsLoss):
-            if fn.reduction == "mean":
+            per_class = lambda w: w is None or w.numel() in (1, self.output_size)      # per-element weights: autograd path
+            if fn.reduction == "mean" and per_class(fn.weight) and per_class(fn.pos_weight):
                 return _lib.LOSS_BCE, fn.weight, fn.pos_weight
         elif isinstance(fn, nn.MultiLabelSoftMarginLoss):
             if fn.weight is None and fn.reduction == "mean":
@@ -430,7 +438,49 @@ class BiGRU(nn.Module):
                                "dstep": torch.zeros(1, device=dev, dtype=torch.int32),
                                "gext": gext, "grad": gext[:P], "loss": gext[P:P + 1],
                                "scal": torch.zeros(2, device=dev, dtype=torch.float32)}
+            self._import_optimizer_state(st)
+            self._mirror_optimizer_state()
         return st
+
+    @staticmethod
+    def _bump_step(st, k):
+        st["step"] += k
+        ms = st.get("mirror_steps")
+        if ms:
+            torch._foreach_add_(ms, float(k))
+
+    def _import_optimizer_state(self, st):
+        """Moments the user's torch.optim.Adam already holds (generic steps taken before, or a loaded optimizer.state_dict())
+        become the fused step's flat moments."""
+        opt = getattr(self, "optimizer", None)
+        if opt is None:
+            return
+        steps = []
+        for p, (off, n, _) in zip(self._ordered_params(), self._views):
+            ps = opt.state.get(p)
+            if not ps or "exp_avg" not in ps:
+                return
+            steps.append(int(float(ps["step"])) if "step" in ps else 0)
+        if len(set(steps)) != 1:
+            return
+        with torch.no_grad():
+            for p, (off, n, _) in zip(self._ordered_params(), self._views):
+                ps = opt.state[p]
+                st["m"][off:off + n].copy_(ps["exp_avg"].reshape(-1).to(st["m"].device))
+                st["v"][off:off + n].copy_(ps["exp_avg_sq"].reshape(-1).to(st["v"].device))
+        st["step"] = steps[0]
+        st["dstep"].fill_(steps[0])
+
+    def _mirror_optimizer_state(self):
+        """optimizer.state[p] = views of the flat moments + a step tensor, in torch.optim.Adam's own format: optimizer.state_dict()
+        checkpoints carry the fused step's moments, and a later generic optimizer.step() continues from them (in place)."""
+        opt, st = getattr(self, "optimizer", None), self._adam
+        if opt is None or st is None or self._adam_spec() is None:
+            return
+        for p, (off, n, shape) in zip(self._ordered_params(), self._views):
+            opt.state[p] = {"step": torch.tensor(float(st["step"])), "exp_avg": st["m"][off:off + n].view(shape),
+                            "exp_avg_sq": st["v"][off:off + n].view(shape)}
+        st["mirror_steps"] = [opt.state[p]["step"] for p in self._ordered_params()]
 
     def _launch_fwd_loss_bwd(self, lib, plan, x, h0, tgt, kind, wv, pwv, denom, logits, dlogits, stash, args, st, s):
         # the loss sees the REAL batch rows (tgt's); logits / dlogits may carry zero-padded rows behind them (whole batch tiles)
@@ -453,7 +503,7 @@ class BiGRU(nn.Module):
                                                 _lib.ptr(st["v"]), self._flat.numel(), _lib.ptr(sq), float(self.clip),
                                                 float(g["lr"]), float(b1), float(b2), float(g["eps"]), _lib.ptr(st["dstep"]),
                                                 1.0, s), "bigru_clip_adam_step_dev")
-        st["step"] += 1
+        self._bump_step(st, 1)
 
     def _graph_for(self, key, x, tgt, kind, wv, pwv, denom, g):
         """CUDA graph(s) of the train step for one (shape, loss) key: static input / output buffers, the
@@ -491,7 +541,7 @@ class BiGRU(nn.Module):
             gb = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gb, capture_error_mode="thread_local"):
                 self._launch_update(lib, g, st, _stream_ptr(dev))
-        st["step"] -= 1                                   # the capture ran the host-side bookkeeping once without stepping
+        self._bump_step(st, -1)                                   # the capture ran the host-side bookkeeping once without stepping
         ent["launches"] = int(lib.bigru_launch_count() - n0)
         lib.bigru_launch_count_add(-ent["launches"])      # captured, not executed
         ent["ga"], ent["gb"], ent["fresh"] = ga, gb, True
@@ -563,7 +613,7 @@ class BiGRU(nn.Module):
                     if ent["gb"] is not None:
                         allreduce_flat_(st["gext"], self._dp_group)
                         ent["gb"].replay()
-                    st["step"] += 1
+                    self._bump_step(st, 1)
                     lib.bigru_launch_count_add(ent["launches"])
                     return st["loss"].clone(), ent["logits"][:B].clone()
             x, h0 = padded(x, h0)

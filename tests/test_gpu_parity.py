@@ -525,6 +525,59 @@ def test_auto_precision_and_batch_padding():
                 assert abs(float(loss) - float(lr_.detach())) <= tol_l * max(1.0, abs(float(lr_.detach())))
 
 
+def test_fused_adam_state_lives_in_the_optimizer():
+    """The fused train step keeps Adam's moments in flat buffers; optimizer.state mirrors them (views + step counters) in
+    torch.optim.Adam's own format: a checkpoint of optimizer.state_dict() resumes the fused step, and the generic autograd step
+    (any loss / optimiser route) continues from the same moments."""
+    import copy
+    pkg = _pkg()
+    B, T, F, H, L, C = 8, 5, 6, 12, 1, 3
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, T, F, generator=g).cuda()
+    y = torch.randint(0, C, (B,), generator=g).cuda()
+
+    def fresh(state=None):
+        torch.manual_seed(2)
+        m = pkg.BiGRU(H, F, C, L, 50, 0.0, False, True, precision="fp32").cuda()
+        if state is not None:
+            m.load_state_dict(state)
+        m.add_loss_fn(nn.CrossEntropyLoss())
+        m.add_optimizer(torch.optim.Adam(m.parameters(), lr=1e-2))
+        return m.train()
+
+    m1 = fresh()
+    for _ in range(3):
+        m1.train_step(x, y)
+    sd_opt = copy.deepcopy(m1.optimizer.state_dict())
+    sd_model = {k: v.clone() for k, v in m1.state_dict().items()}
+    st = sd_opt["state"]
+    assert len(st) == len(list(m1.parameters())) and all(int(float(v["step"])) == 3 for v in st.values())
+    assert all(float(v["exp_avg"].abs().max()) > 0 for v in st.values())
+    for _ in range(2):
+        m1.train_step(x, y)
+    want = torch.cat([p.detach().reshape(-1) for p in m1.parameters()]).cpu()
+    # (b) resume from the checkpoint, fused
+    m2 = fresh(sd_model)
+    m2.optimizer.load_state_dict(sd_opt)
+    for _ in range(2):
+        m2.train_step(x, y)
+    got = torch.cat([p.detach().reshape(-1) for p in m2.parameters()]).cpu()
+    assert float((got - want).abs().max()) < 1e-6
+    assert all(int(float(v["step"])) == 5 for v in m2.optimizer.state_dict()["state"].values())
+    # (c) resume from the checkpoint, generic autograd step with torch's own Adam arithmetic
+    m3 = fresh(sd_model)
+    m3.optimizer.load_state_dict(sd_opt)
+    for _ in range(2):
+        m3._generic_step(x, y)
+    got3 = torch.cat([p.detach().reshape(-1) for p in m3.parameters()]).cpu()
+    assert float((got3 - want).abs().max()) < 2e-4
+    # a per-element BCE weight cannot be fused: the step falls back to autograd instead of raising
+    mb = pkg.BiGRU(H, F, C, L, 50, 0.0, False, True, precision="fp32").cuda().train()
+    mb.add_loss_fn(nn.BCEWithLogitsLoss(weight=torch.rand(B, C).cuda()))
+    mb.add_optimizer(torch.optim.Adam(mb.parameters(), lr=1e-3))
+    assert not mb.can_fuse_step()
+
+
 def test_long_sequence_config_reduced():
     """BASELINE config 4 (B256,T1024,F128,H512,L2) at reduced batch/length on the exact FFMA path (logits <= 1e-4 rel of the
     torch.nn.GRU CPU path); the bf16x3 path must refuse H = 512 loudly (its split weights do not fit tensor memory)."""
