@@ -1146,11 +1146,359 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanx_bwd_kernel(const __grid_
     if (warp == EPI_WARPS) tc::tmem_dealloc(tmem, 512);
 }
 
+// ping-pong form: both parts (hi, lo) of a 16-row dgh sub-tile against one row block: 24 MMAs with N = 16
+__device__ __forceinline__ void bwd2_issue_block(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_hi, uint64_t desc_lo) {
+    constexpr uint32_t idesc = tc::umma_idesc_bf16(128, NBS);
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                tcs::umma_bf16_ts(tmem_d, tmem_a + (uint32_t)((g * 4 + kk) * 8),
+                                  (part ? desc_lo : desc_hi) + (uint64_t)(g * (HS_CHUNK >> 4) + 2 * kk), idesc,
+                                  (part == 0 && g == 0 && kk == 0) ? 0u : 1u);
+        }
+    }
+}
+
+template <int H>
+__global__ void __launch_bounds__(THREADS, 1) gru_scanx_bwd2_kernel(const __grid_constant__ BwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int CS = H / 64, NKH = H / 128, NRB = 2 * NKH;
+    // Ping-pong form: the 32-row tile is worked as two 16-row SUB-TILES.  The thread <-> data mapping of the single-tile kernel
+    // already splits by sub-tile - epilogue warps 0-3 touch only batch columns 0-15 (as partial-sum routers AND as owners),
+    // warps 4-7 only columns 16-31 - so the two warp groups are simply decoupled: own dgh operand tiles (N = 16), own
+    // accumulators, own barriers; the control thread alternates the sub-tiles, and while the tensor pipe multiplies one
+    // sub-tile the other group routes / reduces / does its gate-gradient math.
+    constexpr int DT_BYTES = 3 * HS_CHUNK;                // one part of one dgh sub-tile
+    constexpr int SUBD = 4 * DT_BYTES;                     // [2 buf][2 part] of one sub-tile
+    constexpr int SUBN = 4 * HS_CHUNK;
+    const int B = p.B, T = p.T;
+    uint8_t* sD = smem;                                    // [2 sub][2 buf][2 part][3 gates][HS_CHUNK]
+    uint8_t* sN = sD + (size_t)2 * SUBD;                   // [2 sub][2 buf][2 part][HS_CHUNK]   da_n (dgi n-gate rows, store only)
+    uint8_t* sR = sN + (size_t)2 * SUBN;                   // [2 buf][4 src][8 cg][64 j] float4 (column groups 0-3: sub-tile 0, 4-7: sub-tile 1)
+    uint8_t* sIn = sR + (size_t)2 * RECV_BYTES;            // [NSB][G | YB | dY]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + (size_t)NSB * BWD_STAGE);
+    uint64_t* recv_full = bars;        // [2 sub][2 buf]
+    uint64_t* mma_a = bars + 4;        // [2 sub] row blocks of the other k half done
+    uint64_t* mma_b = bars + 6;        // [2 sub] all row blocks done
+    uint64_t* epi_done = bars + 8;     // [2 sub]
+    uint64_t* st_done = bars + 10;     // [2 sub]
+    uint64_t* in_full = bars + 12;     // [NSB]
+    uint64_t* in_empty = bars + 12 + NSB;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12 + 2 * NSB);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t c = tc::cluster_ctarank();
+    const int cluster_id = blockIdx.x / CS;
+    const int ntiles = B / NB;
+    const int d = cluster_id / ntiles, tile = cluster_id % ntiles;
+    const bool top = p.dlogits != nullptr;
+    const int kh_own = (int)c >> 1;                        // k half that contains this CTA's own units (H = 256)
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) tc::mbar_init(&recv_full[i], 1);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&mma_a[i], 1); tc::mbar_init(&mma_b[i], 1);
+            tc::mbar_init(&epi_done[i], EPI_WARPS / 2); tc::mbar_init(&st_done[i], EPI_WARPS / 2);
+        }
+        for (int i = 0; i < NSB; ++i) { tc::mbar_init(&in_full[i], 1); tc::mbar_init(&in_empty[i], EPI_WARPS); }
+        tc::fence_mbar_init();
+    }
+    if (warp == EPI_WARPS) tc::tmem_alloc(tmem_slot, 512);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    if (warp < EPI_WARPS)
+        tcs::load_weights_to_tmem(p.WTimg + ((size_t)d * CS + c) * 128 * (NRB * 192), NRB * 192, tmem, A_COL, warp, lane);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+
+    if (warp == EPI_WARPS + 1) {
+        if (tc::elect_one()) {
+            bool ok = true;
+            for (int s = 0; s < T; ++s) {
+                const int st = s % NSB;
+                if (s >= NSB && ok) ok = tc::mbar_wait(&in_empty[st], ((s / NSB) - 1) & 1, p.dbg, 0x2300 + (s & 0xff));
+                const int t = d == 0 ? T - 1 - s : s;
+                const bool first = d == 0 ? t == 0 : t == T - 1;
+                uint8_t* dst = sIn + (size_t)st * BWD_STAGE;
+                tc::mbar_arrive_expect_tx(&in_full[st], (uint32_t)(G_BLOCK + (top ? 0 : DY_BLOCK) + (first ? 0 : YB_BLOCK)));
+                const size_t blk = blk_index(d, tile, t, (int)c, ntiles, T, CS);
+                tc::bulk_g2s(dst, reinterpret_cast<const uint8_t*>(p.GX) + blk * G_BLOCK, G_BLOCK, &in_full[st]);
+                if (!top) tc::bulk_g2s(dst + G_BLOCK + YB_BLOCK, reinterpret_cast<const uint8_t*>(p.dYBX) + blk * DY_BLOCK, DY_BLOCK, &in_full[st]);
+                if (!first) {
+                    const size_t pblk = blk_index(d, tile, d == 0 ? t - 1 : t + 1, (int)c, ntiles, T, CS);
+                    tc::bulk_g2s(dst + G_BLOCK, reinterpret_cast<const uint8_t*>(p.YBX) + pblk * YB_BLOCK, YB_BLOCK, &in_full[st]);
+                }
+            }
+        }
+    } else if (warp == EPI_WARPS) {
+        if (tc::elect_one()) {
+            bool ok = true;
+            auto store_tile = [&](int sub, int step) {        // 16-row boxes (the tensor maps of this form have box 64 x 16)
+                const int tt = d == 0 ? T - 1 - step : step;
+                const int row = tt * B + tile * NB + sub * NBS;
+                const uint8_t* tb = sD + (size_t)sub * SUBD + (size_t)(step & 1) * 2 * DT_BYTES;
+                const uint8_t* nb = sN + (size_t)sub * SUBN + (size_t)(step & 1) * 2 * HS_CHUNK;
+                const int cu = (int)c * UNITS;
+                tc::tma_store_2d(&p.tmGIh, tb, d * 3 * H + cu, row);                               // da_r
+                tc::tma_store_2d(&p.tmGIl, tb + DT_BYTES, d * 3 * H + cu, row);
+                tc::tma_store_2d(&p.tmGIh, tb + HS_CHUNK, d * 3 * H + H + cu, row);                // da_z
+                tc::tma_store_2d(&p.tmGIl, tb + DT_BYTES + HS_CHUNK, d * 3 * H + H + cu, row);
+                tc::tma_store_2d(&p.tmGIh, nb, d * 3 * H + 2 * H + cu, row);                       // da_n
+                tc::tma_store_2d(&p.tmGIl, nb + HS_CHUNK, d * 3 * H + 2 * H + cu, row);
+                tc::tma_store_2d(&p.tmGNh, tb + 2 * HS_CHUNK, d * H + cu, row);                    // da_n * r
+                tc::tma_store_2d(&p.tmGNl, tb + DT_BYTES + 2 * HS_CHUNK, d * H + cu, row);
+                tc::tma_store_commit();
+            };
+            const uint32_t db0 = tc::smem_u32(sD);
+            const int Tend = T + (p.dh0 ? 1 : 0);          // one more product (no gate math) when d(h0) is wanted
+            for (int s = 1; s < Tend; ++s) {
+                const int pb = (s - 1) & 1;
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                    if (ok) ok = tc::mbar_wait(&epi_done[sub], (s - 1) & 1, p.dbg, 0x2700 + (s & 0xff));
+                    if (sub == 0) SCANX_TS(0);
+                    tc::tcgen05_fence_after();
+                    tc::mbar_arrive_expect_tx(&recv_full[sub * 2 + (s & 1)], (uint32_t)(CS - 1) * 4096u);
+                    const uint32_t tb = db0 + (uint32_t)sub * SUBD + (uint32_t)pb * 2 * DT_BYTES;
+                    const uint64_t dhi = tc::umma_desc_k_sw128(tb), dlo = tc::umma_desc_k_sw128(tb + DT_BYTES);
+                    const uint32_t td = tmem + (uint32_t)(sub * 4 * NBS);
+                    const int ko = 1 - kh_own;
+                    bwd2_issue_block(td + (uint32_t)((0 * NKH + ko) * NBS), tmem + A_COL + (uint32_t)((0 * NKH + ko) * 96), dhi, dlo);
+                    bwd2_issue_block(td + (uint32_t)((1 * NKH + ko) * NBS), tmem + A_COL + (uint32_t)((1 * NKH + ko) * 96), dhi, dlo);
+                    tc::umma_commit(&mma_a[sub]);
+                    if (sub == 0) SCANX_TS(1);
+                    bwd2_issue_block(td + (uint32_t)((0 * NKH + kh_own) * NBS), tmem + A_COL + (uint32_t)((0 * NKH + kh_own) * 96), dhi, dlo);
+                    bwd2_issue_block(td + (uint32_t)((1 * NKH + kh_own) * NBS), tmem + A_COL + (uint32_t)((1 * NKH + kh_own) * 96), dhi, dlo);
+                    tma_store_wait_read1();            // the tile of THIS sub-tile stored two steps ago has been read (the other's may be in flight)
+                    tc::umma_commit(&mma_b[sub]);
+                    if (sub == 0) SCANX_TS(3);
+                    if (ok) ok = tc::mbar_wait(&st_done[sub], (s - 1) & 1, p.dbg, 0x2a00 + (s & 0xff));
+                    store_tile(sub, s - 1);
+                }
+            }
+            if (Tend == T) {
+                for (int sub = 0; sub < 2; ++sub) {
+                    if (ok) ok = tc::mbar_wait(&epi_done[sub], (T - 1) & 1, p.dbg, 0x2700);
+                    if (ok) ok = tc::mbar_wait(&st_done[sub], (T - 1) & 1, p.dbg, 0x2a00);
+                    store_tile(sub, T - 1);
+                }
+            }
+            tc::tma_store_wait_all();
+        }
+    } else {
+        // ---- epilogue.  Owner role: unit j = (warp & 1)*32 + lane of this CTA, batch columns [8*(warp >> 1), +8).
+        //      Partial-sum role: TMEM lane quarter q = warp & 3 -> output unit k = 128*kh + 32q + lane, columns [16*half, +16).
+        const int q = warp & 3, half = warp >> 2;          // half == sub-tile of this warp (router AND owner roles)
+        const int sub = half;
+        const int j = (warp & 1) * 32 + lane;
+        const int unit = (int)c * UNITS + j;
+        const int c0 = 8 * (warp >> 1);
+        const int tid = threadIdx.x;
+        float dhz[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dhz[i] = 0.f;
+        float h_avg[8], h_max[8];
+        int h_arg[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { h_avg[i] = 0.f; h_max[i] = 0.f; h_arg[i] = -1; }
+        if (top) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int b = tile * NB + c0 + i;
+                float dl = 0.f, dm = 0.f, da = 0.f;
+                for (int cc = 0; cc < p.C; ++cc) {
+                    const float g = p.dlogits[(int64_t)b * p.C + cc];
+                    const float* w = p.lin_w + (int64_t)cc * 3 * H;
+                    dl = fmaf(g, w[unit], dl); dm = fmaf(g, w[H + unit], dm); da = fmaf(g, w[2 * H + unit], da);
+                }
+                dhz[i] = dl;
+                h_avg[i] = da / (float)T; h_max[i] = dm; h_arg[i] = p.arg[(int64_t)b * H + unit];
+            }
+        }
+        float sb_r = 0.f, sb_z = 0.f, sb_n = 0.f, sb_nr = 0.f;
+        uint32_t e_off[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e_off[i] = tc::sw128_offset(c0 - 16 * sub + i, j);      // row inside the 16-row sub-tile
+        // partial-sum destination inside a receive buffer: [src = c][cg = 4*half + i][jd] float4, jd = (q & 1)*32 + lane
+        const uint32_t r_off = (((uint32_t)c * 8 + 4 * half) * 64 + (uint32_t)((q & 1) * 32 + lane)) * 16;
+        const uint32_t sIn_u = tc::smem_u32(sIn), sR_u = tc::smem_u32(sR), sD_u = tc::smem_u32(sD), sN_u = tc::smem_u32(sN);
+        bool ok = true;
+        // recurrent part of dh for this thread's (unit, 8 columns) at step s: every CTA's row blocks -> partial sums (hi + lo
+        // blocks of one k share a lane) -> owner's receive buffer (st.async / local store) -> sum over the CS sources
+        auto reduce_partials = [&](int s, float (&acc)[8]) {
+            const int buf = s & 1;
+            const uint32_t rb_local = sR_u + (uint32_t)buf * RECV_BYTES;
+            const uint32_t rbar_l = tc::smem_u32(&recv_full[sub * 2 + buf]);
+            auto route = [&](int kh) {
+                float vh[16], vl[16];
+                const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 4 * NBS);
+                tmem_ld16f(ta + (uint32_t)((0 * NKH + kh) * NBS), vh);
+                tmem_ld16f(ta + (uint32_t)((1 * NKH + kh) * NBS), vl);
+                tmem_ld_wait_pin(vh, vl);
+                const uint32_t dest = (uint32_t)(2 * kh + (q >> 1));
+                const uint32_t lp = rb_local + r_off;
+                if (dest == c) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        tc::sts_f4(lp + (uint32_t)(i * 64 * 16),
+                                   make_float4(vh[4 * i] + vl[4 * i], vh[4 * i + 1] + vl[4 * i + 1], vh[4 * i + 2] + vl[4 * i + 2], vh[4 * i + 3] + vl[4 * i + 3]));
+                } else {
+                    const uint32_t ra = tc::mapa_u32(lp, dest), rb = tc::mapa_u32(rbar_l, dest);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 u;
+                        u.x = __float_as_uint(vh[4 * i] + vl[4 * i]); u.y = __float_as_uint(vh[4 * i + 1] + vl[4 * i + 1]);
+                        u.z = __float_as_uint(vh[4 * i + 2] + vl[4 * i + 2]); u.w = __float_as_uint(vh[4 * i + 3] + vl[4 * i + 3]);
+                        tc::st_async_v4(ra + (uint32_t)(i * 64 * 16), u, rb);
+                    }
+                }
+            };
+            if (NKH == 2) {
+                if (tid == 0) SCANX_TS(4);
+                if (ok) ok = tc::mbar_wait(&mma_a[sub], (s - 1) & 1, p.dbg, 0x2800 + (s & 0xff));
+                tc::tcgen05_fence_after();
+                route(1 - kh_own);
+            }
+            if (ok) ok = tc::mbar_wait(&mma_b[sub], (s - 1) & 1, p.dbg, 0x2900 + (s & 0xff));
+            if (tid == 0) SCANX_TS(7);
+            tc::tcgen05_fence_after();
+            route(NKH == 2 ? kh_own : 0);
+            tc::tcgen05_fence_before();
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + sub) : "memory");      // this CTA's own contributions (of this warp group) are in the buffer
+            if (ok) ok = tc::mbar_wait_cluster(&recv_full[sub * 2 + buf], ((s - 1) >> 1) & 1, p.dbg, 0x2b00 + (s & 0xff));
+            if (tid == 0) SCANX_TS(8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int src = 0; src < CS; ++src) {
+                const uint32_t rp = rb_local + (uint32_t)((((src * 8 + 2 * (warp >> 1)) * 64) + j) * 16);
+                const float4 x0 = tc::lds_f4(rp), x1 = tc::lds_f4(rp + 64 * 16);
+                acc[0] += x0.x; acc[1] += x0.y; acc[2] += x0.z; acc[3] += x0.w; acc[4] += x1.x; acc[5] += x1.y; acc[6] += x1.z; acc[7] += x1.w;
+            }
+        };
+        for (int s = 0; s < T; ++s) {
+            const int t = d == 0 ? T - 1 - s : s;
+            const bool first = d == 0 ? t == 0 : t == T - 1;
+            float vr[8], vz[8], vn[8], vhn[8], vhp[8], vdy[8];
+            {
+                const int st = s % NSB;
+                if (ok) ok = tc::mbar_wait(&in_full[st], (s / NSB) & 1, p.dbg, 0x2200 + (s & 0xff));
+                const uint32_t gp = sIn_u + (uint32_t)st * BWD_STAGE + 32u * tid;
+                const float4 a0 = tc::lds_f4(gp), a1 = tc::lds_f4(gp + 16), b0 = tc::lds_f4(gp + 8192), b1 = tc::lds_f4(gp + 8192 + 16),
+                             n0 = tc::lds_f4(gp + 16384), n1 = tc::lds_f4(gp + 16384 + 16), m0 = tc::lds_f4(gp + 24576), m1 = tc::lds_f4(gp + 24576 + 16);
+                float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0, y0 = p0, y1 = p0;
+                if (!first) { p0 = tc::lds_f4(gp + G_BLOCK); p1 = tc::lds_f4(gp + G_BLOCK + 16); }
+                if (!top) { y0 = tc::lds_f4(gp + G_BLOCK + YB_BLOCK); y1 = tc::lds_f4(gp + G_BLOCK + YB_BLOCK + 16); }
+                vr[0] = a0.x; vr[1] = a0.y; vr[2] = a0.z; vr[3] = a0.w; vr[4] = a1.x; vr[5] = a1.y; vr[6] = a1.z; vr[7] = a1.w;
+                vz[0] = b0.x; vz[1] = b0.y; vz[2] = b0.z; vz[3] = b0.w; vz[4] = b1.x; vz[5] = b1.y; vz[6] = b1.z; vz[7] = b1.w;
+                vn[0] = n0.x; vn[1] = n0.y; vn[2] = n0.z; vn[3] = n0.w; vn[4] = n1.x; vn[5] = n1.y; vn[6] = n1.z; vn[7] = n1.w;
+                vhn[0] = m0.x; vhn[1] = m0.y; vhn[2] = m0.z; vhn[3] = m0.w; vhn[4] = m1.x; vhn[5] = m1.y; vhn[6] = m1.z; vhn[7] = m1.w;
+                vhp[0] = p0.x; vhp[1] = p0.y; vhp[2] = p0.z; vhp[3] = p0.w; vhp[4] = p1.x; vhp[5] = p1.y; vhp[6] = p1.z; vhp[7] = p1.w;
+                vdy[0] = y0.x; vdy[1] = y0.y; vdy[2] = y0.z; vdy[3] = y0.w; vdy[4] = y1.x; vdy[5] = y1.y; vdy[6] = y1.z; vdy[7] = y1.w;
+                if (first && p.h0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) vhp[i] = p.h0[((int64_t)d * B + tile * NB + c0 + i) * H + unit];
+                }
+                if (top) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) vdy[i] = h_avg[i] + (h_arg[i] == t ? h_max[i] : 0.f);
+                }
+            }
+            float c_n[8], c_r[8], c_z[8], pre[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float r = vr[i], z = vz[i], n = vn[i];
+                c_n[i] = (1.f - z) * (1.f - n * n);
+                c_r[i] = vhn[i] * r * (1.f - r);
+                c_z[i] = (vhp[i] - n) * z * (1.f - z);
+                pre[i] = dhz[i] + vdy[i];
+            }
+            float acc[8];
+            const int buf = s & 1;
+            if (s > 0) reduce_partials(s, acc);
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+            }
+            const uint32_t tileb = sD_u + (uint32_t)sub * SUBD + (uint32_t)buf * 2 * DT_BYTES;
+            const uint32_t nbuf = sN_u + (uint32_t)sub * SUBN + (uint32_t)buf * 2 * HS_CHUNK;
+            float dar[8], daz[8], dan[8], danr[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float dh = acc[i] + pre[i];
+                dan[i] = dh * c_n[i];
+                dar[i] = dan[i] * c_r[i];
+                daz[i] = dh * c_z[i];
+                danr[i] = dan[i] * vr[i];
+                dhz[i] = dh * vz[i];
+                __nv_bfloat16 hi, lo;
+                split_bf16(dar[i], hi, lo);
+                tc::sts_bf16(tileb + e_off[i], hi);
+                tc::sts_bf16(tileb + DT_BYTES + e_off[i], lo);
+                split_bf16(daz[i], hi, lo);
+                tc::sts_bf16(tileb + HS_CHUNK + e_off[i], hi);
+                tc::sts_bf16(tileb + DT_BYTES + HS_CHUNK + e_off[i], lo);
+                split_bf16(danr[i], hi, lo);
+                tc::sts_bf16(tileb + 2 * HS_CHUNK + e_off[i], hi);
+                tc::sts_bf16(tileb + DT_BYTES + 2 * HS_CHUNK + e_off[i], lo);
+            }
+            if (tid == 0) SCANX_TS(9);
+            tc::tcgen05_fence_before();
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&epi_done[sub]);
+            // the ring slot is released only HERE, after this step's results (which consume every value loaded from the slot)
+            // have been written: an arrive right behind the loads was seen to overtake them (the loads sat in the LSU queue behind
+            // the previous step's global stores), so the producer's next bulk copy replaced the slot before it had been read
+            if (lane == 0) tc::mbar_arrive(&in_empty[s % NSB]);
+            if (tid == 0) SCANX_TS(10);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                __nv_bfloat16 hi, lo;
+                split_bf16(dan[i], hi, lo);
+                tc::sts_bf16(nbuf + e_off[i], hi);
+                tc::sts_bf16(nbuf + HS_CHUNK + e_off[i], lo);
+            }
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&st_done[sub]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { sb_r += dar[i]; sb_z += daz[i]; sb_n += dan[i]; sb_nr += danr[i]; }
+        }
+        float* dbi = p.db_ih + (int64_t)d * p.dir_stride;
+        float* dbh = p.db_hh + (int64_t)d * p.dir_stride;
+        atomicAdd(dbi + unit, sb_r); atomicAdd(dbi + H + unit, sb_z); atomicAdd(dbi + 2 * H + unit, sb_n);
+        atomicAdd(dbh + unit, sb_r); atomicAdd(dbh + H + unit, sb_z); atomicAdd(dbh + 2 * H + unit, sb_nr);
+        if (p.dh0) {
+            // gradient of the initial hidden state = z-carry of the last step + W_hh^T dgh of the last step (one more product)
+            float acc[8];
+            reduce_partials(T, acc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) p.dh0[((int64_t)d * B + tile * NB + c0 + i) * H + unit] = dhz[i] + acc[i];
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();
+    if (warp == EPI_WARPS) tc::tmem_dealloc(tmem, 512);
+}
+
 static inline cudaError_t launch_bwd(const BwdParams& p_in, cudaStream_t st) {
     BwdParams p = p_in;
     if ((p.H != 128 && p.H != 256) || p.B % NB != 0) return cudaErrorInvalidValue;
+    // H = 256: the ping-pong form (two 16-row sub-tiles); BIGRU_X3_BWD=single selects the single-tile kernel
+    static const bool single = [] { const char* e = getenv("BIGRU_X3_BWD"); return e && e[0] == 's'; }();
+    const bool pp = p.H == 256 && !single;
     {
-        const uint32_t box[2] = {64u, (uint32_t)NB};
+        const uint32_t box[2] = {64u, (uint32_t)(pp ? NBS : NB)};
         const uint64_t d1[2] = {(uint64_t)p.D * 3 * p.H, (uint64_t)p.T * p.B};
         const uint64_t s1[1] = {(uint64_t)p.D * 3 * p.H * 2};
         const uint64_t d2[2] = {(uint64_t)p.D * p.H, (uint64_t)p.T * p.B};
@@ -1161,7 +1509,7 @@ static inline cudaError_t launch_bwd(const BwdParams& p_in, cudaStream_t st) {
     }
     const int CS = p.H / UNITS;
     const size_t smem = bwd_smem_bytes();
-    void (*kern)(BwdParams) = p.H == 128 ? gru_scanx_bwd_kernel<128> : gru_scanx_bwd_kernel<256>;
+    void (*kern)(BwdParams) = p.H == 128 ? gru_scanx_bwd_kernel<128> : (pp ? gru_scanx_bwd2_kernel<256> : gru_scanx_bwd_kernel<256>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
