@@ -192,6 +192,7 @@ SWEEP = [  # B, T, F, H, L, C, bidir, h0
     (3, 4, 5, 128, 2, 2, False, False),
     (32, 1, 16, 256, 1, 2, True, False),      # single time step / two time steps on the 4-CTA-cluster kernels (ping-pong forward)
     (64, 2, 16, 256, 2, 2, True, True),
+    (32, 300, 8, 256, 1, 2, True, False),     # many steps: barrier phase bookkeeping of the ping-pong scans far beyond the ring depths
     (32, 1, 16, 512, 1, 2, True, False),
     (64, 6, 24, 512, 2, 3, True, False),      # hidden 512 (bf16 path: 8-CTA clusters, tc_scan_w.cuh), two batch tiles
     (40, 3, 128, 512, 1, 2, False, False),
