@@ -78,7 +78,7 @@ class _Plan:
         _lib.check(lib.bigru_device_check(device.index if device.index is not None else torch.cuda.current_device()),
                    "bigru_device_check")
         h = _lib.C.c_void_p()
-        _lib.check(lib.bigru_plan_create(B, T, model.n_features, model.hidden_size, model.n_layers, model.output_size,
+        _lib.check(lib.bigru_plan_create(B, T, model.n_features, model.plan_hidden(B), model.n_layers, model.output_size,
                                          int(model.bidirectional), _PRECISIONS[model.resolved_precision(B)], _lib.C.byref(h)),
                    "bigru_plan_create")
         self.handle, self.B, self.T, self.device = h, B, T, device
@@ -137,18 +137,22 @@ class _BiGRUFunction(torch.autograd.Function):
 
     @staticmethod
     def _forward(ctx, lib, plan, model, x, h0, B):
+        Hp = model.plan_hidden(B)
+        pflat = model._plan_params()                     # zero-padded hidden units scattered in when Hp > hidden_size
+        h0 = model._pad_last(h0, Hp)
         logits = torch.empty(B, model.output_size, device=x.device, dtype=torch.float32)
-        hn = torch.empty(model.n_layers * model.n_directions, B, model.hidden_size, device=x.device, dtype=torch.float32)
+        hn = torch.empty(model.n_layers * model.n_directions, B, Hp, device=x.device, dtype=torch.float32)
         need_grad = any(ctx.needs_input_grad)        # grad mode is off inside Function.forward; ask the ctx
         stash = plan.acquire_stash()
         training = bool(model.training and model.dropout_p > 0)
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
         model._last_seed = seed                       # the dropout masks are a pure function of (seed, element index)
-        _lib.check(lib.bigru_forward(plan.handle, _lib.ptr(model._flat), _lib.ptr(x), _lib.ptr(h0),
+        _lib.check(lib.bigru_forward(plan.handle, _lib.ptr(pflat), _lib.ptr(x), _lib.ptr(h0),
                                      float(model.dropout_p), int(bool(model.spatial_dropout)), int(training), seed,
                                      _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(logits), _lib.ptr(hn),
                                      _stream_ptr(x.device)), "bigru_forward")
-        model._last_hidden = hn
+        model._last_hidden = hn if Hp == model.hidden_size else hn[..., :model.hidden_size]
+        ctx.pflat = pflat if need_grad else None
         model._last_plan_stash = (plan, stash)
         if need_grad:
             ctx.model, ctx.plan, ctx.stash, ctx.seed, ctx.training = model, plan, stash, seed, training
@@ -170,11 +174,11 @@ class _BiGRUFunction(torch.autograd.Function):
             dl = dlogits.new_zeros(Bp, dlogits.shape[1])
             dl[:B] = dlogits
             dlogits = dl
-        grads = torch.empty_like(model._flat)
+        grads = torch.empty_like(ctx.pflat)
         dx = torch.empty_like(x) if ctx.needs_input_grad[1] else None
         dh0 = torch.empty_like(h0) if (h0 is not None and ctx.needs_input_grad[2]) else None
         with torch.cuda.device(x.device):
-            _lib.check(lib.bigru_backward(plan.handle, _lib.ptr(model._flat), _lib.ptr(x), _lib.ptr(h0),
+            _lib.check(lib.bigru_backward(plan.handle, _lib.ptr(ctx.pflat), _lib.ptr(x), _lib.ptr(h0),
                                           float(model.dropout_p), int(bool(model.spatial_dropout)), int(ctx.training),
                                           ctx.seed, _lib.ptr(ctx.stash), _lib.ptr(plan.scratch), _lib.ptr(dlogits),
                                           _lib.ptr(grads), _lib.ptr(dx), _lib.ptr(dh0), _stream_ptr(x.device)), "bigru_backward")
@@ -183,6 +187,10 @@ class _BiGRUFunction(torch.autograd.Function):
         if Bp != B:
             dx = dx[:B] if dx is not None else None
             dh0 = dh0[:, :B] if dh0 is not None else None
+        grads = model._plan_grads(grads)                  # drop the padded hidden units' entries
+        if dh0 is not None and dh0.shape[-1] != model.hidden_size:
+            dh0 = dh0[..., :model.hidden_size]
+        ctx.pflat = None
         pg = tuple(grads[o:o + n].view(shape) for (o, n, shape) in model._views)
         return (None, dx, dh0) + pg
 
@@ -198,7 +206,7 @@ class BiGRU(nn.Module):
                 gradients): meets the reference's 1e-4 logits tolerance; H in {128, 256} (other batch sizes than whole 32-row tiles
                 run zero-padded, any feature count),
       "bf16"    single bf16 operands on tcgen05, fp32 accumulation and state (fastest, ~3e-3 on logits); H in {128, 256, 512},
-      "auto"    "bf16x3" for every batch shape it takes, "fp32" otherwise (decided per batch shape).
+      "auto"    "bf16x3" for hidden sizes up to 256 (smaller models run zero-padded to 128 / 256 hidden units), "fp32" beyond.
     Default: $BIGRU_B200_PRECISION or "fp32".
     """
 
@@ -303,18 +311,89 @@ class BiGRU(nn.Module):
 
     # ------------------------------------------------------------------ plans
     def resolved_precision(self, batch: int = 0) -> str:
-        """The precision a batch runs at ("auto": the fp32-class tensor-core path wherever it applies)."""
+        """The precision a batch runs at ("auto": the fp32-class tensor-core path wherever it applies, i.e. hidden_size <= 256)."""
         if self.precision != "auto":
             return self.precision
-        ok = self.hidden_size in (128, 256)
-        return "bf16x3" if ok else "fp32"
+        return "bf16x3" if self.hidden_size <= 256 else "fp32"
+
+    def plan_hidden(self, batch: int = 0) -> int:
+        """Hidden size of the C plan.  The tensor-core kernels exist for 128 / 256 (/ 512 at "bf16") hidden units; smaller models run
+        ZERO-PADDED to the next of these: a padded unit has zero weights and biases, so r = z = 1/2, n = 0 and its state stays 0
+        from h0 = 0 on; it feeds zero columns of W_hh / W_ih / the head.  Logits, loss and the gradients of the real parameters are
+        exactly those of the unpadded model (up to summation order); the padded gradient entries are dropped."""
+        prec, H = self.resolved_precision(batch), self.hidden_size
+        sizes = {"bf16x3": (128, 256), "bf16": (128, 256, 512)}.get(prec, ())
+        for hp in sizes:
+            if H <= hp:
+                return hp
+        return H
+
+    def _pad_map(self, dev):
+        """(index tensor, padded parameter count): position of every real parameter inside the padded plan's flat vector."""
+        Hp, H = self.plan_hidden(), self.hidden_size
+        if Hp == H:
+            return None
+        key = (Hp, dev.index)
+        hit = getattr(self, "_pad_cache", None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        D, L, F, C = self.n_directions, self.n_layers, self.n_features, self.output_size
+        idx, off_p = [], 0
+
+        def rows(n_cols_small, n_cols_pad, col_map):
+            # a [3H][cols] block -> padded [3Hp][cols_pad]: row g*H + j -> g*Hp + j, column through col_map
+            r = (np.arange(3)[:, None] * Hp + np.arange(H)[None, :]).reshape(-1)
+            return (r[:, None] * n_cols_pad + col_map[None, :]).reshape(-1)
+
+        for l in range(L):
+            I, Ip = (F, F) if l == 0 else (D * H, D * Hp)
+            cm = np.arange(F) if l == 0 else (np.arange(D)[:, None] * Hp + np.arange(H)[None, :]).reshape(-1)
+            for d in range(D):
+                idx.append(off_p + rows(I, Ip, cm)); off_p += 3 * Hp * Ip                     # W_ih
+                idx.append(off_p + rows(H, Hp, np.arange(H))); off_p += 3 * Hp * Hp           # W_hh
+                b = (np.arange(3)[:, None] * Hp + np.arange(H)[None, :]).reshape(-1)
+                idx.append(off_p + b); off_p += 3 * Hp                                        # b_ih
+                idx.append(off_p + b); off_p += 3 * Hp                                        # b_hh
+        cmh = (np.arange(3)[:, None] * Hp + np.arange(H)[None, :]).reshape(-1)                # head: last | max | avg, H wide each
+        idx.append(off_p + (np.arange(C)[:, None] * 3 * Hp + cmh[None, :]).reshape(-1)); off_p += C * 3 * Hp
+        idx.append(off_p + np.arange(C)); off_p += C
+        index = torch.from_numpy(np.concatenate(idx).astype(np.int64)).to(dev)
+        assert index.numel() == self._flat.numel()
+        self._pad_cache = (key, (index, off_p))
+        return self._pad_cache[1]
+
+    def _plan_params(self, buf=None):
+        """The flat parameter vector as the C plan sees it (zero-padded hidden units scattered in when plan_hidden() > hidden_size)."""
+        pm = self._pad_map(self._flat.device)
+        if pm is None:
+            return self._flat
+        index, P = pm
+        if buf is None:
+            buf = torch.zeros(P, device=self._flat.device, dtype=torch.float32)
+        buf.index_copy_(0, index, self._flat.detach())
+        return buf
+
+    def _plan_grads(self, pgrad, out=None):
+        pm = self._pad_map(self._flat.device)
+        if pm is None:
+            return pgrad
+        return torch.index_select(pgrad, 0, pm[0], out=out) if out is not None else torch.index_select(pgrad, 0, pm[0])
+
+    @staticmethod
+    def _pad_last(t, Hp):
+        """[.., .., H] -> [.., .., Hp] with zeros (initial hidden states)."""
+        if t is None or t.shape[-1] == Hp:
+            return t
+        out = t.new_zeros(tuple(t.shape[:-1]) + (Hp,))
+        out[..., :t.shape[-1]] = t
+        return out
 
     def _padded_batch(self, batch: int) -> int:
         """The tensor-core paths work on whole batch tiles (32 rows at bf16x3, 16 at bf16): other batch sizes run zero-padded
         to the next multiple.  Batch rows are independent and the padded rows receive a zero upstream gradient, so logits,
         loss and every gradient of the real rows are unchanged."""
         prec = self.resolved_precision(batch)
-        mult = 32 if (prec == "bf16x3" or (prec == "bf16" and self.hidden_size == 512)) else (16 if prec == "bf16" else 1)
+        mult = 32 if (prec == "bf16x3" or (prec == "bf16" and self.plan_hidden(batch) == 512)) else (16 if prec == "bf16" else 1)
         return (batch + mult - 1) // mult * mult
 
     def _plan_for(self, x) -> _Plan:
@@ -349,8 +428,9 @@ class BiGRU(nn.Module):
         plan, stash = self._last_plan_stash
         off = _lib.C.c_size_t()
         _lib.check(_lib.load().bigru_stash_argmax_offset(plan.handle, _lib.C.byref(off)), "bigru_stash_argmax_offset")
-        n = plan.B * self.hidden_size * 4
-        return stash[off.value:off.value + n].view(torch.int32).view(plan.B, self.hidden_size)[:getattr(self, "_last_batch", plan.B)].clone()
+        Hp = self.plan_hidden(plan.B)
+        n = plan.B * Hp * 4
+        return stash[off.value:off.value + n].view(torch.int32).view(plan.B, Hp)[:getattr(self, "_last_batch", plan.B), :self.hidden_size].clone()
 
     # ------------------------------------------------------------------ reference surface
     def forward(self, input_seq, hidden=None):
@@ -438,6 +518,10 @@ class BiGRU(nn.Module):
                                "dstep": torch.zeros(1, device=dev, dtype=torch.int32),
                                "gext": gext, "grad": gext[:P], "loss": gext[P:P + 1],
                                "scal": torch.zeros(2, device=dev, dtype=torch.float32)}
+            pm = self._pad_map(dev)
+            if pm is not None:                                # zero-padded hidden units (plan_hidden): the plan's own parameter / gradient vectors
+                st["pflat"] = torch.zeros(pm[1], device=dev, dtype=torch.float32)
+                st["pgrad"] = torch.empty(pm[1], device=dev, dtype=torch.float32)
             self._import_optimizer_state(st)
             self._mirror_optimizer_state()
         return st
@@ -485,13 +569,18 @@ class BiGRU(nn.Module):
     def _launch_fwd_loss_bwd(self, lib, plan, x, h0, tgt, kind, wv, pwv, denom, logits, dlogits, stash, args, st, s):
         # the loss sees the REAL batch rows (tgt's); logits / dlogits may carry zero-padded rows behind them (whole batch tiles)
         B, C = tgt.shape[0], logits.shape[1]
-        _lib.check(lib.bigru_forward(plan.handle, _lib.ptr(self._flat), _lib.ptr(x), _lib.ptr(h0), *args,
+        padded = "pflat" in st
+        pflat = self._plan_params(st["pflat"]) if padded else self._flat
+        pgrad = st["pgrad"] if padded else st["grad"]
+        _lib.check(lib.bigru_forward(plan.handle, _lib.ptr(pflat), _lib.ptr(x), _lib.ptr(h0), *args,
                                      _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(logits), None, s), "bigru_forward")
         _lib.check(lib.bigru_loss(kind, _lib.ptr(logits), _lib.ptr(tgt), _lib.ptr(wv), _lib.ptr(pwv), B, C, denom,
                                   _lib.ptr(st["loss"]), _lib.ptr(dlogits), s), "bigru_loss")
-        _lib.check(lib.bigru_backward(plan.handle, _lib.ptr(self._flat), _lib.ptr(x), _lib.ptr(h0), *args,
-                                      _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(dlogits), _lib.ptr(st["grad"]),
+        _lib.check(lib.bigru_backward(plan.handle, _lib.ptr(pflat), _lib.ptr(x), _lib.ptr(h0), *args,
+                                      _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(dlogits), _lib.ptr(pgrad),
                                       None, None, s), "bigru_backward")
+        if padded:
+            self._plan_grads(pgrad, out=st["grad"])
 
     def _launch_update(self, lib, g, st, s):
         """clip_grad_norm_(clip) + Adam on the flat buffers; the step counter is incremented on the device."""
@@ -591,6 +680,7 @@ class BiGRU(nn.Module):
                     hp[:, :B] = h0
                     h0 = hp
                 return xp, h0
+            h0 = self._pad_last(h0, self.plan_hidden(B))
             self._last_batch = B
             if self.use_cuda_graph and not training and h0 is None and not torch.cuda.is_current_stream_capturing():
                 key = (B, int(x.shape[1]), self.precision, kind, id(wv), id(pwv), denom, float(g["lr"]), tuple(g["betas"]),
@@ -648,7 +738,7 @@ class BiGRU(nn.Module):
             self._flatten()
         lib = _lib.load()
         self._window_args(dataset, start, count)
-        if self._padded_batch(count) != count:                # not whole batch tiles: collate on the device, then the padded path
+        if self._padded_batch(count) != count or self.plan_hidden(count) != self.hidden_size:      # padded shapes: collate on the device first
             self._win_ctx = None
             return self.forward(dataset.collate(start, count)[0])
         plan = self._plan_for(torch.empty(count, dataset.window, 0, device=self._flat.device))     # keyed by (B, T)
@@ -672,7 +762,7 @@ class BiGRU(nn.Module):
             raise RuntimeError("train_step_windows needs a fusable loss and torch.optim.Adam (see train_step)")
         lib = _lib.load()
         kind, w, pw = spec
-        if self._padded_batch(count) != count:                # not whole batch tiles: collate on the device, then train_step
+        if self._padded_batch(count) != count or self.plan_hidden(count) != self.hidden_size:      # padded shapes: collate, then train_step
             self._window_args(dataset, start, count)
             x, y = dataset.collate(start, count)
             tgt = y.reshape(count, -1)[:, 0].to(torch.int64) if kind == _lib.LOSS_CE else y.reshape(count, self.output_size)

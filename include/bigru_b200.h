@@ -47,7 +47,9 @@ extern "C" {
                                       Both tensor-core paths take any n_features (the layer-0 operands are stored with the
                                       feature extent zero-padded to a multiple of 8 inside the plan's workspaces).  Other
                                       batch sizes: append zero rows to x (and zero rows to d_logits) up to the next multiple -
-                                      batch rows are independent; the Python mirror does exactly that.  Anything else returns
+                                      batch rows are independent; the Python mirror does exactly that.  Smaller hidden sizes:
+                                      zero-pad the parameters to the next supported hidden size (padded units stay at state 0 and
+                                      feed zero weights; BiGRU.plan_hidden / _pad_map of the mirror).  Anything else returns
                                       BIGRU_ERR_UNSUPPORTED. */
 
 #define BIGRU_LOSS_CE   0          /* torch.nn.CrossEntropyLoss (BASELINE.json configs) */

@@ -47,13 +47,14 @@ def precisions():
 
 
 def supported(precision, B, F, H, h0=False):
-    """Through the Python mirror the tensor-core paths take any batch size (zero-padded to whole batch tiles) and any feature
-    count (layer-0 K extent padded to 8 inside the plan) for H in {128, 256}; BIGRU_PREC_BF16 has no initial hidden state."""
+    """Through the Python mirror the tensor-core paths take any batch size (zero-padded to whole batch tiles), any feature count
+    (layer-0 K extent padded to 8 inside the plan) and any hidden size up to 256 (bf16x3) / 512 (bf16) - smaller models run
+    zero-padded to 128 / 256 / 512 hidden units; BIGRU_PREC_BF16 has no initial hidden state."""
     if precision == "fp32":
         return True
     if precision == "bf16x3":
-        return H in (128, 256)
-    return H in (128, 256, 512) and not h0          # H = 512: the 8-CTA-cluster kernels of tc_scan_w.cuh
+        return H <= 256
+    return H <= 512 and not h0
 
 
 def rel(a, b):

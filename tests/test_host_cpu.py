@@ -85,14 +85,19 @@ def test_model_surface_and_state_dict(pkg, golden_dir):
     assert mine.can_fuse_step()
     mine.add_loss_fn(nn.CrossEntropyLoss(label_smoothing=0.1))
     assert not mine.can_fuse_step()
-    # precision="auto": the fp32-class tensor-core path for every batch shape it takes, the exact FFMA path otherwise
+    # precision="auto": the fp32-class tensor-core path for hidden sizes up to 256 (smaller models zero-padded to 128 / 256 hidden
+    # units, other batch sizes to whole 32-row tiles), the exact FFMA path beyond
     auto = pkg.BiGRU(256, 64, 3, 2, precision="auto")
     assert auto.resolved_precision(512) == "bf16x3" and auto.resolved_precision(500) == "bf16x3"
     assert auto._padded_batch(512) == 512 and auto._padded_batch(500) == 512 and auto._padded_batch(1) == 32
-    assert pkg.BiGRU(256, 64, 3, 2, precision="bf16")._padded_batch(500) == 512 - 0 and pkg.BiGRU(256, 64, 3, 2, precision="bf16")._padded_batch(17) == 32
+    assert pkg.BiGRU(256, 64, 3, 2, precision="bf16")._padded_batch(500) == 512 and pkg.BiGRU(256, 64, 3, 2, precision="bf16")._padded_batch(17) == 32
     assert pkg.BiGRU(256, 64, 3, 2, precision="fp32")._padded_batch(500) == 500
     assert pkg.BiGRU(256, 108, 3, 2, precision="auto").resolved_precision(512) == "bf16x3"     # any feature count (padded K extent)
-    assert pkg.BiGRU(8, 108, 4, 1, precision="auto").resolved_precision(64) == "fp32"
+    small = pkg.BiGRU(8, 108, 4, 1, precision="auto")                                          # the shipped checkpoint's shape
+    assert small.resolved_precision(64) == "bf16x3" and small.plan_hidden() == 128
+    assert pkg.BiGRU(200, 16, 3, 2, precision="auto").plan_hidden() == 256
+    assert pkg.BiGRU(300, 16, 3, 2, precision="auto").resolved_precision() == "fp32" and pkg.BiGRU(300, 16, 3, 2, precision="auto").plan_hidden() == 300
+    assert pkg.BiGRU(300, 16, 3, 2, precision="bf16").plan_hidden() == 512 and pkg.BiGRU(8, 4, 2, 1, precision="fp32").plan_hidden() == 8
     assert pkg.BiGRU(256, 64, 3, 2, precision="bf16").resolved_precision(7) == "bf16"
     with pytest.raises(ValueError):
         pkg.BiGRU(8, 4, 2, 1, precision="fp64")
