@@ -619,8 +619,11 @@ class BiGRU(nn.Module):
         self._launch_update(lib, g, st, s)
         torch.cuda.current_stream(dev).synchronize()
         n0 = lib.bigru_launch_count()
+        # an explicit capture stream ON THE MODEL'S DEVICE: torch's default capture stream is created once per process, on whichever
+        # device was current then
+        cap = torch.cuda.Stream(device=dev)
         ga = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(ga, capture_error_mode="thread_local"):
+        with torch.cuda.graph(ga, stream=cap, capture_error_mode="thread_local"):
             s = _stream_ptr(dev)
             self._launch_fwd_loss_bwd(lib, plan, ent["x"], None, ent["tgt"], kind, wv, pwv, denom, ent["logits"], ent["dlogits"], ent["stash"], args, st, s)
             if self._dp_world == 1:
@@ -628,7 +631,7 @@ class BiGRU(nn.Module):
         gb = None
         if self._dp_world > 1:
             gb = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gb, capture_error_mode="thread_local"):
+            with torch.cuda.graph(gb, stream=cap, capture_error_mode="thread_local"):
                 self._launch_update(lib, g, st, _stream_ptr(dev))
         self._bump_step(st, -1)                                   # the capture ran the host-side bookkeeping once without stepping
         ent["launches"] = int(lib.bigru_launch_count() - n0)

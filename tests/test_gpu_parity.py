@@ -583,6 +583,32 @@ def test_fused_adam_state_lives_in_the_optimizer():
     assert not mb.can_fuse_step()
 
 
+def test_model_on_a_device_that_is_not_current():
+    """A model on cuda:1 while cuda:0 is the current device: every C-ABI call must run on the model's device and stream (per-device
+    shared-memory opt-ins, device guards in the mirror); results equal the same model on cuda:0."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    pkg = _pkg()
+    B, T, F, H, L, C = 32, 6, 16, 128, 2, 3
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, T, F, generator=g)
+    y = torch.randint(0, C, (B,), generator=g)
+    torch.cuda.set_device(0)
+    for prec in precisions():
+        outs = []
+        for dev in (0, 1):
+            torch.manual_seed(4)
+            m = pkg.BiGRU(H, F, C, L, 50, 0.0, False, True, precision=prec).to(f"cuda:{dev}").train()
+            m.add_loss_fn(nn.CrossEntropyLoss()); m.add_optimizer(torch.optim.Adam(m.parameters(), lr=1e-3))
+            assert torch.cuda.current_device() == 0
+            for _ in range(3):
+                loss, logits = m.train_step(x.to(f"cuda:{dev}"), y.to(f"cuda:{dev}"))
+            outs.append((float(loss), logits.cpu(), m.flat_parameters().cpu()))
+        tol = 1e-6 if prec != "bf16" else 5e-3
+        assert abs(outs[0][0] - outs[1][0]) <= tol and float((outs[0][1] - outs[1][1]).abs().max()) <= tol * 10
+        assert float((outs[0][2] - outs[1][2]).abs().max()) <= tol * 10
+
+
 def test_long_sequence_config_reduced():
     """BASELINE config 4 (B256,T1024,F128,H512,L2) at reduced batch/length on the exact FFMA path (logits <= 1e-4 rel of the
     torch.nn.GRU CPU path); the bf16x3 path must refuse H = 512 loudly (its split weights do not fit tensor memory)."""
