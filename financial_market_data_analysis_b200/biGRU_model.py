@@ -749,11 +749,12 @@ class BiGRU(nn.Module):
         stash = plan.acquire_stash()
         training = bool(self.training and self.dropout_p > 0)
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
-        _lib.check(lib.bigru_forward_windows(plan.handle, _lib.ptr(self._flat), _lib.ptr(dataset.x_raw), _lib.ptr(dataset.x_min),
-                                             _lib.ptr(dataset.x_max), int(start), dataset.n_rows, float(self.dropout_p),
-                                             int(bool(self.spatial_dropout)), int(training), seed, _lib.ptr(stash),
-                                             _lib.ptr(plan.scratch), _lib.ptr(logits), None, _stream_ptr(self._flat.device)),
-                   "bigru_forward_windows")
+        with torch.cuda.device(self._flat.device):
+            _lib.check(lib.bigru_forward_windows(plan.handle, _lib.ptr(self._flat), _lib.ptr(dataset.x_raw), _lib.ptr(dataset.x_min),
+                                                 _lib.ptr(dataset.x_max), int(start), dataset.n_rows, float(self.dropout_p),
+                                                 int(bool(self.spatial_dropout)), int(training), seed, _lib.ptr(stash),
+                                                 _lib.ptr(plan.scratch), _lib.ptr(logits), None, _stream_ptr(self._flat.device)),
+                       "bigru_forward_windows")
         self._win_ctx = (plan, stash, training, seed)
         return logits
 
@@ -827,9 +828,10 @@ class BiGRU(nn.Module):
             raise ValueError("multilabel metrics need a [batch, n_classes] indicator target "
                              "(biGRU_model.py:213-221 feeds sigmoid(pred) > 0.5 to sklearn)")
         tgt = target.to(device=logits.device, dtype=torch.float32).contiguous()
-        _lib.check(_lib.load().bigru_multilabel_counts(_lib.ptr(logits), _lib.ptr(tgt), logits.shape[0],
-                                                       logits.shape[1], _lib.ptr(counts_row), _stream_ptr(logits.device)),
-                   "bigru_multilabel_counts")
+        with torch.cuda.device(logits.device):
+            _lib.check(_lib.load().bigru_multilabel_counts(_lib.ptr(logits), _lib.ptr(tgt), logits.shape[0],
+                                                           logits.shape[1], _lib.ptr(counts_row), _stream_ptr(logits.device)),
+                       "bigru_multilabel_counts")
 
     @staticmethod
     def _scores(counts: np.ndarray, sizes, C, beta=0.5):

@@ -141,8 +141,9 @@ class MySQLChunkLoader(Dataset):
         mn = torch.empty(F, device=table.device, dtype=torch.float32)
         mx = torch.empty(F, device=table.device, dtype=torch.float32)
         for ids in self.chunk_indices:
-            _lib.check(lib.bigru_chunk_minmax(_lib.ptr(table), db_length, F, ids[0] - 1, ids[-1], _lib.ptr(mn), _lib.ptr(mx),
-                                              torch.cuda.current_stream(table.device).cuda_stream), "bigru_chunk_minmax")
+            with torch.cuda.device(table.device):
+                _lib.check(lib.bigru_chunk_minmax(_lib.ptr(table), db_length, F, ids[0] - 1, ids[-1], _lib.ptr(mn), _lib.ptr(mx),
+                                                  torch.cuda.current_stream(table.device).cuda_stream), "bigru_chunk_minmax")
             x_min, x_max = mn.cpu().reshape(1, F).clone(), mx.cpu().reshape(1, F).clone()
             x_min[0], x_max[0] = widen_degenerate(x_min[0], x_max[0])
             self.norm_params.append((x_min, x_max))
@@ -229,19 +230,21 @@ class MySQLBatchLoader(Dataset):
 
     def _gather(self, start, count, width):
         out = torch.empty(count, width, self.n_features, device=self.device, dtype=torch.float32)
-        _lib.check(_lib.load().bigru_window_gather_norm(
-            _lib.ptr(self.x_raw), _lib.ptr(self.x_min), _lib.ptr(self.x_max), start, self.n_rows, count, width,
-            self.n_features, _lib.ptr(out), torch.cuda.current_stream(self.device).cuda_stream),
-            "bigru_window_gather_norm")
+        with torch.cuda.device(self.device):             # the C ABI launches on the current device: make it the chunk's
+            _lib.check(_lib.load().bigru_window_gather_norm(
+                _lib.ptr(self.x_raw), _lib.ptr(self.x_min), _lib.ptr(self.x_max), start, self.n_rows, count, width,
+                self.n_features, _lib.ptr(out), torch.cuda.current_stream(self.device).cuda_stream),
+                "bigru_window_gather_norm")
         return out
 
     def collate(self, start: int, count: int):
         """x[count, W, F] (normalised) and y[count, 1, C] for windows start .. start+count-1."""
         x = self._gather(start, count, self.window)
         y = torch.empty(count, 1, self.n_targets, device=self.device, dtype=torch.float32)
-        _lib.check(_lib.load().bigru_window_targets(
-            _lib.ptr(self.y), start, self.n_rows, count, self.window, self.n_targets, _lib.ptr(y),
-            torch.cuda.current_stream(self.device).cuda_stream), "bigru_window_targets")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().bigru_window_targets(
+                _lib.ptr(self.y), start, self.n_rows, count, self.window, self.n_targets, _lib.ptr(y),
+                torch.cuda.current_stream(self.device).cuda_stream), "bigru_window_targets")
         return x, y
 
     def batches(self, batch_size: int, drop_incomplete: bool = True):
