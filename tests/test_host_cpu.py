@@ -103,6 +103,45 @@ def test_model_surface_and_state_dict(pkg, golden_dir):
         pkg.BiGRU(8, 4, 2, 1, precision="fp64")
 
 
+def test_hidden_padding_index_map(pkg):
+    """BiGRU._pad_map (real parameter -> position in the zero-padded plan's flat vector) against an independent construction:
+    every weight tensor zero-padded by its own rule (gate rows g*H + j -> g*Hp + j, input columns of upper layers d*H + k ->
+    d*Hp + k, head columns part*H + j -> part*Hp + j) and flattened in the C-ABI order."""
+    import oracle_c
+    for H, F, L, bidir, C, prec in ((8, 108, 1, True, 4, "auto"), (33, 5, 3, True, 3, "bf16x3"), (7, 3, 2, False, 2, "bf16"),
+                                    (200, 16, 2, True, 3, "auto"), (300, 9, 2, True, 2, "bf16")):
+        torch.manual_seed(H)
+        m = pkg.BiGRU(H, F, C, L, 50, 0.0, False, bidir, precision=prec)
+        D, Hp = (2 if bidir else 1), m.plan_hidden()
+        assert Hp in (128, 256, 512) and Hp >= H
+        sd = {k: v.detach().numpy() for k, v in m.state_dict().items()}
+        padded = {}
+
+        def pad_rows(w, cols_out, colmap):
+            out = np.zeros((3 * Hp, cols_out), np.float32)
+            for g in range(3):
+                out[g * Hp:g * Hp + H][:, colmap] = w[g * H:(g + 1) * H]
+            return out
+        for l in range(L):
+            I = F if l == 0 else D * H
+            colmap = np.arange(F) if l == 0 else np.concatenate([d * Hp + np.arange(H) for d in range(D)])
+            for d in range(D):
+                sfx = f"l{l}" + ("_reverse" if d else "")
+                padded[f"gru.weight_ih_{sfx}"] = pad_rows(sd[f"gru.weight_ih_{sfx}"], F if l == 0 else D * Hp, colmap)
+                padded[f"gru.weight_hh_{sfx}"] = pad_rows(sd[f"gru.weight_hh_{sfx}"], Hp, np.arange(H))
+                for b in ("bias_ih", "bias_hh"):
+                    padded[f"gru.{b}_{sfx}"] = pad_rows(sd[f"gru.{b}_{sfx}"][:, None], 1, np.arange(1))[:, 0]
+        lw = np.zeros((C, 3 * Hp), np.float32)
+        for part in range(3):
+            lw[:, part * Hp:part * Hp + H] = sd["linear.weight"][:, part * H:(part + 1) * H]
+        padded["linear.weight"], padded["linear.bias"] = lw, sd["linear.bias"]
+        want = oracle_c.flatten_params(padded, L, D)
+        got = m._plan_params().numpy()
+        assert got.shape == want.shape and np.array_equal(got, want), (H, F, L, bidir)
+        back = m._plan_grads(torch.from_numpy(want)).numpy()                      # unpad = the original flat vector
+        assert np.array_equal(back, m.flat_parameters().detach().numpy())
+
+
 def test_chunk_loader_host_logic(pkg, golden_dir, tmp_path):
     """MySQLChunkLoader / TrainValTestSplit are host code: compare with the unmodified reference's output."""
     import pickle
