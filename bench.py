@@ -338,21 +338,26 @@ def main():
                         last_loss[0] = float(loss_host[k])
 
             run_e2e(warmup)
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            run_e2e(steps)
-            e1.record()
-            barrier()
-            ms_e = e0.elapsed_time(e1)
-            if world > 1:
-                ms_e = max_over_ranks(ms_e, dev)
+            reps = []
+            for _ in range(3):                  # a host hiccup (other tenants on the box's cores) shows in a 60 ms region: best of 3
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                run_e2e(steps)
+                e1.record()
+                barrier()
+                ms_r = e0.elapsed_time(e1)
+                if world > 1:
+                    ms_r = max_over_ranks(ms_r, dev)
+                reps.append(ms_r)
+            ms_e = min(reps)
             out["e2e"] = {"value": B * world / (ms_e / steps * 1e-3), "unit": "sequences/s",
                           "h2d_bytes_per_step": host[0][0].numel() * 4 + host[0][1].numel() * 8, "d2h_bytes_per_step": 4,
-                          "ms_per_step": ms_e / steps, "loss": last_loss[0],
+                          "ms_per_step": ms_e / steps, "loss": last_loss[0], "ms_per_step_repetitions": [r / steps for r in reps],
                           "how": "BiGRU.train_step on DevicePrefetcher batches: pinned host -> device copy of every step's inputs on a "
                                  "side stream ahead of their use, every step's loss read back through a pinned ring and consumed by the "
-                                 "host %d steps later (all reads complete inside the timed region)" % (LAG - 1)}
+                                 "host %d steps later (all reads complete inside the timed region); the region of `steps` steps is timed 3 times, the fastest is "
+                                 "reported (all three in ms_per_step_repetitions)" % (LAG - 1)}
 
         if with_roofline:
             psteps = 3
