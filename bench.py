@@ -351,7 +351,16 @@ def main():
                     ms_r = max_over_ranks(ms_r, dev)
                 reps.append(ms_r)
             ms_e = min(reps)
-            out["e2e"] = {"value": B * world / (ms_e / steps * 1e-3), "unit": "sequences/s",
+            # what the box's host -> device link gives right now (pinned, 128 MB): the full-batch arm needs
+            # h2d_bytes_per_step * steps/s of it; a contended PCIe link shows here, not in the kernels
+            probe_src = torch.empty(32 * 1024 * 1024, dtype=torch.float32).pin_memory()
+            probe_dst = torch.empty_like(probe_src, device=dev)
+            probe_dst.copy_(probe_src, non_blocking=True); torch.cuda.synchronize()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record(); probe_dst.copy_(probe_src, non_blocking=True); p1.record(); torch.cuda.synchronize()
+            h2d_gbps = probe_src.numel() * 4 / (p0.elapsed_time(p1) * 1e-3) / 1e9
+            del probe_src, probe_dst
+            out["e2e"] = {"value": B * world / (ms_e / steps * 1e-3), "unit": "sequences/s", "h2d_probe_gbps": h2d_gbps,
                           "h2d_bytes_per_step": host[0][0].numel() * 4 + host[0][1].numel() * 8, "d2h_bytes_per_step": 4,
                           "ms_per_step": ms_e / steps, "loss": last_loss[0], "ms_per_step_repetitions": [r / steps for r in reps],
                           "how": "BiGRU.train_step on DevicePrefetcher batches: pinned host -> device copy of every step's inputs on a "
@@ -434,21 +443,31 @@ def main():
         dss = [MySQLBatchLoader.from_tensors(cx.to(dev), cy.to(dev), (xmin, xmax), window=T) for cx, cy in chunks]
         side = torch.cuda.Stream(device=dev)
 
+        wl_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        wl_ev = [None] * 4
+
         def step_windows(i):
             ds, (cx, cy) = dss[i % 4], chunks[i % 4]
+            k = i % 4
+            if wl_ev[k] is not None:
+                wl_ev[k].synchronize()                         # the loss of 4 steps ago has reached the host
             with torch.cuda.stream(side):                      # this step's chunk: 164 KB host -> device
                 ds.x_raw.copy_(cx, non_blocking=True)
                 ds.y.copy_(cy, non_blocking=True)
             torch.cuda.current_stream(dev).wait_stream(side)
             loss, _ = model.train_step_windows(ds, 0, B)
+            wl_host[k:k + 1].copy_(loss, non_blocking=True)    # every step's loss is read back (pinned ring, consumed 4 steps later)
+            wl_ev[k] = torch.cuda.Event()
+            wl_ev[k].record()
             side.wait_stream(torch.cuda.current_stream(dev))
             return loss
 
         ms_w, _ = timed(step_windows, args.steps, args.warmup)
         e2e_windows = {"value": B * world / (ms_w / args.steps * 1e-3), "unit": "sequences/s", "ms_per_step": ms_w / args.steps,
-                       "h2d_bytes_per_step": n_rows * (F + 1) * 4, "d2h_bytes_per_step": 0,
-                       "how": "host chunk (B+T-1 rows x F, pinned) -> device copy inside the timed region -> BiGRU.train_step_windows: the "
-                              "windowed collation, min-max normalisation and the cast are fused into the first kernel (no x[B,T,F] anywhere)"}
+                       "h2d_bytes_per_step": n_rows * (F + 1) * 4, "d2h_bytes_per_step": 4,
+                       "how": "host chunk (B+T-1 rows x F + targets, pinned) -> device copy inside the timed region -> BiGRU.train_step_windows: the "
+                              "windowed collation, min-max normalisation and the cast are fused into the first kernel (no x[B,T,F] anywhere); "
+                              "every step's loss is read back to the host through a pinned ring"}
     except Exception as e:                                      # the extra arm must never break the bench line
         e2e_windows = {"error": str(e)[:200]}
 
