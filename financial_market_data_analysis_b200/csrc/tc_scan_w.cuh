@@ -700,11 +700,302 @@ __global__ void __launch_bounds__(THREADS, 1) gru_scanw_bwd_kernel(const __grid_
     if (warp == EPI_WARPS) tc::tmem_dealloc(tmem, 512);
 }
 
+// ping-pong form: a 16-row dgh sub-tile against one row block: 12 MMAs with N = 16
+__device__ __forceinline__ void bwd2_issue_block(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc) {
+    constexpr uint32_t idesc = tc::umma_idesc_bf16(128, tcx::NBS);
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+            tcs::umma_bf16_ts(tmem_d, tmem_a + (uint32_t)((g * 4 + kk) * 8), desc + (uint64_t)(g * (tcx::HS_CHUNK >> 4) + 2 * kk), idesc,
+                              (g == 0 && kk == 0) ? 0u : 1u);
+    }
+}
+
+template <int H>
+__global__ void __launch_bounds__(THREADS, 1) gru_scanw_bwd2_kernel(const __grid_constant__ BwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    using G = Geo<H>;
+    constexpr int CS = G::CS, NRB = G::NRB, RECV_BYTES = G::RECV_BYTES;
+    // Ping-pong form (see tcx::gru_scanx_bwd2_kernel): epilogue warps 0-3 only ever touch batch columns 0-15, warps 4-7 columns
+    // 16-31, so the two warp groups run as two decoupled 16-row sub-tiles (own dgh tiles with N = 16, accumulators, barriers).
+    constexpr int NBS = tcx::NBS, HS_CHUNK = tcx::HS_CHUNK;
+    constexpr int DT_BYTES = 3 * HS_CHUNK;                // one dgh sub-tile
+    constexpr int SUBD = 2 * DT_BYTES, SUBN = 2 * HS_CHUNK;
+    constexpr uint32_t A_COL = NRB * NB;                   // accumulators in columns [0, NRB*32): [sub][rb][16]; weights behind them
+    const int B = p.B, T = p.T;
+    uint8_t* sD = smem;                                    // [2 sub][2 buf][3 gates][HS_CHUNK]
+    uint8_t* sN = sD + (size_t)2 * SUBD;                   // [2 sub][2 buf][HS_CHUNK]   da_n (dgi n-gate rows, store only)
+    uint8_t* sR = sN + (size_t)2 * SUBN;                   // [2 buf][CS src][8 cg][64 j] float4 (column groups 0-3: sub-tile 0, 4-7: sub-tile 1)
+    uint8_t* sIn = sR + (size_t)2 * RECV_BYTES;            // [NSB][G | YB | dY]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + (size_t)NSB * BWD_STAGE);
+    uint64_t* recv_full = bars;        // [2 sub][2 buf]
+    uint64_t* mma_a = bars + 4;        // [2 sub] the row blocks owned by other CTA pairs are done
+    uint64_t* mma_b = bars + 6;        // [2 sub] all row blocks done
+    uint64_t* epi_done = bars + 8;     // [2 sub]
+    uint64_t* st_done = bars + 10;     // [2 sub]
+    uint64_t* in_full = bars + 12;     // [NSB]
+    uint64_t* in_empty = bars + 12 + NSB;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12 + 2 * NSB);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t c = tc::cluster_ctarank();
+    const int cluster_id = blockIdx.x / CS;
+    const int ntiles = B / NB;
+    const int d = cluster_id / ntiles, tile = cluster_id % ntiles;
+    const bool top = p.dlogits != nullptr;
+    const int rb_own = (int)c >> 1;                        // row block that contains this CTA's own units
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) tc::mbar_init(&recv_full[i], 1);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&mma_a[i], 1); tc::mbar_init(&mma_b[i], 1);
+            tc::mbar_init(&epi_done[i], EPI_WARPS / 2); tc::mbar_init(&st_done[i], EPI_WARPS / 2);
+        }
+        for (int i = 0; i < NSB; ++i) { tc::mbar_init(&in_full[i], 1); tc::mbar_init(&in_empty[i], EPI_WARPS); }
+        tc::fence_mbar_init();
+    }
+    if (warp == EPI_WARPS) tc::tmem_alloc(tmem_slot, 512);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    if (warp < EPI_WARPS)
+        tcs::load_weights_to_tmem(p.WTimg + ((size_t)d * CS + c) * 128 * (NRB * 192), NRB * 192, tmem, A_COL, warp, lane);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+
+    if (warp == EPI_WARPS + 1) {
+        if (tc::elect_one()) {
+            bool ok = true;
+            for (int s = 0; s < T; ++s) {
+                const int st = s % NSB;
+                if (s >= NSB && ok) ok = tc::mbar_wait(&in_empty[st], ((s / NSB) - 1) & 1, p.dbg, 0x4300 + (s & 0xff));
+                const int t = d == 0 ? T - 1 - s : s;
+                const bool first = d == 0 ? t == 0 : t == T - 1;
+                uint8_t* dst = sIn + (size_t)st * BWD_STAGE;
+                tc::mbar_arrive_expect_tx(&in_full[st], (uint32_t)(G_BLOCK + (top ? 0 : DY_BLOCK) + (first ? 0 : YB_BLOCK)));
+                const size_t blk = blk_index(d, tile, t, (int)c, ntiles, T, CS);
+                tc::bulk_g2s(dst, reinterpret_cast<const uint8_t*>(p.GW) + blk * G_BLOCK, G_BLOCK, &in_full[st]);
+                if (!top) tc::bulk_g2s(dst + G_BLOCK + YB_BLOCK, reinterpret_cast<const uint8_t*>(p.dYBW) + blk * DY_BLOCK, DY_BLOCK, &in_full[st]);
+                if (!first) {
+                    const size_t pblk = blk_index(d, tile, d == 0 ? t - 1 : t + 1, (int)c, ntiles, T, CS);
+                    tc::bulk_g2s(dst + G_BLOCK, reinterpret_cast<const uint8_t*>(p.YBW) + pblk * YB_BLOCK, YB_BLOCK, &in_full[st]);
+                }
+            }
+        }
+    } else if (warp == EPI_WARPS) {
+        if (tc::elect_one()) {
+            bool ok = true;
+            auto store_tile = [&](int sub, int step) {        // 16-row boxes (the tensor maps of this form have box 64 x 16)
+                const int tt = d == 0 ? T - 1 - step : step;
+                const int row = tt * B + tile * NB + sub * NBS;
+                const uint8_t* tb = sD + (size_t)sub * SUBD + (size_t)(step & 1) * DT_BYTES;
+                const uint8_t* nb = sN + (size_t)sub * SUBN + (size_t)(step & 1) * HS_CHUNK;
+                const int cu = (int)c * UNITS;
+                tc::tma_store_2d(&p.tmGI, tb, d * 3 * H + cu, row);                               // da_r
+                tc::tma_store_2d(&p.tmGI, tb + HS_CHUNK, d * 3 * H + H + cu, row);                // da_z
+                tc::tma_store_2d(&p.tmGI, nb, d * 3 * H + 2 * H + cu, row);                       // da_n
+                tc::tma_store_2d(&p.tmGN, tb + 2 * HS_CHUNK, d * H + cu, row);                    // da_n * r
+                tc::tma_store_commit();
+            };
+            const uint32_t db0 = tc::smem_u32(sD);
+            for (int s = 1; s < T; ++s) {
+                const int pb = (s - 1) & 1;
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                    if (ok) ok = tc::mbar_wait(&epi_done[sub], (s - 1) & 1, p.dbg, 0x4700 + (s & 0xff));
+                    tc::tcgen05_fence_after();
+                    tc::mbar_arrive_expect_tx(&recv_full[sub * 2 + (s & 1)], (uint32_t)(CS - 1) * 4096u);
+                    const uint64_t dd = tc::umma_desc_k_sw128(db0 + (uint32_t)sub * SUBD + (uint32_t)pb * DT_BYTES);
+                    const uint32_t td = tmem + (uint32_t)(sub * NRB * NBS);
+#pragma unroll
+                    for (int i = 1; i < NRB; ++i) {
+                        const int rb = (rb_own + i) % NRB;
+                        bwd2_issue_block(td + (uint32_t)(rb * NBS), tmem + A_COL + (uint32_t)(rb * 96), dd);
+                    }
+                    tc::umma_commit(&mma_a[sub]);
+                    bwd2_issue_block(td + (uint32_t)(rb_own * NBS), tmem + A_COL + (uint32_t)(rb_own * 96), dd);
+                    tcx::tma_store_wait_read1();       // the tile of THIS sub-tile stored two steps ago has been read
+                    tc::umma_commit(&mma_b[sub]);
+                    if (ok) ok = tc::mbar_wait(&st_done[sub], (s - 1) & 1, p.dbg, 0x4a00 + (s & 0xff));
+                    store_tile(sub, s - 1);
+                }
+            }
+            for (int sub = 0; sub < 2; ++sub) {
+                if (ok) ok = tc::mbar_wait(&epi_done[sub], (T - 1) & 1, p.dbg, 0x4700);
+                if (ok) ok = tc::mbar_wait(&st_done[sub], (T - 1) & 1, p.dbg, 0x4a00);
+                store_tile(sub, T - 1);
+            }
+            tc::tma_store_wait_all();
+        }
+    } else {
+        // ---- epilogue.  Owner role: unit j = (warp & 1)*32 + lane of this CTA, batch columns [8*(warp >> 1), +8).
+        //      Partial-sum role: TMEM lane quarter q = warp & 3 -> output unit k = 128*rb + 32q + lane, columns [16*half, +16).
+        const int q = warp & 3, half = warp >> 2;          // half == sub-tile of this warp (router AND owner roles)
+        const int sub = half;
+        const int j = (warp & 1) * 32 + lane;
+        const int unit = (int)c * UNITS + j;
+        const int c0 = 8 * (warp >> 1);
+        const int tid = threadIdx.x;
+        float dhz[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dhz[i] = 0.f;
+        float h_avg[8], h_max[8];
+        int h_arg[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { h_avg[i] = 0.f; h_max[i] = 0.f; h_arg[i] = -1; }
+        if (top) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int b = tile * NB + c0 + i;
+                float dl = 0.f, dm = 0.f, da = 0.f;
+                for (int cc = 0; cc < p.C; ++cc) {
+                    const float g = p.dlogits[(int64_t)b * p.C + cc];
+                    const float* w = p.lin_w + (int64_t)cc * 3 * H;
+                    dl = fmaf(g, w[unit], dl); dm = fmaf(g, w[H + unit], dm); da = fmaf(g, w[2 * H + unit], da);
+                }
+                dhz[i] = dl;
+                h_avg[i] = da / (float)T; h_max[i] = dm; h_arg[i] = p.arg[(int64_t)b * H + unit];
+            }
+        }
+        float sb_r = 0.f, sb_z = 0.f, sb_n = 0.f, sb_nr = 0.f;
+        uint32_t e_off[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e_off[i] = tc::sw128_offset(c0 - 16 * sub + i, j);      // row inside the 16-row sub-tile
+        // partial-sum destination inside a receive buffer: [src = c][cg = 4*half + i][jd] float4, jd = (q & 1)*32 + lane
+        const uint32_t r_off = (((uint32_t)c * 8 + 4 * half) * 64 + (uint32_t)((q & 1) * 32 + lane)) * 16;
+        const uint32_t sIn_u = tc::smem_u32(sIn), sR_u = tc::smem_u32(sR), sD_u = tc::smem_u32(sD), sN_u = tc::smem_u32(sN);
+        bool ok = true;
+        auto reduce_partials = [&](int s, float (&acc)[8]) {
+            const int buf = s & 1;
+            const uint32_t rb_local = sR_u + (uint32_t)buf * RECV_BYTES;
+            const uint32_t rbar_l = tc::smem_u32(&recv_full[sub * 2 + buf]);
+            auto route = [&](int rb) {
+                float v[16];
+                tmem_ld16f(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * NRB * NBS + rb * NBS), v);
+                tmem_ld_wait_pin(v);
+                const uint32_t dest = (uint32_t)(2 * rb + (q >> 1));
+                const uint32_t lp = rb_local + r_off;
+                if (dest == c) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) tc::sts_f4(lp + (uint32_t)(i * 64 * 16), make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+                } else {
+                    const uint32_t ra = tc::mapa_u32(lp, dest), rbr = tc::mapa_u32(rbar_l, dest);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 u;
+                        u.x = __float_as_uint(v[4 * i]); u.y = __float_as_uint(v[4 * i + 1]); u.z = __float_as_uint(v[4 * i + 2]); u.w = __float_as_uint(v[4 * i + 3]);
+                        tc::st_async_v4(ra + (uint32_t)(i * 64 * 16), u, rbr);
+                    }
+                }
+            };
+            if (ok) ok = tc::mbar_wait(&mma_a[sub], (s - 1) & 1, p.dbg, 0x4800 + (s & 0xff));
+            tc::tcgen05_fence_after();
+#pragma unroll
+            for (int i = 1; i < NRB; ++i) route((rb_own + i) % NRB);
+            if (ok) ok = tc::mbar_wait(&mma_b[sub], (s - 1) & 1, p.dbg, 0x4900 + (s & 0xff));
+            tc::tcgen05_fence_after();
+            route(rb_own);
+            tc::tcgen05_fence_before();
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + sub) : "memory");      // this warp group's own contributions are in the buffer
+            if (ok) ok = tc::mbar_wait_cluster(&recv_full[sub * 2 + buf], ((s - 1) >> 1) & 1, p.dbg, 0x4b00 + (s & 0xff));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int src = 0; src < CS; ++src) {
+                const uint32_t rp = rb_local + (uint32_t)((((src * 8 + 2 * (warp >> 1)) * 64) + j) * 16);
+                const float4 x0 = tc::lds_f4(rp), x1 = tc::lds_f4(rp + 64 * 16);
+                acc[0] += x0.x; acc[1] += x0.y; acc[2] += x0.z; acc[3] += x0.w; acc[4] += x1.x; acc[5] += x1.y; acc[6] += x1.z; acc[7] += x1.w;
+            }
+        };
+        for (int s = 0; s < T; ++s) {
+            const int t = d == 0 ? T - 1 - s : s;
+            const bool first = d == 0 ? t == 0 : t == T - 1;
+            float vr[8], vz[8], vn[8], vhn[8], vhp[8], vdy[8];
+            {
+                const int st = s % NSB;
+                if (ok) ok = tc::mbar_wait(&in_full[st], (s / NSB) & 1, p.dbg, 0x4200 + (s & 0xff));
+                const uint32_t gp = sIn_u + (uint32_t)st * BWD_STAGE + 16u * tid;
+                const uint4 u0 = tc::lds_u4(gp), u1 = tc::lds_u4(gp + 4096), u2 = tc::lds_u4(gp + 8192), u3 = tc::lds_u4(gp + 12288);
+                uint4 uh = make_uint4(0u, 0u, 0u, 0u);
+                float4 y0 = make_float4(0.f, 0.f, 0.f, 0.f), y1 = y0;
+                if (!first) uh = tc::lds_u4(gp + G_BLOCK);
+                if (!top) { y0 = tc::lds_f4(sIn_u + (uint32_t)st * BWD_STAGE + G_BLOCK + YB_BLOCK + 32u * tid); y1 = tc::lds_f4(sIn_u + (uint32_t)st * BWD_STAGE + G_BLOCK + YB_BLOCK + 32u * tid + 16); }
+                unpack8(u0, vr); unpack8(u1, vz); unpack8(u2, vn); unpack8(u3, vhn); unpack8(uh, vhp);
+                vdy[0] = y0.x; vdy[1] = y0.y; vdy[2] = y0.z; vdy[3] = y0.w; vdy[4] = y1.x; vdy[5] = y1.y; vdy[6] = y1.z; vdy[7] = y1.w;
+                if (top) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) vdy[i] = h_avg[i] + (h_arg[i] == t ? h_max[i] : 0.f);
+                }
+            }
+            float c_n[8], c_r[8], c_z[8], pre[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float r = vr[i], z = vz[i], n = vn[i];
+                c_n[i] = (1.f - z) * (1.f - n * n);
+                c_r[i] = vhn[i] * r * (1.f - r);
+                c_z[i] = (vhp[i] - n) * z * (1.f - z);
+                pre[i] = dhz[i] + vdy[i];
+            }
+            float acc[8];
+            const int buf = s & 1;
+            if (s > 0) reduce_partials(s, acc);
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+            }
+            const uint32_t tileb = sD_u + (uint32_t)sub * SUBD + (uint32_t)buf * DT_BYTES;
+            const uint32_t nbuf = sN_u + (uint32_t)sub * SUBN + (uint32_t)buf * HS_CHUNK;
+            float dar[8], daz[8], dan[8], danr[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float dh = acc[i] + pre[i];
+                dan[i] = dh * c_n[i];
+                dar[i] = dan[i] * c_r[i];
+                daz[i] = dh * c_z[i];
+                danr[i] = dan[i] * vr[i];
+                dhz[i] = dh * vz[i];
+                tc::sts_bf16(tileb + e_off[i], __float2bfloat16(dar[i]));
+                tc::sts_bf16(tileb + HS_CHUNK + e_off[i], __float2bfloat16(daz[i]));
+                tc::sts_bf16(tileb + 2 * HS_CHUNK + e_off[i], __float2bfloat16(danr[i]));
+            }
+            tc::tcgen05_fence_before();
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&epi_done[sub]);
+            // the ring slot is released only here: the published dgh depends on every value loaded from it (see tc_scan.cuh)
+            if (lane == 0) tc::mbar_arrive(&in_empty[s % NSB]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tc::sts_bf16(nbuf + e_off[i], __float2bfloat16(dan[i]));
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&st_done[sub]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { sb_r += dar[i]; sb_z += daz[i]; sb_n += dan[i]; sb_nr += danr[i]; }
+        }
+        float* dbi = p.db_ih + (int64_t)d * p.dir_stride;
+        float* dbh = p.db_hh + (int64_t)d * p.dir_stride;
+        atomicAdd(dbi + unit, sb_r); atomicAdd(dbi + H + unit, sb_z); atomicAdd(dbi + 2 * H + unit, sb_n);
+        atomicAdd(dbh + unit, sb_r); atomicAdd(dbh + H + unit, sb_z); atomicAdd(dbh + 2 * H + unit, sb_nr);
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();
+    if (warp == EPI_WARPS) tc::tmem_dealloc(tmem, 512);
+}
+
 static inline cudaError_t launch_bwd(const BwdParams& p_in, cudaStream_t st) {
     BwdParams p = p_in;
     if (p.H != 512 || p.B % NB != 0) return cudaErrorInvalidValue;
+    // the ping-pong form (two 16-row sub-tiles) is the default; BIGRU_W_BWD=single selects the single-tile kernel
+    static const bool single = [] { const char* e = getenv("BIGRU_W_BWD"); return e && e[0] == 's'; }();
+    const bool pp = !single;
     {
-        const uint32_t box[2] = {64u, (uint32_t)NB};
+        const uint32_t box[2] = {64u, (uint32_t)(pp ? tcx::NBS : NB)};
         const uint64_t d1[2] = {(uint64_t)p.D * 3 * p.H, (uint64_t)p.T * p.B};
         const uint64_t s1[1] = {(uint64_t)p.D * 3 * p.H * 2};
         const uint64_t d2[2] = {(uint64_t)p.D * p.H, (uint64_t)p.T * p.B};
@@ -714,7 +1005,7 @@ static inline cudaError_t launch_bwd(const BwdParams& p_in, cudaStream_t st) {
     }
     const int CS = p.H / UNITS;
     const size_t smem = bwd_smem_bytes(p.H);
-    void (*kern)(BwdParams) = gru_scanw_bwd_kernel<512>;
+    void (*kern)(BwdParams) = pp ? gru_scanw_bwd2_kernel<512> : gru_scanw_bwd_kernel<512>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
