@@ -566,21 +566,55 @@ class BiGRU(nn.Module):
                             "exp_avg_sq": st["v"][off:off + n].view(shape)}
         st["mirror_steps"] = [opt.state[p]["step"] for p in self._ordered_params()]
 
-    def _launch_fwd_loss_bwd(self, lib, plan, x, h0, tgt, kind, wv, pwv, denom, logits, dlogits, stash, args, st, s):
+    def _launch_fwd_loss_bwd(self, lib, plan, x, h0, tgt, kind, wv, pwv, denom, logits, dlogits, stash, args, st, s, part="all"):
+        """part = "all": forward, loss, backward.  Data parallelism splits the backward so that the all-reduce of the upper layers'
+        gradients overlaps the lowest layer's backward: "upper" = forward + loss + layers L-1 .. 1 (+ head), "lower" = layer 0."""
         # the loss sees the REAL batch rows (tgt's); logits / dlogits may carry zero-padded rows behind them (whole batch tiles)
         B, C = tgt.shape[0], logits.shape[1]
         padded = "pflat" in st
-        pflat = self._plan_params(st["pflat"]) if padded else self._flat
+        pflat = (self._plan_params(st["pflat"]) if part != "lower" else st["pflat"]) if padded else self._flat
         pgrad = st["pgrad"] if padded else st["grad"]
-        _lib.check(lib.bigru_forward(plan.handle, _lib.ptr(pflat), _lib.ptr(x), _lib.ptr(h0), *args,
-                                     _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(logits), None, s), "bigru_forward")
-        _lib.check(lib.bigru_loss(kind, _lib.ptr(logits), _lib.ptr(tgt), _lib.ptr(wv), _lib.ptr(pwv), B, C, denom,
-                                  _lib.ptr(st["loss"]), _lib.ptr(dlogits), s), "bigru_loss")
-        _lib.check(lib.bigru_backward(plan.handle, _lib.ptr(pflat), _lib.ptr(x), _lib.ptr(h0), *args,
-                                      _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(dlogits), _lib.ptr(pgrad),
-                                      None, None, s), "bigru_backward")
-        if padded:
+        if part != "lower":
+            _lib.check(lib.bigru_forward(plan.handle, _lib.ptr(pflat), _lib.ptr(x), _lib.ptr(h0), *args,
+                                         _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(logits), None, s), "bigru_forward")
+            _lib.check(lib.bigru_loss(kind, _lib.ptr(logits), _lib.ptr(tgt), _lib.ptr(wv), _lib.ptr(pwv), B, C, denom,
+                                      _lib.ptr(st["loss"]), _lib.ptr(dlogits), s), "bigru_loss")
+        if part == "all":
+            _lib.check(lib.bigru_backward(plan.handle, _lib.ptr(pflat), _lib.ptr(x), _lib.ptr(h0), *args,
+                                          _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(dlogits), _lib.ptr(pgrad),
+                                          None, None, s), "bigru_backward")
+        else:
+            lo_hi = (self.n_layers - 1, 1) if part == "upper" else (0, 0)
+            _lib.check(lib.bigru_backward_layers(plan.handle, _lib.ptr(pflat), _lib.ptr(x), _lib.ptr(h0), *args,
+                                                 _lib.ptr(stash), _lib.ptr(plan.scratch), _lib.ptr(dlogits), _lib.ptr(pgrad),
+                                                 None, None, lo_hi[0], lo_hi[1], s), "bigru_backward_layers")
+        if padded and part != "upper":
             self._plan_grads(pgrad, out=st["grad"])
+
+    def _dp_split(self, st) -> int:
+        """Offset (in the flat gradient) where the upper layers' parameters start, or 0 when the data-parallel step is not split:
+        needs more than one layer, a tensor-core plan (bigru_backward_layers) and no hidden-size padding (the padded plan's
+        gradients are gathered only after the whole backward)."""
+        if self._dp_world <= 1 or self.n_layers < 2 or "pflat" in st or self.resolved_precision() == "fp32":
+            return 0
+        if os.environ.get("BIGRU_B200_DP_OVERLAP", "0") != "1":      # opt-in: measured no faster (two collectives cost more than the overlap wins)
+            return 0
+        per_dir0 = 3 * self.hidden_size * (self.n_features + self.hidden_size + 2)
+        return self.n_directions * per_dir0
+
+    def _dp_allreduce_overlapped(self, st, split, dev, lower):
+        """All-reduce of [split, P] + loss on a side stream (issued after the upper layers' backward), `lower()` = the lowest
+        layer's backward on the main stream meanwhile, then the all-reduce of [0, split) and the join."""
+        main = torch.cuda.current_stream(dev)
+        side = st.get("side")
+        if side is None:
+            side = st["side"] = torch.cuda.Stream(device=dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            allreduce_flat_(st["gext"][split:], self._dp_group)          # upper layers + head + the loss (last element)
+        lower()
+        allreduce_flat_(st["gext"][:split], self._dp_group)
+        main.wait_stream(side)
 
     def _launch_update(self, lib, g, st, s):
         """clip_grad_norm_(clip) + Adam on the flat buffers; the step counter is incremented on the device."""
@@ -613,9 +647,16 @@ class BiGRU(nn.Module):
         # one eager pass on the static buffers first (first-use work such as shared-memory opt-ins happens outside the capture);
         # its parameter update is real: it is the step the caller asked for
         s = _stream_ptr(dev)
-        self._launch_fwd_loss_bwd(lib, plan, ent["x"], None, ent["tgt"], kind, wv, pwv, denom, ent["logits"], ent["dlogits"], ent["stash"], args, st, s)
-        if self._dp_world > 1:
-            allreduce_flat_(st["gext"], self._dp_group)
+        split = self._dp_split(st)
+        fwd_bwd = lambda part, s_: self._launch_fwd_loss_bwd(lib, plan, ent["x"], None, ent["tgt"], kind, wv, pwv, denom, ent["logits"],
+                                                             ent["dlogits"], ent["stash"], args, st, s_, part)
+        if split:
+            fwd_bwd("upper", s)
+            self._dp_allreduce_overlapped(st, split, dev, lambda: fwd_bwd("lower", s))
+        else:
+            fwd_bwd("all", s)
+            if self._dp_world > 1:
+                allreduce_flat_(st["gext"], self._dp_group)
         self._launch_update(lib, g, st, s)
         torch.cuda.current_stream(dev).synchronize()
         n0 = lib.bigru_launch_count()
@@ -625,9 +666,14 @@ class BiGRU(nn.Module):
         ga = torch.cuda.CUDAGraph()
         with torch.cuda.graph(ga, stream=cap, capture_error_mode="thread_local"):
             s = _stream_ptr(dev)
-            self._launch_fwd_loss_bwd(lib, plan, ent["x"], None, ent["tgt"], kind, wv, pwv, denom, ent["logits"], ent["dlogits"], ent["stash"], args, st, s)
+            fwd_bwd("upper" if split else "all", s)
             if self._dp_world == 1:
                 self._launch_update(lib, g, st, s)
+        ga2 = None
+        if split:                                         # the lowest layer's backward: replayed while the upper layers' gradients are reduced
+            ga2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga2, stream=cap, capture_error_mode="thread_local"):
+                fwd_bwd("lower", _stream_ptr(dev))
         gb = None
         if self._dp_world > 1:
             gb = torch.cuda.CUDAGraph()
@@ -636,7 +682,7 @@ class BiGRU(nn.Module):
         self._bump_step(st, -1)                                   # the capture ran the host-side bookkeeping once without stepping
         ent["launches"] = int(lib.bigru_launch_count() - n0)
         lib.bigru_launch_count_add(-ent["launches"])      # captured, not executed
-        ent["ga"], ent["gb"], ent["fresh"] = ga, gb, True
+        ent["ga"], ent["ga2"], ent["gb"], ent["fresh"], ent["split"] = ga, ga2, gb, True, split
         if len(self._graphs) > 4:
             self._graphs.clear()
         self._graphs[key] = ent
@@ -704,7 +750,10 @@ class BiGRU(nn.Module):
                     ent["tgt"].copy_(tgt, non_blocking=True)
                     ent["ga"].replay()
                     if ent["gb"] is not None:
-                        allreduce_flat_(st["gext"], self._dp_group)
+                        if ent["ga2"] is not None:
+                            self._dp_allreduce_overlapped(st, ent["split"], dev, ent["ga2"].replay)
+                        else:
+                            allreduce_flat_(st["gext"], self._dp_group)
                         ent["gb"].replay()
                     self._bump_step(st, 1)
                     lib.bigru_launch_count_add(ent["launches"])
@@ -718,10 +767,16 @@ class BiGRU(nn.Module):
             self._last_seed = seed
             s = _stream_ptr(dev)
             args = (float(self.dropout_p), int(bool(self.spatial_dropout)), int(training), seed)
-            self._launch_fwd_loss_bwd(lib, plan, x, h0, tgt, kind, wv, pwv, denom, logits, dlogits, stash, args, st, s)
+            split = self._dp_split(st)
+            if split:                                                # upper layers' gradients are reduced while layer 0 runs its backward
+                self._launch_fwd_loss_bwd(lib, plan, x, h0, tgt, kind, wv, pwv, denom, logits, dlogits, stash, args, st, s, "upper")
+                self._dp_allreduce_overlapped(st, split, dev, lambda: self._launch_fwd_loss_bwd(
+                    lib, plan, x, h0, tgt, kind, wv, pwv, denom, logits, dlogits, stash, args, st, s, "lower"))
+            else:
+                self._launch_fwd_loss_bwd(lib, plan, x, h0, tgt, kind, wv, pwv, denom, logits, dlogits, stash, args, st, s)
+                if self._dp_world > 1:
+                    allreduce_flat_(st["gext"], self._dp_group)      # ONE all-reduce: shard gradients of the global-mean loss + the loss
             plan.release_stash(stash)
-            if self._dp_world > 1:
-                allreduce_flat_(st["gext"], self._dp_group)          # ONE all-reduce: shard gradients of the global-mean loss + the loss
             self._launch_update(lib, g, st, s)
             return st["loss"].clone(), (logits[:B] if Bp != B else logits)
 

@@ -343,6 +343,29 @@ extern "C" int bigru_backward(const bigru_plan* plan, const float* d_params, con
                         (float*)d_scratch, d_dlogits, d_grads, d_dx, d_dh0, st);
 }
 
+extern "C" int bigru_backward_layers(const bigru_plan* plan, const float* d_params, const float* d_x, const float* d_h0,
+                                     float dropout_p, int spatial, int training, uint64_t seed, const void* d_stash,
+                                     void* d_scratch, const float* d_dlogits, float* d_grads, float* d_dx, float* d_dh0,
+                                     int layer_from, int layer_to, void* stream) {
+    if (!plan || !d_params || !d_stash || !d_scratch || !d_dlogits || !d_grads) {
+        bigru_set_error("backward_layers: null argument");
+        return BIGRU_ERR_ARG;
+    }
+    if (layer_from >= plan->L || layer_to < 0 || layer_to > layer_from) {
+        bigru_set_error("backward_layers: bad layer range %d..%d for %d layers", layer_from, layer_to, plan->L);
+        return BIGRU_ERR_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plan->prec == BIGRU_PREC_BF16)
+        return backward_bf16(*plan, d_params, d_x, d_h0, dropout_p, spatial, training, seed, d_stash, d_scratch,
+                             d_dlogits, d_grads, d_dx, d_dh0, st, layer_from, layer_to);
+    if (plan->prec == BIGRU_PREC_BF16X3)
+        return backward_x3(*plan, d_params, d_x, d_h0, dropout_p, spatial, training, seed, d_stash, d_scratch,
+                           d_dlogits, d_grads, d_dx, d_dh0, st, layer_from, layer_to);
+    bigru_set_error("backward_layers: the fp32 path runs its layers in one call (bigru_backward)");
+    return BIGRU_ERR_UNSUPPORTED;
+}
+
 extern "C" int bigru_forward_windows(const bigru_plan* plan, const float* d_params, const float* d_src, const float* d_xmin,
                                      const float* d_xmax, int64_t start, int64_t N, float dropout_p, int spatial,
                                      int training, uint64_t seed, void* d_stash, void* d_scratch, float* d_logits,

@@ -568,7 +568,11 @@ static int forward_bf16(const bigru_plan& p, const float* params, const float* x
 // ---------------------------------------------------------------------------------------------------
 static int backward_bf16(const bigru_plan& p, const float* params, const float* x, const float* h0, float drop,
                          int spatial, int training, uint64_t seed, const void* stash_v, void* scratch_v,
-                         const float* dlogits, float* grads, float* dx, float* dh0, cudaStream_t st) {
+                         const float* dlogits, float* grads, float* dx, float* dh0, cudaStream_t st, int l_from = -1, int l_to = 0) {
+    // layers l_from .. l_to (downwards; l_from = -1: from the top layer).  A call that starts at the top layer also zeroes the gradient
+    // vector and forms the head's gradients; a later call for the lower layers continues from the dY the upper call left in scratch.
+    if (l_from < 0) l_from = p.L - 1;
+    const bool from_top = l_from == p.L - 1;
     if (h0 || dh0) { bigru_set_error("BIGRU_PREC_BF16: initial hidden state / its gradient are not supported"); return BIGRU_ERR_UNSUPPORTED; }
     const Bf16Layout L = bf16_layout(p);
     const bool wide = bf16_wide(p);
@@ -578,16 +582,17 @@ static int backward_bf16(const bigru_plan& p, const float* params, const float* 
     const int64_t R = (int64_t)B * T;
     const bool do_drop = training && drop > 0.f;
     unsigned int* dbg = (unsigned int*)(const_cast<uint8_t*>(S) + L.dbg);
-    CUDA_TRY(cudaMemsetAsync(grads, 0, sizeof(float) * p.nparams, st));
+    if (from_top) CUDA_TRY(cudaMemsetAsync(grads, 0, sizeof(float) * p.nparams, st));
     const float* cat = (const float*)(S + L.cat);
-    {
+    if (from_top) {
         const int bchunk = 16;
         KLAUNCH(KC_HEAD, 0.0, 0.0, st, head_bwd_w_kernel<<<dim3(nblk2(3 * H, 128), C, (B + bchunk - 1) / bchunk), 128, 0, st>>>(
                     dlogits, cat, grads + p.off_linw(), grads + p.off_linb(), B, 3 * H, C, bchunk));
     }
     float* dY = (float*)(W + L.dYa);
     float* dYnext = (float*)(W + L.dYb);
-    for (int l = p.L - 1; l >= 0; --l) {
+    if ((p.L - 1 - l_from) & 1) { float* t_ = dY; dY = dYnext; dYnext = t_; }      // the buffers alternate per layer
+    for (int l = l_from; l >= l_to; --l) {
         const int I = (int)p.in_size(l);
         // 1. BPTT scan
         if (wide) {

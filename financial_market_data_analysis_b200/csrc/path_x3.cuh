@@ -305,7 +305,11 @@ static int forward_x3(const bigru_plan& p, const float* params, const float* x, 
 // ---------------------------------------------------------------------------------------------------
 static int backward_x3(const bigru_plan& p, const float* params, const float* x, const float* h0, float drop,
                        int spatial, int training, uint64_t seed, const void* stash_v, void* scratch_v,
-                       const float* dlogits, float* grads, float* dx, float* dh0, cudaStream_t st) {
+                       const float* dlogits, float* grads, float* dx, float* dh0, cudaStream_t st, int l_from = -1, int l_to = 0) {
+    // layers l_from .. l_to (downwards; l_from = -1: from the top layer).  A call that starts at the top layer also zeroes the gradient
+    // vector and forms the head's gradients; a later call for the lower layers continues from the dY the upper call left in scratch.
+    if (l_from < 0) l_from = p.L - 1;
+    const bool from_top = l_from == p.L - 1;
     const X3Layout L = x3_layout(p);
     const uint8_t* S = (const uint8_t*)stash_v;
     uint8_t* W = (uint8_t*)scratch_v;
@@ -313,20 +317,21 @@ static int backward_x3(const bigru_plan& p, const float* params, const float* x,
     const int64_t R = (int64_t)B * T;
     const bool do_drop = training && drop > 0.f;
     unsigned int* dbg = (unsigned int*)(const_cast<uint8_t*>(S) + L.dbg);
-    CUDA_TRY(cudaMemsetAsync(grads, 0, sizeof(float) * p.nparams, st));
+    if (from_top) CUDA_TRY(cudaMemsetAsync(grads, 0, sizeof(float) * p.nparams, st));
     const float* cat = (const float*)(S + L.cat);
-    {
+    if (from_top) {
         const int bchunk = 16;
         KLAUNCH(KC_HEAD, 0.0, 0.0, st, head_bwd_w_kernel<<<dim3(nblk2(3 * H, 128), C, (B + bchunk - 1) / bchunk), 128, 0, st>>>(
                     dlogits, cat, grads + p.off_linw(), grads + p.off_linb(), B, 3 * H, C, bchunk));
     }
     float* dY = (float*)(W + L.dYa);
     float* dYnext = (float*)(W + L.dYb);
+    if ((p.L - 1 - l_from) & 1) { float* t_ = dY; dY = dYnext; dYnext = t_; }      // the buffers alternate per layer
     bf16_t* dgi_hi = (bf16_t*)(W + L.gi);
     bf16_t* dgi_lo = dgi_hi + (size_t)R * D * 3 * H;
     bf16_t* dghn_hi = (bf16_t*)(W + L.dghn_hi);
     bf16_t* dghn_lo = (bf16_t*)(W + L.dghn_lo);
-    for (int l = p.L - 1; l >= 0; --l) {
+    for (int l = l_from; l >= l_to; --l) {
         const int I = (int)p.in_size(l);
         tcx::BwdParams b{};
         b.B = B; b.T = T; b.H = H; b.D = D;

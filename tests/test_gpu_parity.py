@@ -709,22 +709,27 @@ def test_two_gpu_data_parallel_step_matches_single_gpu(tmp_path):
         dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
         g = torch.Generator().manual_seed(3)
         x = torch.randn(64, 12, 16, generator=g); t = torch.randint(0, 3, (64,), generator=g)
-        def run(dp):
+        def run(dp, prec, graph="1"):
+            os.environ["BIGRU_B200_CUDA_GRAPH"] = graph
             torch.manual_seed(0)
-            m = pkg.BiGRU(128, 16, 3, 2, 1, 0.0, False, True, precision="fp32").cuda()
+            m = pkg.BiGRU(128, 16, 3, 2, 1, 0.0, False, True, precision=prec).cuda()
             m.add_loss_fn(nn.CrossEntropyLoss()); m.add_optimizer(torch.optim.Adam(m.parameters(), lr=1e-2)); m.train()
             if dp:
                 m.enable_data_parallel()
                 xs, ts = shard_batch(x, rank, world), shard_batch(t, rank, world)
             else:
                 xs, ts = x, t
-            for _ in range(3):
+            for _ in range(4):
                 loss, _ = m.train_step(xs.cuda(), ts.cuda())
             return m.flat_parameters().clone(), float(loss)
-        pd, ld = run(True); ps, ls = run(False)
-        err = float((pd - ps).norm() / ps.norm())
-        if rank == 0: print("DPERR", err, ld, ls)
-        assert err < 1e-5 and abs(ld - ls) < 1e-5
+        # fp32: the exact path; bf16x3: the tensor-core path, with and without the split backward whose upper-layer all-reduce
+        # overlaps layer 0 (BIGRU_B200_DP_OVERLAP=1), captured in CUDA graphs and with plain launches
+        for prec, overlap, graph, tol in (("fp32", "0", "1", 1e-5), ("bf16x3", "0", "1", 2e-3), ("bf16x3", "1", "1", 2e-3), ("bf16x3", "1", "0", 2e-3)):
+            os.environ["BIGRU_B200_DP_OVERLAP"] = overlap
+            pd, ld = run(True, prec, graph); ps, ls = run(False, prec, graph)
+            err = float((pd - ps).norm() / ps.norm())
+            if rank == 0: print("DPERR", prec, overlap, graph, err, ld, ls)
+            assert err < tol and abs(ld - ls) < tol, (prec, overlap, err, ld, ls)
         dist.destroy_process_group()
     '''))
     env = dict(os.environ, REPO=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
