@@ -207,7 +207,7 @@ class BiGRU(nn.Module):
                 run zero-padded, any feature count),
       "bf16"    single bf16 operands on tcgen05, fp32 accumulation and state (fastest, ~3e-3 on logits); H in {128, 256, 512},
       "auto"    "bf16x3" for hidden sizes up to 256 (smaller models run zero-padded to 128 / 256 hidden units), "fp32" beyond.
-    Default: $BIGRU_B200_PRECISION or "fp32".
+    Default: $BIGRU_B200_PRECISION or "auto" (the reference tolerance at tensor-core speed wherever the kernels apply).
     """
 
     def __init__(self, hidden_size, n_features, output_size, n_layers=1, clip=50, dropout=0.2,
@@ -222,7 +222,7 @@ class BiGRU(nn.Module):
         self.spatial_dropout = spatial_dropout
         self.bidirectional = bidirectional
         self.n_directions = 2 if bidirectional else 1
-        self.precision = precision or os.environ.get("BIGRU_B200_PRECISION", "fp32")
+        self.precision = precision or os.environ.get("BIGRU_B200_PRECISION", "auto")
         if self.precision != "auto" and self.precision not in _PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_PRECISIONS) + ['auto']}")
 
