@@ -21,6 +21,10 @@
 // its local dgh tile [32 x 192] (hi, then lo) and sends the fp32 partial sums of units it does not own to their owners
 // (st.async into a receive buffer); hi/lo row blocks of one k share a lane, so their sum is formed in registers.
 //
+// Kernels in this file: gru_scanx_fwd_kernel / gru_scanx_bwd_kernel (single 32-row tile per cluster: H = 128, and H = 256 on
+// request) and their PING-PONG forms gru_scanx_fwd2_kernel / gru_scanx_bwd2_kernel (H = 256, the default): the tile is worked as
+// two 16-row sub-tiles that alternate on the tensor pipe, the epilogue warps and the DSMEM network (see the comments there).
+//
 // Blocked ("scan-private") layouts (time-major, fp32): block (d, tile, t, cta) = (((d*ntiles + tile)*T + t)*CS + cta),
 // inside a block [gate][thread 0..255][8 batch columns]; thread tid = j + 64*(cb/8) <-> unit j = tid % 64 of the CTA,
 // batch columns [8*(tid/64), +8) of the 32-row tile.
