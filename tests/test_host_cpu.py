@@ -103,6 +103,25 @@ def test_model_surface_and_state_dict(pkg, golden_dir):
         pkg.BiGRU(8, 4, 2, 1, precision="fp64")
 
 
+def test_dp_split_offset_is_the_first_upper_layer_parameter(pkg, monkeypatch):
+    """BiGRU._dp_split (data-parallel overlap experiment): the flat-gradient offset where layer 1 starts equals the offset of
+    gru.weight_ih_l1 in the C-ABI parameter order; the split is off by default, for one layer, for fp32 and for padded hidden sizes."""
+    m = pkg.BiGRU(128, 24, 3, 2, precision="bf16x3")
+    m._dp_world = 2
+    names = [n for n, _ in m.named_parameters()]
+    off = {n: o for n, (o, _, _) in zip(names, m._views)}
+    assert m._dp_split({}) == 0                                         # opt-in only
+    monkeypatch.setenv("BIGRU_B200_DP_OVERLAP", "1")
+    assert m._dp_split({}) == off["gru.weight_ih_l1"] > 0
+    assert m._dp_split({"pflat": None}) == 0                            # hidden-size padding: gradients are gathered after the whole backward
+    one = pkg.BiGRU(128, 24, 3, 1, precision="bf16x3"); one._dp_world = 2
+    assert one._dp_split({}) == 0
+    f32 = pkg.BiGRU(128, 24, 3, 2, precision="fp32"); f32._dp_world = 2
+    assert f32._dp_split({}) == 0
+    m._dp_world = 1
+    assert m._dp_split({}) == 0
+
+
 def test_hidden_padding_index_map(pkg):
     """BiGRU._pad_map (real parameter -> position in the zero-padded plan's flat vector) against an independent construction:
     every weight tensor zero-padded by its own rule (gate rows g*H + j -> g*Hp + j, input columns of upper layers d*H + k ->
